@@ -1,0 +1,159 @@
+// common.cuh — context, error plumbing and small device helpers shared by all translation units
+// of libiife.so.  Hand-written CUDA for sm_100a; no torch types, no CPU fallback.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+#include "../../include/iife.h"
+
+namespace iife {
+
+struct Ctx {
+  bool init = false;
+  int device = -1;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr;      // stream all work is enqueued on
+  cudaStream_t own_stream = nullptr;  // created by iife_init
+  int64_t dev_bytes = 0;
+  int64_t launches = 0;
+  // NCCL (comm.cu)
+  void *nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+Ctx &ctx();
+
+int set_err(int code, const char *fmt, ...);
+const char *get_err();
+
+#define IIFE_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return ::iife::set_err(_e == cudaErrorMemoryAllocation ? IIFE_ERR_NOMEM : IIFE_ERR_CUDA, \
+                             "%s:%d: %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define IIFE_TRY(expr)        \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != IIFE_OK) return _rc; \
+  } while (0)
+
+#define IIFE_NEED_INIT()                                                                   \
+  do {                                                                                     \
+    if (!::iife::ctx().init)                                                               \
+      return ::iife::set_err(IIFE_ERR_NO_DEVICE, "iife_init() has not been called (no CUDA device bound)"); \
+  } while (0)
+
+// launch bookkeeping: every kernel launch of the library goes through this macro so that
+// iife_launch_count() is an honest count.
+#define IIFE_LAUNCH(kernel, grid, block, smem, ...)                          \
+  do {                                                                       \
+    kernel<<<(grid), (block), (smem), ::iife::ctx().stream>>>(__VA_ARGS__);  \
+    ::iife::ctx().launches++;                                                \
+  } while (0)
+
+#define IIFE_CHECK_LAUNCH() IIFE_CUDA(cudaGetLastError())
+
+// device allocation with accounting
+int dev_alloc(void **p, size_t bytes);
+int dev_free(void *p, size_t bytes);
+template <class T>
+inline int dev_alloc_t(T **p, size_t n) {
+  return dev_alloc((void **)p, (n ? n : 1) * sizeof(T));
+}
+template <class T>
+inline int dev_free_t(T *p, size_t n) {
+  return dev_free((void *)p, (n ? n : 1) * sizeof(T));
+}
+
+// RAII temporary device buffer (freed on scope exit; stream-ordered with cudaFreeAsync)
+template <class T>
+struct Tmp {
+  T *p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    n = count;
+    return dev_alloc_t(&p, n);
+  }
+  ~Tmp() {
+    if (p) dev_free_t(p, n);
+  }
+  Tmp() = default;
+  Tmp(const Tmp &) = delete;
+  Tmp &operator=(const Tmp &) = delete;
+};
+
+struct Mat {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  int *rowptr = nullptr;  // [n_rows+1]
+  int *colind = nullptr;  // [nnz]
+  double *val = nullptr;  // [nnz]
+  // cached explicit transpose (built on first use) and the gather permutation of its values
+  Mat *T = nullptr;
+  int *T_perm = nullptr;
+  bool T_vals_valid = false;
+  // cached inverse Jacobi diagonal (zero -> 1), invalidated when values change
+  double *dinv = nullptr;
+  bool dinv_valid = false;
+  uint64_t fp = 0;
+  bool fp_valid = false;
+  int max_row_len = -1;  // lazily computed
+};
+
+int mat_alloc(Mat **out, int64_t n_rows, int64_t n_cols, int64_t nnz);
+int mat_free(Mat *A);
+int mat_ensure_transpose(Mat *A);  // builds A->T (+values)
+int mat_ensure_dinv(Mat *A);       // Jacobi inverse diagonal with zero -> 1
+int mat_fingerprint(Mat *A, uint64_t *fp);
+int mat_max_row_len(Mat *A, int *out);
+
+// exclusive scan of int32 counts into int32 offsets (n+1 outputs: out[n] = total); total64 returned
+// on the host (synchronises the stream).
+int exclusive_scan_i32(const int *in, int *out, int64_t n, int64_t *total64);
+
+// SpMV launchers (spmv.cu)
+int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double *y);
+// w = A p and *dot_out = sum_i p_i w_i over the rows of A (partials + deterministic last-block
+// reduce); if flag != nullptr and *flag != 0 the kernel is a no-op.
+int spmv_dot_launch(const Mat *A, const double *p, double *w, double *dot_out, double *partials,
+                    unsigned int *counter, const int *flag);
+int spmv_pick_lpr(const Mat *A);
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over the lanes of a power-of-two sub-group of the warp (xor butterfly: all lanes get it)
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double *smem32) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem32[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    v = lane < nw ? smem32[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+#endif
+
+}  // namespace iife

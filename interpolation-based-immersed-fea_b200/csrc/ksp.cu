@@ -1,0 +1,769 @@
+// ksp.cu — device-resident Krylov solvers: Jacobi-preconditioned CG and FGMRES(m).
+//
+// Replaces the Krylov branch of the reference's solveKSP (common.py:554-574 + 628-636), i.e. PETSc's
+// KSPCG / KSPFGMRES + PCJACOBI as configured there, with PETSc's defaults restated in SURVEY.md A.5-A.8:
+//   CG      left preconditioning, preconditioned residual norm, test against max(rtol*||D^-1 b||, atol)
+//   FGMRES  right (flexible) preconditioning, true residual norm, classical Gram-Schmidt, no refinement,
+//           Givens-updated residual estimate, restart m, test against max(rtol*||b||, atol)
+//   Jacobi  z = r / diag(A), zero diagonal entries replaced by 1
+//
+// All scalars of the iteration (alpha, beta, norms, the Hessenberg matrix, Givens rotations, the
+// iteration counter and the converged reason) live in device memory and are produced by the *last
+// CTA to finish* of the kernel that reduces them, in a fixed order (bit-reproducible).  The host only
+// enqueues kernels — as a CUDA graph of a chunk of iterations for CG — and polls the reason flag once
+// per chunk; after convergence the remaining kernels of the chunk are no-ops.  There is no host
+// round trip per iteration.
+#include "common.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+namespace iife {
+
+// scalar slots
+enum {
+  S_BETA = 0, S_BETA_OLD, S_DELTA, S_DP, S_TTOL, S_RHO0, S_RTOL, S_ATOL, S_DTOL, S_SCALE, S_RES, S_TT,
+  S_COUNT = 16
+};
+// flag slots
+enum { F_REASON = 0, F_ITS, F_LOC_IT, F_MAXIT, F_HAPEND, F_COUNT = 8 };
+
+constexpr int VEC_THREADS = 256;
+constexpr int MAX_PARTIALS = 2048;
+
+struct KspWork {
+  double *sc = nullptr;         // [S_COUNT]
+  int *fl = nullptr;            // [F_COUNT]
+  double *partials = nullptr;   // [4 * MAX_PARTIALS] (+ multi-dot partials allocated separately)
+  unsigned int *counters = nullptr;  // [4]
+  double *hist = nullptr;       // device residual history [hist_len]
+  int64_t hist_len = 0;
+};
+
+__device__ __forceinline__ void log_hist(double *hist, long long hist_len, int its, double v) {
+  if (hist && its < hist_len) hist[its] = v;
+}
+
+// KSPConvergedDefault evaluated by one thread
+__device__ __forceinline__ void converged_default(double *sc, int *fl, int its, double rnorm) {
+  if (fl[F_REASON] != 0) return;
+  if (isnan(rnorm) || isinf(rnorm)) {
+    fl[F_REASON] = IIFE_KSP_DIVERGED_NANORINF;
+  } else if (rnorm <= sc[S_TTOL]) {
+    fl[F_REASON] = (rnorm < sc[S_ATOL]) ? IIFE_KSP_CONVERGED_ATOL : IIFE_KSP_CONVERGED_RTOL;
+  } else if (rnorm >= sc[S_DTOL] * sc[S_RHO0]) {
+    fl[F_REASON] = IIFE_KSP_DIVERGED_DTOL;
+  }
+}
+
+// ---- generic "last CTA reduces" epilogue: returns true in ALL threads of the last block, with the
+// NR reduced sums available in out[] (shared).  partials layout: [r * MAX_PARTIALS + block].
+template <int NR>
+__device__ __forceinline__ bool grid_reduce(double (&acc)[NR], double *partials, unsigned int *counter, double *out_sh,
+                                            double *red_sh, bool *last_sh) {
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    double b = block_sum(acc[r], red_sh);
+    if (threadIdx.x == 0) partials[r * MAX_PARTIALS + blockIdx.x] = b;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    *last_sh = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!*last_sh) return false;
+  __threadfence();
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    double s = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += __ldcg(partials + r * MAX_PARTIALS + k);
+    s = block_sum(s, red_sh);
+    if (threadIdx.x == 0) out_sh[r] = s;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+  __syncthreads();
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CG kernels
+// ------------------------------------------------------------------------------------------------
+// after r = b - A x0:  dp = ||D^-1 r||, beta = (D^-1 r, r), rho0 = ||D^-1 b||, test(0)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_init(const double *__restrict__ r, const double *__restrict__ b, const double *__restrict__ dinv, int64_t n,
+          double *sc, int *fl, double *partials, unsigned int *counter, double *hist, long long hist_len) {
+  __shared__ double red[32];
+  __shared__ double out[3];
+  __shared__ bool last;
+  double acc[3] = {0.0, 0.0, 0.0};
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double d = dinv ? dinv[i] : 1.0;
+    double ri = r[i], z = d * ri, zb = d * b[i];
+    acc[0] = fma(z, z, acc[0]);
+    acc[1] = fma(z, ri, acc[1]);
+    acc[2] = fma(zb, zb, acc[2]);
+  }
+  if (grid_reduce<3>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
+    double dp = sqrt(out[0]), beta = out[1], rho0 = sqrt(out[2]);
+    sc[S_DP] = dp;
+    sc[S_BETA] = beta;
+    sc[S_BETA_OLD] = beta;
+    sc[S_RHO0] = rho0;
+    sc[S_TTOL] = fmax(sc[S_RTOL] * rho0, sc[S_ATOL]);
+    fl[F_ITS] = 0;
+    log_hist(hist, hist_len, 0, dp);
+    converged_default(sc, fl, 0, dp);
+    if (fl[F_REASON] == 0) {
+      // checks PETSc makes at the top of iteration i (KSPSolve_CG): its is already i+1 there
+      if (beta == 0.0) { fl[F_REASON] = IIFE_KSP_CONVERGED_ATOL; fl[F_ITS] = 1; }
+      else if (beta < 0.0) { fl[F_REASON] = IIFE_KSP_DIVERGED_INDEFINITE_PC; fl[F_ITS] = 1; }
+      else if (isnan(beta) || isinf(beta)) { fl[F_REASON] = IIFE_KSP_DIVERGED_NANORINF; fl[F_ITS] = 1; }
+      else if (fl[F_MAXIT] <= 0) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
+    }
+  }
+}
+
+// p = z (first iteration) or p = z + (beta/beta_old) p, with z = D^-1 r recomputed (never stored)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_p(const double *__restrict__ r, const double *__restrict__ dinv, double *__restrict__ p, int64_t n,
+       const double *__restrict__ sc, const int *__restrict__ fl) {
+  if (fl[F_REASON] != 0) return;
+  bool first = (fl[F_ITS] == 0);
+  double bb = first ? 0.0 : sc[S_BETA] / sc[S_BETA_OLD];
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double z = (dinv ? dinv[i] : 1.0) * r[i];
+    p[i] = first ? z : fma(bb, p[i], z);
+  }
+}
+
+// alpha = beta/delta; x += alpha p; r -= alpha w; z = D^-1 r; (z,r), (z,z) -> beta, dp, test(i+1)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+            const double *__restrict__ w, const double *__restrict__ dinv, int64_t n, double *sc, int *fl,
+            double *partials, unsigned int *counter, double *hist, long long hist_len) {
+  if (fl[F_REASON] != 0) return;
+  __shared__ double red[32];
+  __shared__ double out[2];
+  __shared__ bool last;
+  double delta = sc[S_DELTA];
+  if (!(delta > 0.0)) {
+    // (p, A p) <= 0 or NaN: DIVERGED_INDEFINITE_MAT, no update (PETSc: its = i+1 at that point)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      // every block takes this branch from the same delta; only one writes
+      fl[F_ITS] = fl[F_ITS] + 1;
+      __threadfence();
+      fl[F_REASON] = isnan(delta) ? IIFE_KSP_DIVERGED_NANORINF : IIFE_KSP_DIVERGED_INDEFINITE_MAT;
+    }
+    return;
+  }
+  double alpha = sc[S_BETA] / delta;
+  double acc[2] = {0.0, 0.0};
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double pi = p[i], wi = __ldcs(w + i);
+    x[i] = fma(alpha, pi, x[i]);
+    double ri = fma(-alpha, wi, r[i]);
+    r[i] = ri;
+    double z = (dinv ? dinv[i] : 1.0) * ri;
+    acc[0] = fma(z, ri, acc[0]);
+    acc[1] = fma(z, z, acc[1]);
+  }
+  if (grid_reduce<2>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
+    double beta = out[0], dp = sqrt(out[1]);
+    int its = fl[F_ITS] + 1;
+    sc[S_BETA_OLD] = sc[S_BETA];
+    sc[S_BETA] = beta;
+    sc[S_DP] = dp;
+    fl[F_ITS] = its;
+    log_hist(hist, hist_len, its, dp);
+    converged_default(sc, fl, its, dp);
+    if (fl[F_REASON] == 0) {
+      if (its >= fl[F_MAXIT]) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
+      else if (beta == 0.0) { fl[F_REASON] = IIFE_KSP_CONVERGED_ATOL; fl[F_ITS] = its + 1; }
+      else if (beta < 0.0) { fl[F_REASON] = IIFE_KSP_DIVERGED_INDEFINITE_PC; fl[F_ITS] = its + 1; }
+      else if (isnan(beta) || isinf(beta)) { fl[F_REASON] = IIFE_KSP_DIVERGED_NANORINF; fl[F_ITS] = its + 1; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FGMRES kernels.  Device-side small arrays: H (m+1) x m column-major, cs[m], sn[m], rs[m+1], y[m].
+// ------------------------------------------------------------------------------------------------
+struct GmresSmall {
+  double *H, *cs, *sn, *rs, *y;
+  int m;  // restart
+};
+
+// ||v||^2 of the fresh residual in V0 -> rs[0], scale, test at cycle start (true residual)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gm_cycle_start(const double *__restrict__ v0, const double *__restrict__ b, int64_t n, double *sc, int *fl,
+                 GmresSmall gs, double *partials, unsigned int *counter, double *hist, long long hist_len,
+                 int first_cycle) {
+  if (fl[F_REASON] != 0) return;
+  __shared__ double red[32];
+  __shared__ double out[2];
+  __shared__ bool last;
+  double acc[2] = {0.0, 0.0};
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double v = v0[i];
+    acc[0] = fma(v, v, acc[0]);
+    if (first_cycle) {
+      double bi = b[i];
+      acc[1] = fma(bi, bi, acc[1]);
+    }
+  }
+  if (grid_reduce<2>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
+    double res = sqrt(out[0]);
+    if (first_cycle) {
+      double rho0 = sqrt(out[1]);
+      sc[S_RHO0] = rho0;
+      sc[S_TTOL] = fmax(sc[S_RTOL] * rho0, sc[S_ATOL]);
+      fl[F_ITS] = 0;
+      log_hist(hist, hist_len, 0, res);
+    }
+    sc[S_RES] = res;
+    gs.rs[0] = res;
+    sc[S_SCALE] = res != 0.0 ? 1.0 / res : 0.0;
+    fl[F_LOC_IT] = 0;
+    fl[F_HAPEND] = 0;
+    converged_default(sc, fl, fl[F_ITS], res);
+    if (fl[F_REASON] == 0 && fl[F_ITS] >= fl[F_MAXIT]) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
+  }
+}
+
+// v_j *= scale (normalise in place), z_j = D^-1 v_j
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gm_scale_pc(double *__restrict__ v, double *__restrict__ z, const double *__restrict__ dinv, int64_t n,
+              const double *__restrict__ sc, const int *__restrict__ fl, int j) {
+  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != j) return;
+  double s = sc[S_SCALE];
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double vi = v[i] * s;
+    v[i] = vi;
+    z[i] = (dinv ? dinv[i] : 1.0) * vi;
+  }
+}
+
+// classical Gram-Schmidt, part 1: h_k = (w, v_k), k = 0..j, into H[:, j].  KT vectors per sweep.
+constexpr int KT = 8;
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gm_dots(const double *__restrict__ w, double *const *__restrict__ V, int64_t n, int j, GmresSmall gs,
+          const int *__restrict__ fl, double *mpartials, unsigned int *counter) {
+  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != j) return;
+  __shared__ double red[32];
+  __shared__ bool last;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k0 = 0; k0 <= j; k0 += KT) {
+    double acc[KT];
+    const double *vp[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      acc[k] = 0.0;
+      vp[k] = V[min(k0 + k, j)];
+    }
+    for (int64_t i = i0; i < n; i += stride) {
+      double wi = w[i];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) acc[k] = fma(wi, vp[k][i], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      double b = block_sum(acc[k], red);
+      if (threadIdx.x == 0 && k0 + k <= j) mpartials[(size_t)(k0 + k) * gridDim.x + blockIdx.x] = b;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // one warp per coefficient, fixed order
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int k = warp; k <= j; k += nw) {
+    double s = 0.0;
+    for (int bb = lane; bb < (int)gridDim.x; bb += 32) s += __ldcg(mpartials + (size_t)k * gridDim.x + bb);
+    s = warp_sum(s);
+    if (lane == 0) gs.H[(size_t)j * (gs.m + 1) + k] = s;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+// classical Gram-Schmidt, part 2: w -= sum_k h_k v_k; ||w||^2; then (last CTA, one thread) the
+// Hessenberg/Givens update, residual estimate and convergence test of PETSc's KSPFGMRESCycle.
+constexpr int ROWS_PT = 2;
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gm_update(double *__restrict__ w, double *const *__restrict__ V, int64_t n, int j, GmresSmall gs, double *sc,
+            int *fl, double *partials, unsigned int *counter, double *hist, long long hist_len) {
+  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != j) return;
+  extern __shared__ double hsh[];  // j+1 coefficients
+  __shared__ double red[32];
+  __shared__ double out[1];
+  __shared__ bool last;
+  const double *Hj = gs.H + (size_t)j * (gs.m + 1);
+  for (int k = threadIdx.x; k <= j; k += blockDim.x) hsh[k] = Hj[k];
+  __syncthreads();
+  double acc[1] = {0.0};
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * ROWS_PT;
+  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x) * ROWS_PT + threadIdx.x; base < n; base += stride) {
+    double a[ROWS_PT];
+    int64_t idx[ROWS_PT];
+#pragma unroll
+    for (int r = 0; r < ROWS_PT; ++r) {
+      idx[r] = base + (int64_t)r * blockDim.x;
+      a[r] = idx[r] < n ? w[idx[r]] : 0.0;
+    }
+    for (int k = 0; k <= j; ++k) {
+      const double *vk = V[k];
+      double h = hsh[k];
+#pragma unroll
+      for (int r = 0; r < ROWS_PT; ++r)
+        if (idx[r] < n) a[r] = fma(-h, vk[idx[r]], a[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS_PT; ++r)
+      if (idx[r] < n) {
+        w[idx[r]] = a[r];
+        acc[0] = fma(a[r], a[r], acc[0]);
+      }
+  }
+  if (grid_reduce<1>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
+    const int m1 = gs.m + 1;
+    double *hh = gs.H + (size_t)j * m1;
+    double tt = sqrt(out[0]);
+    // happy breakdown test (fgmres.c): hapbnd = min(|tt / rs[j]|, haptol = 1e-30)
+    double hapbnd = fabs(tt / gs.rs[j]);
+    if (hapbnd > 1e-30) hapbnd = 1e-30;
+    bool hapend = false;
+    if (tt > hapbnd) {
+      sc[S_SCALE] = 1.0 / tt;
+    } else {
+      sc[S_SCALE] = 0.0;
+      hapend = true;
+    }
+    hh[j + 1] = tt;
+    // apply the previous rotations to the new column
+    for (int k = 0; k < j; ++k) {
+      double t1 = hh[k], t2 = hh[k + 1];
+      hh[k] = gs.cs[k] * t1 + gs.sn[k] * t2;
+      hh[k + 1] = -gs.sn[k] * t1 + gs.cs[k] * t2;
+    }
+    // new rotation annihilating hh[j+1]
+    double res;
+    if (!hapend) {
+      double t = sqrt(hh[j] * hh[j] + hh[j + 1] * hh[j + 1]);
+      if (t == 0.0) {
+        fl[F_REASON] = IIFE_KSP_DIVERGED_BREAKDOWN;
+        t = 1.0;
+      }
+      gs.cs[j] = hh[j] / t;
+      gs.sn[j] = hh[j + 1] / t;
+      gs.rs[j + 1] = -gs.sn[j] * gs.rs[j];
+      gs.rs[j] = gs.cs[j] * gs.rs[j];
+      hh[j] = gs.cs[j] * hh[j] + gs.sn[j] * hh[j + 1];
+      res = fabs(gs.rs[j + 1]);
+    } else {
+      // happy breakdown: the Krylov space is invariant, the exact solution is in it
+      res = 0.0;
+      gs.rs[j + 1] = 0.0;
+    }
+    int its = fl[F_ITS] + 1;
+    fl[F_ITS] = its;
+    fl[F_LOC_IT] = j + 1;
+    sc[S_RES] = res;
+    log_hist(hist, hist_len, its, res);
+    converged_default(sc, fl, its, res);
+    if (fl[F_REASON] == 0) {
+      if (hapend) fl[F_REASON] = IIFE_KSP_DIVERGED_BREAKDOWN;
+      else if (its >= fl[F_MAXIT]) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
+    }
+  }
+}
+
+// back substitution H(0:k,0:k) y = rs(0:k), k = loc_it, one warp
+__global__ void k_gm_solve_y(GmresSmall gs, const int *__restrict__ fl) {
+  int k = fl[F_LOC_IT];
+  if (k <= 0) return;
+  int lane = threadIdx.x;
+  const int m1 = gs.m + 1;
+  for (int i = k - 1; i >= 0; --i) {
+    double s = 0.0;
+    for (int c = i + 1 + lane; c < k; c += 32) s += gs.H[(size_t)c * m1 + i] * gs.y[c];
+    s = warp_sum(s);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (lane == 0) {
+      double d = gs.H[(size_t)i * m1 + i];
+      gs.y[i] = d != 0.0 ? (gs.rs[i] - s) / d : 0.0;
+    }
+    __syncwarp();
+  }
+}
+
+// x += sum_{k < loc_it} y_k z_k ; the last CTA resets loc_it
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gm_build_x(double *__restrict__ x, double *const *__restrict__ Z, int64_t n, GmresSmall gs, int *fl,
+             unsigned int *counter) {
+  int kk = fl[F_LOC_IT];
+  if (kk <= 0) return;
+  extern __shared__ double ysh[];
+  __shared__ bool last;
+  for (int k = threadIdx.x; k < kk; k += blockDim.x) ysh[k] = gs.y[k];
+  __syncthreads();
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * ROWS_PT;
+  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x) * ROWS_PT + threadIdx.x; base < n; base += stride) {
+    double a[ROWS_PT];
+    int64_t idx[ROWS_PT];
+#pragma unroll
+    for (int r = 0; r < ROWS_PT; ++r) {
+      idx[r] = base + (int64_t)r * blockDim.x;
+      a[r] = idx[r] < n ? x[idx[r]] : 0.0;
+    }
+    for (int k = 0; k < kk; ++k) {
+      const double *zk = Z[k];
+      double y = ysh[k];
+#pragma unroll
+      for (int r = 0; r < ROWS_PT; ++r)
+        if (idx[r] < n) a[r] = fma(y, zk[idx[r]], a[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS_PT; ++r)
+      if (idx[r] < n) x[idx[r]] = a[r];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    last = (t == gridDim.x - 1);
+    if (last) {
+      fl[F_LOC_IT] = 0;
+      *counter = 0u;
+    }
+  }
+}
+
+// r = b  (copy; the SpMV r -= A x follows), gated by the reason flag
+__global__ void __launch_bounds__(VEC_THREADS)
+k_copy_gated(const double *__restrict__ src, double *__restrict__ dst, int64_t n, const int *__restrict__ fl) {
+  if (fl && fl[F_REASON] != 0) return;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+// y = y - A x gated: implemented with the plain SpMV when the flag is clear (checked on the device
+// inside a tiny wrapper kernel would cost a launch; instead FGMRES restarts are rare and the SpMV
+// result is harmless after convergence because V0 is not read any more).
+
+static int vec_grid(int64_t n) {
+  int64_t g = (n + VEC_THREADS - 1) / VEC_THREADS;
+  int64_t cap = (int64_t)ctx().sm_count * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  if (g > MAX_PARTIALS) g = MAX_PARTIALS;
+  return (int)g;
+}
+
+struct HostFlags {
+  int fl[F_COUNT];
+};
+
+static int poll_flags(const KspWork &w, HostFlags *pinned) {
+  IIFE_CUDA(cudaMemcpyAsync(pinned->fl, w.fl, sizeof(int) * F_COUNT, cudaMemcpyDeviceToHost, ctx().stream));
+  IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+  return IIFE_OK;
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CG driver (device pointers)
+// ------------------------------------------------------------------------------------------------
+static int cg_solve(Mat *A, const double *dinv, const double *b, double *x, int64_t max_it, KspWork &w,
+                    HostFlags *hf) {
+  Ctx &c = ctx();
+  const int64_t n = A->n_rows;
+  Tmp<double> r, p, wv;
+  IIFE_TRY(r.alloc((size_t)n));
+  IIFE_TRY(p.alloc((size_t)n));
+  IIFE_TRY(wv.alloc((size_t)n));
+  const int g = vec_grid(n);
+  // r = b - A x0
+  IIFE_LAUNCH(k_copy_gated, g, VEC_THREADS, 0, b, r.p, n, (const int *)nullptr);
+  IIFE_TRY(spmv_launch(A, -1.0, x, 1.0, r.p));
+  IIFE_LAUNCH(k_cg_init, g, VEC_THREADS, 0, r.p, b, dinv, n, w.sc, w.fl, w.partials, w.counters, w.hist,
+              (long long)w.hist_len);
+  IIFE_CHECK_LAUNCH();
+  IIFE_TRY(poll_flags(w, hf));
+  if (hf->fl[F_REASON] != 0) return IIFE_OK;
+
+  int chunk = env_int("IIFE_KSP_CHUNK", 32);
+  if (chunk < 1) chunk = 1;
+  const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0;
+  auto enqueue_iteration = [&]() -> int {
+    IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl);
+    IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl));
+    IIFE_LAUNCH(k_cg_update, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
+                w.hist, (long long)w.hist_len);
+    return IIFE_OK;
+  };
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches_per_chunk = 0;
+  if (use_graph) {
+    int64_t before = c.launches;
+    cudaError_t e = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      int rc = IIFE_OK;
+      for (int k = 0; k < chunk && rc == IIFE_OK; ++k) rc = enqueue_iteration();
+      e = cudaStreamEndCapture(c.stream, &graph);
+      if (rc == IIFE_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+      if (rc != IIFE_OK || e != cudaSuccess || !exec) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        graph = nullptr;
+        exec = nullptr;
+      }
+    } else {
+      cudaGetLastError();
+    }
+    launches_per_chunk = c.launches - before;
+    c.launches = before;  // captured, not launched yet
+  }
+  int rc = IIFE_OK;
+  int64_t enq = 0;
+  while (rc == IIFE_OK) {
+    if (exec) {
+      cudaError_t e = cudaGraphLaunch(exec, c.stream);
+      if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e)); break; }
+      c.launches += launches_per_chunk;
+    } else {
+      for (int k = 0; k < chunk && rc == IIFE_OK; ++k) rc = enqueue_iteration();
+      if (rc != IIFE_OK) break;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "CG launch: %s", cudaGetErrorString(e)); break; }
+    }
+    enq += chunk;
+    if ((rc = poll_flags(w, hf)) != IIFE_OK) break;
+    if (hf->fl[F_REASON] != 0) break;
+    if (enq > max_it + chunk) { rc = set_err(IIFE_ERR_STATE, "CG driver ran past max_it without a reason"); break; }
+  }
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FGMRES driver (device pointers)
+// ------------------------------------------------------------------------------------------------
+static int fgmres_solve(Mat *A, const double *dinv, const double *b, double *x, int64_t max_it, int restart,
+                        KspWork &w, HostFlags *hf) {
+  Ctx &c = ctx();
+  const int64_t n = A->n_rows;
+  int m = restart;
+  if (m < 1) m = 30;
+  if ((int64_t)m > max_it && max_it > 0) m = (int)max_it;
+  if (m > 10000) m = 10000;
+  const int g = vec_grid(n);
+  // small device arrays
+  Tmp<double> small;
+  size_t hs = (size_t)(m + 1) * m;
+  IIFE_TRY(small.alloc(hs + 4 * (size_t)(m + 1)));
+  IIFE_CUDA(cudaMemsetAsync(small.p, 0, (hs + 4 * (size_t)(m + 1)) * sizeof(double), c.stream));
+  GmresSmall gs;
+  gs.H = small.p;
+  gs.cs = small.p + hs;
+  gs.sn = gs.cs + (m + 1);
+  gs.rs = gs.sn + (m + 1);
+  gs.y = gs.rs + (m + 1);
+  gs.m = m;
+  // basis vectors allocated lazily; pointer tables on the device
+  std::vector<double *> V, Z;
+  Tmp<double *> vtab, ztab;
+  Tmp<double> mpart;
+  IIFE_TRY(vtab.alloc((size_t)m + 1));
+  IIFE_TRY(ztab.alloc((size_t)m + 1));
+  IIFE_TRY(mpart.alloc((size_t)(m + 1) * g));
+  int rc = IIFE_OK;
+  // grow the basis up to V[upto_v], Z[upto_z]; called only at points where the stream is idle
+  auto ensure_vecs = [&](int upto_v, int upto_z) -> int {
+    bool grew = false;
+    while ((int)V.size() <= upto_v) {
+      double *pnew = nullptr;
+      IIFE_TRY(dev_alloc_t(&pnew, (size_t)n));
+      V.push_back(pnew);
+      grew = true;
+    }
+    while ((int)Z.size() <= upto_z) {
+      double *pnew = nullptr;
+      IIFE_TRY(dev_alloc_t(&pnew, (size_t)n));
+      Z.push_back(pnew);
+      grew = true;
+    }
+    if (grew) {
+      IIFE_CUDA(cudaStreamSynchronize(c.stream));
+      IIFE_CUDA(cudaMemcpy(vtab.p, V.data(), V.size() * sizeof(double *), cudaMemcpyHostToDevice));
+      IIFE_CUDA(cudaMemcpy(ztab.p, Z.data(), Z.size() * sizeof(double *), cudaMemcpyHostToDevice));
+    }
+    return IIFE_OK;
+  };
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(c.stream);
+    for (double *pv : V) dev_free_t(pv, (size_t)n);
+    for (double *pz : Z) dev_free_t(pz, (size_t)n);
+  };
+  int chunk = env_int("IIFE_KSP_CHUNK", 16);
+  if (chunk < 1) chunk = 1;
+  bool first_cycle = true;
+  int64_t enq_total = 0;
+  bool done = false;
+  while (rc == IIFE_OK && !done) {
+    // cycle start: V0 = b - A x
+    if ((rc = ensure_vecs(chunk < m ? chunk : m, (chunk < m ? chunk : m) - 1)) != IIFE_OK) break;
+    IIFE_LAUNCH(k_copy_gated, g, VEC_THREADS, 0, b, V[0], n, (const int *)w.fl);
+    if ((rc = spmv_launch(A, -1.0, x, 1.0, V[0])) != IIFE_OK) break;
+    IIFE_LAUNCH(k_gm_cycle_start, g, VEC_THREADS, 0, V[0], b, n, w.sc, w.fl, gs, w.partials, w.counters, w.hist,
+                (long long)w.hist_len, first_cycle ? 1 : 0);
+    first_cycle = false;
+    if ((rc = poll_flags(w, hf)) != IIFE_OK) break;
+    if (hf->fl[F_REASON] != 0) { done = true; break; }
+    for (int j = 0; j < m && rc == IIFE_OK; ++j) {
+      IIFE_LAUNCH(k_gm_scale_pc, g, VEC_THREADS, 0, V[j], Z[j], dinv, n, w.sc, w.fl, j);
+      // w = A z_j into V[j+1]  (harmless after convergence: V[j+1] is not read any more)
+      if ((rc = spmv_launch(A, 1.0, Z[j], 0.0, V[j + 1])) != IIFE_OK) break;
+      IIFE_LAUNCH(k_gm_dots, g, VEC_THREADS, 0, V[j + 1], (double *const *)vtab.p, n, j, gs, w.fl, mpart.p,
+                  w.counters + 1);
+      IIFE_LAUNCH(k_gm_update, g, VEC_THREADS, (size_t)(j + 1) * sizeof(double), V[j + 1], (double *const *)vtab.p, n,
+                  j, gs, w.sc, w.fl, w.partials, w.counters, w.hist, (long long)w.hist_len);
+      ++enq_total;
+      if ((j + 1) % chunk == 0 || j + 1 == m) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "FGMRES launch: %s", cudaGetErrorString(e)); break; }
+        if ((rc = poll_flags(w, hf)) != IIFE_OK) break;
+        if (hf->fl[F_REASON] != 0) break;
+        if (j + 1 < m) {
+          int upto = j + 1 + chunk < m ? j + 1 + chunk : m;
+          if ((rc = ensure_vecs(upto, upto - 1)) != IIFE_OK) break;
+        }
+      }
+    }
+    if (rc != IIFE_OK) break;
+    // build the solution from however many inner iterations were completed in this cycle
+    IIFE_LAUNCH(k_gm_solve_y, 1, 32, 0, gs, w.fl);
+    IIFE_LAUNCH(k_gm_build_x, g, VEC_THREADS, (size_t)(m + 1) * sizeof(double), x, (double *const *)ztab.p, n, gs, w.fl,
+                w.counters + 2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "FGMRES build: %s", cudaGetErrorString(e)); break; }
+    if ((rc = poll_flags(w, hf)) != IIFE_OK) break;
+    if (hf->fl[F_REASON] != 0) done = true;
+    if (enq_total > max_it + m) { rc = set_err(IIFE_ERR_STATE, "FGMRES driver ran past max_it without a reason"); break; }
+  }
+  cleanup();
+  return rc;
+}
+
+__global__ void k_ksp_setup(double *sc, int *fl, double rtol, double atol, double dtol, int maxit) {
+  for (int k = 0; k < S_COUNT; ++k) sc[k] = 0.0;
+  for (int k = 0; k < F_COUNT; ++k) fl[k] = 0;
+  sc[S_RTOL] = rtol;
+  sc[S_ATOL] = atol;
+  sc[S_DTOL] = dtol;
+  fl[F_MAXIT] = maxit;
+}
+
+}  // namespace iife
+
+using namespace iife;
+
+extern "C" int iife_ksp_solve(iife_mat A_, int ksp_type, int pc_type, double rtol, double atol, double dtol,
+                              int64_t max_it, int restart, const double *b, double *x, int mem, iife_halo halo,
+                              iife_ksp_result *res, double *hist, int64_t hist_len) {
+  IIFE_NEED_INIT();
+  Ctx &c = ctx();
+  Mat *A = (Mat *)A_;
+  if (!A || !b || !x) return set_err(IIFE_ERR_ARG, "NULL argument");
+  if (halo) return set_err(IIFE_ERR_UNSUPPORTED, "distributed KSP goes through iife_ksp_solve_dist");
+  if (A->n_rows != A->n_cols) return set_err(IIFE_ERR_ARG, "KSP needs a square operator, got %lld x %lld", (long long)A->n_rows, (long long)A->n_cols);
+  if (ksp_type != IIFE_KSP_CG && ksp_type != IIFE_KSP_FGMRES) return set_err(IIFE_ERR_ARG, "unknown ksp_type %d", ksp_type);
+  if (pc_type != IIFE_PC_NONE && pc_type != IIFE_PC_JACOBI) return set_err(IIFE_ERR_ARG, "unknown pc_type %d", pc_type);
+  if (max_it < 0) max_it = 0;
+  if (max_it > 0x7ffffff0LL) max_it = 0x7ffffff0LL;
+  if (dtol <= 0.0) dtol = 1e4;
+  const int64_t n = A->n_rows;
+  const double *dinv = nullptr;
+  if (pc_type == IIFE_PC_JACOBI) {
+    IIFE_TRY(mat_ensure_dinv(A));
+    dinv = A->dinv;
+  }
+  KspWork w;
+  Tmp<double> sc, partials, dhist, dx, db;
+  Tmp<int> fl;
+  Tmp<unsigned int> counters;
+  IIFE_TRY(sc.alloc(S_COUNT));
+  IIFE_TRY(fl.alloc(F_COUNT));
+  IIFE_TRY(partials.alloc(4 * MAX_PARTIALS));
+  IIFE_TRY(counters.alloc(4));
+  IIFE_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned int), c.stream));
+  w.sc = sc.p;
+  w.fl = fl.p;
+  w.partials = partials.p;
+  w.counters = counters.p;
+  if (hist && hist_len > 0) {
+    IIFE_TRY(dhist.alloc((size_t)hist_len));
+    IIFE_CUDA(cudaMemsetAsync(dhist.p, 0, (size_t)hist_len * sizeof(double), c.stream));
+    w.hist = dhist.p;
+    w.hist_len = hist_len;
+  }
+  IIFE_LAUNCH(k_ksp_setup, 1, 1, 0, w.sc, w.fl, rtol, atol, dtol, (int)max_it);
+  IIFE_CHECK_LAUNCH();
+  const double *bd = b;
+  double *xd = x;
+  if (mem == IIFE_MEM_HOST) {
+    IIFE_TRY(dx.alloc((size_t)n));
+    IIFE_TRY(db.alloc((size_t)n));
+    IIFE_CUDA(cudaMemcpyAsync(dx.p, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    IIFE_CUDA(cudaMemcpyAsync(db.p, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    bd = db.p;
+    xd = dx.p;
+  }
+  HostFlags *hf = nullptr;
+  IIFE_CUDA(cudaMallocHost((void **)&hf, sizeof(HostFlags)));
+  int rc;
+  if (n == 0) {
+    rc = IIFE_OK;
+    for (int k = 0; k < F_COUNT; ++k) hf->fl[k] = 0;
+    hf->fl[F_REASON] = IIFE_KSP_CONVERGED_ATOL;
+  } else if (ksp_type == IIFE_KSP_CG) {
+    rc = cg_solve(A, dinv, bd, xd, max_it, w, hf);
+  } else {
+    rc = fgmres_solve(A, dinv, bd, xd, max_it, restart, w, hf);
+  }
+  if (rc == IIFE_OK) {
+    double hsc[S_COUNT] = {0};
+    if (n > 0) {
+      cudaMemcpyAsync(hsc, w.sc, sizeof(hsc), cudaMemcpyDeviceToHost, c.stream);
+      cudaMemcpyAsync(hf->fl, w.fl, sizeof(int) * F_COUNT, cudaMemcpyDeviceToHost, c.stream);
+    }
+    if (mem == IIFE_MEM_HOST) cudaMemcpyAsync(x, xd, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream);
+    if (w.hist) cudaMemcpyAsync(hist, w.hist, (size_t)hist_len * sizeof(double), cudaMemcpyDeviceToHost, c.stream);
+    cudaError_t e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) rc = set_err(IIFE_ERR_CUDA, "KSP finish: %s", cudaGetErrorString(e));
+    if (res) {
+      res->iterations = hf->fl[F_ITS];
+      res->reason = hf->fl[F_REASON];
+      res->_pad = 0;
+      res->rnorm = ksp_type == IIFE_KSP_CG ? hsc[S_DP] : hsc[S_RES];
+      res->rnorm0 = hsc[S_RHO0];
+    }
+  }
+  cudaFreeHost(hf);
+  return rc;
+}

@@ -1,0 +1,678 @@
+// mat.cu — device CSR (AIJ) matrices: upload/validation, value refresh, fingerprint, explicit
+// transpose (replaces MatTranspose, reference la_utils.py:178,180), diagonal (MatGetDiagonal,
+// reference common.py:222,305) and the Jacobi inverse diagonal with PETSc's zero -> 1 rule.
+#include "common.cuh"
+
+namespace iife {
+
+int mat_alloc(Mat **out, int64_t n_rows, int64_t n_cols, int64_t nnz) {
+  Mat *A = new Mat();
+  A->n_rows = n_rows;
+  A->n_cols = n_cols;
+  A->nnz = nnz;
+  int rc = dev_alloc_t(&A->rowptr, (size_t)n_rows + 1);
+  if (rc == IIFE_OK) rc = dev_alloc_t(&A->colind, (size_t)nnz);
+  if (rc == IIFE_OK) rc = dev_alloc_t(&A->val, (size_t)nnz);
+  if (rc != IIFE_OK) {
+    mat_free(A);
+    return rc;
+  }
+  *out = A;
+  return IIFE_OK;
+}
+
+int mat_free(Mat *A) {
+  if (!A) return IIFE_OK;
+  if (A->T) mat_free(A->T);
+  if (A->T_perm) dev_free_t(A->T_perm, (size_t)A->nnz);
+  if (A->dinv) dev_free_t(A->dinv, (size_t)A->n_rows);
+  if (A->rowptr) dev_free_t(A->rowptr, (size_t)A->n_rows + 1);
+  if (A->colind) dev_free_t(A->colind, (size_t)A->nnz);
+  if (A->val) dev_free_t(A->val, (size_t)A->nnz);
+  delete A;
+  return IIFE_OK;
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_narrow_i64(const long long *__restrict__ in, int *__restrict__ out, int64_t n,
+                             int *__restrict__ bad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    long long v = in[i];
+    if (v < 0 || v > 0x7fffffffLL) atomicOr(bad, 1);
+    out[i] = (int)v;
+  }
+}
+
+__global__ void k_widen_i32(const int *__restrict__ in, long long *__restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = in[i];
+}
+
+// CSR validation: bit 1 rowptr not monotone / bad ends, bit 2 column out of range, bit 4 columns not
+// strictly ascending in a row.
+__global__ void k_validate_rowptr(const int *__restrict__ rowptr, int64_t n_rows, int64_t nnz,
+                                  int *__restrict__ bad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (i == 0) {
+    if (rowptr[0] != 0 || (int64_t)rowptr[n_rows] != nnz) atomicOr(bad, 1);
+  }
+  for (; i < n_rows; i += stride)
+    if (rowptr[i + 1] < rowptr[i]) atomicOr(bad, 1);
+}
+
+__global__ void k_validate_cols(const int *__restrict__ rowptr, const int *__restrict__ colind, int64_t n_rows,
+                                int64_t n_cols, int64_t nnz, int *__restrict__ bad) {
+  // one thread per entry: compare with predecessor unless the entry starts a row.  Row starts are
+  // found by marking: entry p starts a row iff some rowptr[i] == p; instead of a search we check the
+  // weaker-but-sufficient condition per row in a second loop below (thread per row over row heads).
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; p < nnz; p += stride) {
+    int c = colind[p];
+    if (c < 0 || (int64_t)c >= n_cols) atomicOr(bad, 2);
+  }
+  // per-row ascending check (rows are short in every workload of this path; long rows just take longer)
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < n_rows; i += stride) {
+    int b = rowptr[i], e = rowptr[i + 1];
+    if (b < 0 || e > nnz || e < b) continue;  // reported by k_validate_rowptr
+    for (int q = b + 1; q < e; ++q)
+      if (colind[q] <= colind[q - 1]) {
+        atomicOr(bad, 4);
+        break;
+      }
+  }
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// order-independent 64-bit fingerprint: sum over i of mix(salt + i*K + x_i)
+__global__ void k_fingerprint(const int *__restrict__ a, int64_t n, unsigned long long salt,
+                              unsigned long long *__restrict__ acc) {
+  unsigned long long s = 0;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    s += mix64(salt + (unsigned long long)i * 0xD6E8FEB86659FD93ull + (unsigned long long)(unsigned int)a[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+}
+
+// ---- transpose
+__global__ void k_col_count(const int *__restrict__ colind, int64_t nnz, int *__restrict__ cnt) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; p < nnz; p += stride) atomicAdd(&cnt[colind[p]], 1);
+}
+
+// scatter with an atomic cursor: T.colind[pos] = row, perm[pos] = p.  Order inside a T row is
+// arbitrary here and made ascending (hence deterministic) by the sort kernels below.
+template <int LPR>
+__global__ void k_transpose_fill(const int *__restrict__ rowptr, const int *__restrict__ colind, int64_t n_rows,
+                                 const int *__restrict__ t_rowptr, int *__restrict__ cursor,
+                                 int *__restrict__ t_col, int *__restrict__ t_perm) {
+  int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  int lg = threadIdx.x % LPR;
+  int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  for (int64_t i = gid; i < n_rows; i += ngroups) {
+    int b = rowptr[i], e = rowptr[i + 1];
+    for (int p = b + lg; p < e; p += LPR) {
+      int c = colind[p];
+      int pos = t_rowptr[c] + atomicAdd(&cursor[c], 1);
+      t_col[pos] = (int)i;
+      t_perm[pos] = p;
+    }
+  }
+}
+
+__device__ __forceinline__ void cmpx(int &k, int &v, int ok, int ov, bool up_keep_min) {
+  // keep min if up_keep_min else max (keys unique inside a row, so ties do not occur; padded keys
+  // are INT_MAX and may tie with each other harmlessly)
+  bool take = up_keep_min ? (ok < k) : (ok > k);
+  if (take) {
+    k = ok;
+    v = ov;
+  }
+}
+
+// rows with 2..32 entries: one warp per row, bitonic sort in registers through shuffles.
+// rows with more entries are appended to `long_rows`.
+__global__ void k_sort_rows_warp(const int *__restrict__ t_rowptr, int *__restrict__ t_col,
+                                 int *__restrict__ t_perm, int64_t n_rows, int *__restrict__ long_rows,
+                                 int *__restrict__ n_long) {
+  int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = w; i < n_rows; i += nw) {
+    int b = t_rowptr[i], len = t_rowptr[i + 1] - b;
+    if (len <= 1) continue;
+    if (len > 32) {
+      if (lane == 0) long_rows[atomicAdd(n_long, 1)] = (int)i;
+      continue;
+    }
+    int k = lane < len ? t_col[b + lane] : 0x7fffffff;
+    int v = lane < len ? t_perm[b + lane] : -1;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        int ok = __shfl_xor_sync(0xffffffffu, k, stride);
+        int ov = __shfl_xor_sync(0xffffffffu, v, stride);
+        bool ascending = ((lane & size) == 0);
+        bool lower = ((lane & stride) == 0);
+        cmpx(k, v, ok, ov, ascending == lower);
+      }
+    }
+    if (lane < len) {
+      t_col[b + lane] = k;
+      t_perm[b + lane] = v;
+    }
+  }
+}
+
+// long rows: one CTA per row; bitonic sort in shared memory when the padded length fits SORT_SMEM
+// pairs, otherwise in place in global memory (virtual padding with INT_MAX beyond len).
+constexpr int SORT_SMEM = 4096;
+__global__ void k_sort_rows_block(const int *__restrict__ t_rowptr, int *__restrict__ t_col,
+                                  int *__restrict__ t_perm, const int *__restrict__ long_rows,
+                                  const int *__restrict__ n_long) {
+  __shared__ int sk[SORT_SMEM];
+  __shared__ int sv[SORT_SMEM];
+  int nl = *n_long;
+  for (int r = blockIdx.x; r < nl; r += gridDim.x) {
+    int i = long_rows[r];
+    int b = t_rowptr[i], len = t_rowptr[i + 1] - b;
+    int P = 1;
+    while (P < len) P <<= 1;
+    if (P <= SORT_SMEM) {
+      for (int t = threadIdx.x; t < P; t += blockDim.x) {
+        sk[t] = t < len ? t_col[b + t] : 0x7fffffff;
+        sv[t] = t < len ? t_perm[b + t] : -1;
+      }
+      __syncthreads();
+      for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+            int lo = 2 * t - (t & (stride - 1));
+            int hi = lo + stride;
+            bool asc = ((lo & size) == 0);
+            int kl = sk[lo], kh = sk[hi];
+            if ((kl > kh) == asc) {
+              sk[lo] = kh;
+              sk[hi] = kl;
+              int tv = sv[lo];
+              sv[lo] = sv[hi];
+              sv[hi] = tv;
+            }
+          }
+          __syncthreads();
+        }
+      }
+      for (int t = threadIdx.x; t < len; t += blockDim.x) {
+        t_col[b + t] = sk[t];
+        t_perm[b + t] = sv[t];
+      }
+      __syncthreads();
+    } else {
+      // global-memory bitonic network with virtual +inf padding: an element index >= len is +inf.
+      // A compare-exchange touching a virtual element never moves a real element upward past len in
+      // an ascending-final network only if handled explicitly, so we treat (lo real, hi virtual) as
+      // already ordered when ascending and swap-needed when descending — the latter cannot be
+      // represented in place.  We therefore sort with the all-ascending "bitonic via reversal" form,
+      // in which virtual elements (always the largest) only ever need to stay at high indices.
+      for (int size = 2; size <= P; size <<= 1) {
+        // first step of each stage: compare i with its mirror in the block of `size`
+        for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+          int blk = t / (size >> 1), off = t % (size >> 1);
+          int lo = blk * size + off;
+          int hi = blk * size + size - 1 - off;
+          if (hi < len) {
+            int kl = t_col[b + lo], kh = t_col[b + hi];
+            if (kl > kh) {
+              t_col[b + lo] = kh;
+              t_col[b + hi] = kl;
+              int vl = t_perm[b + lo];
+              t_perm[b + lo] = t_perm[b + hi];
+              t_perm[b + hi] = vl;
+            }
+          }
+        }
+        __syncthreads();
+        for (int stride = size >> 2; stride > 0; stride >>= 1) {
+          for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+            int lo = 2 * t - (t & (stride - 1));
+            int hi = lo + stride;
+            if (hi < len) {
+              int kl = t_col[b + lo], kh = t_col[b + hi];
+              if (kl > kh) {
+                t_col[b + lo] = kh;
+                t_col[b + hi] = kl;
+                int vl = t_perm[b + lo];
+                t_perm[b + lo] = t_perm[b + hi];
+                t_perm[b + hi] = vl;
+              }
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+  }
+}
+
+__global__ void k_gather_vals(const double *__restrict__ val, const int *__restrict__ perm,
+                              double *__restrict__ out, int64_t nnz) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; p < nnz; p += stride) out[p] = val[perm[p]];
+}
+
+template <int LPR>
+__global__ void k_diag(const int *__restrict__ rowptr, const int *__restrict__ colind,
+                       const double *__restrict__ val, int64_t n_rows, double *__restrict__ diag, int jacobi) {
+  int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  int lg = threadIdx.x % LPR;
+  int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  // all lanes of a group iterate together (uniform trip count across the warp via the row loop bound)
+  int64_t n_iter = (n_rows + ngroups - 1) / ngroups;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    int64_t i = gid + it * ngroups;
+    double d = 0.0;
+    if (i < n_rows) {
+      int b = rowptr[i], e = rowptr[i + 1];
+      for (int p = b + lg; p < e; p += LPR)
+        if (colind[p] == (int)i) d = val[p];
+    }
+    // at most one lane holds the diagonal: combine with an add over the group
+    d = group_sum<LPR>(d);
+    if (i < n_rows && lg == 0) {
+      if (jacobi) d = (d == 0.0) ? 1.0 : 1.0 / d;  // PCJACOBI: zero diagonal -> 1
+      diag[i] = d;
+    }
+  }
+}
+
+__global__ void k_max_row_len(const int *__restrict__ rowptr, int64_t n_rows, int *__restrict__ out) {
+  int m = 0;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n_rows; i += stride) m = max(m, rowptr[i + 1] - rowptr[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+static int grid_for(int64_t n, int threads = 256) {
+  int64_t g = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)ctx().sm_count * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int mat_max_row_len(Mat *A, int *out) {
+  if (A->max_row_len < 0) {
+    Tmp<int> d;
+    IIFE_TRY(d.alloc(1));
+    IIFE_CUDA(cudaMemsetAsync(d.p, 0, sizeof(int), ctx().stream));
+    if (A->n_rows > 0) IIFE_LAUNCH(k_max_row_len, grid_for(A->n_rows), 256, 0, A->rowptr, A->n_rows, d.p);
+    IIFE_CHECK_LAUNCH();
+    int h = 0;
+    IIFE_CUDA(cudaMemcpyAsync(&h, d.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+    A->max_row_len = h;
+  }
+  *out = A->max_row_len;
+  return IIFE_OK;
+}
+
+int mat_fingerprint(Mat *A, uint64_t *fp) {
+  if (!A->fp_valid) {
+    Tmp<unsigned long long> acc;
+    IIFE_TRY(acc.alloc(1));
+    IIFE_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long), ctx().stream));
+    IIFE_LAUNCH(k_fingerprint, grid_for(A->n_rows + 1), 256, 0, A->rowptr, A->n_rows + 1, 0x1111ull, acc.p);
+    if (A->nnz > 0) IIFE_LAUNCH(k_fingerprint, grid_for(A->nnz), 256, 0, A->colind, A->nnz, 0x2222ull, acc.p);
+    IIFE_CHECK_LAUNCH();
+    unsigned long long h = 0;
+    IIFE_CUDA(cudaMemcpyAsync(&h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx().stream));
+    IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+    // fold the shape in on the host
+    unsigned long long s = h;
+    s ^= 0x9E3779B97F4A7C15ull * (unsigned long long)(A->n_rows + 1);
+    s ^= 0xC2B2AE3D27D4EB4Full * (unsigned long long)(A->n_cols + 1);
+    s ^= 0x165667B19E3779F9ull * (unsigned long long)(A->nnz + 1);
+    A->fp = s;
+    A->fp_valid = true;
+  }
+  *fp = A->fp;
+  return IIFE_OK;
+}
+
+static int pick_lpr_mean(const Mat *A) {
+  double mean = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
+  if (mean <= 2.5) return 2;
+  if (mean <= 5.0) return 4;
+  if (mean <= 10.0) return 8;
+  if (mean <= 20.0) return 16;
+  return 32;
+}
+
+// Build the explicit transpose of A: pattern (rows column-sorted) and the gather permutation
+// perm with T.val[p] = A.val[perm[p]].  Values are NOT filled here (see gather_vals_launch).
+int transpose_build(const Mat *A, Mat **T_out, int **perm_out) {
+  Ctx &c = ctx();
+  Mat *T = nullptr;
+  int *perm = nullptr;
+  IIFE_TRY(mat_alloc(&T, A->n_cols, A->n_rows, A->nnz));
+  int rc = IIFE_OK;
+  Tmp<int> cnt, long_rows, n_long;
+  do {
+    if ((rc = cnt.alloc((size_t)A->n_cols + 1)) != IIFE_OK) break;
+    if ((rc = dev_alloc_t(&perm, (size_t)A->nnz)) != IIFE_OK) break;
+    cudaMemsetAsync(cnt.p, 0, ((size_t)A->n_cols + 1) * sizeof(int), c.stream);
+    if (A->nnz > 0) IIFE_LAUNCH(k_col_count, grid_for(A->nnz), 256, 0, A->colind, A->nnz, cnt.p);
+    int64_t total = 0;
+    if ((rc = exclusive_scan_i32(cnt.p, T->rowptr, A->n_cols, &total)) != IIFE_OK) break;
+    if (total != A->nnz) {
+      rc = set_err(IIFE_ERR_STATE, "transpose: column histogram total %lld != nnz %lld", (long long)total,
+                   (long long)A->nnz);
+      break;
+    }
+    cudaMemsetAsync(cnt.p, 0, ((size_t)A->n_cols + 1) * sizeof(int), c.stream);
+    if (A->nnz > 0) {
+      int lpr = pick_lpr_mean(A);
+      int64_t threads = A->n_rows * lpr;
+      int g = grid_for(threads);
+      switch (lpr) {
+        case 2: IIFE_LAUNCH(k_transpose_fill<2>, g, 256, 0, A->rowptr, A->colind, A->n_rows, T->rowptr, cnt.p, T->colind, perm); break;
+        case 4: IIFE_LAUNCH(k_transpose_fill<4>, g, 256, 0, A->rowptr, A->colind, A->n_rows, T->rowptr, cnt.p, T->colind, perm); break;
+        case 8: IIFE_LAUNCH(k_transpose_fill<8>, g, 256, 0, A->rowptr, A->colind, A->n_rows, T->rowptr, cnt.p, T->colind, perm); break;
+        case 16: IIFE_LAUNCH(k_transpose_fill<16>, g, 256, 0, A->rowptr, A->colind, A->n_rows, T->rowptr, cnt.p, T->colind, perm); break;
+        default: IIFE_LAUNCH(k_transpose_fill<32>, g, 256, 0, A->rowptr, A->colind, A->n_rows, T->rowptr, cnt.p, T->colind, perm); break;
+      }
+      // order each T row by ascending column (= source row): deterministic, PETSc-like storage
+      if ((rc = long_rows.alloc((size_t)A->n_cols)) != IIFE_OK) break;
+      if ((rc = n_long.alloc(1)) != IIFE_OK) break;
+      cudaMemsetAsync(n_long.p, 0, sizeof(int), c.stream);
+      IIFE_LAUNCH(k_sort_rows_warp, grid_for(A->n_cols * 32), 256, 0, T->rowptr, T->colind, perm, A->n_cols,
+                  long_rows.p, n_long.p);
+      IIFE_LAUNCH(k_sort_rows_block, c.sm_count * 2, 512, 0, T->rowptr, T->colind, perm, long_rows.p, n_long.p);
+    }
+    cudaError_t e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) rc = set_err(IIFE_ERR_CUDA, "transpose kernels: %s", cudaGetErrorString(e));
+  } while (0);
+  if (rc != IIFE_OK) {
+    mat_free(T);
+    if (perm) dev_free_t(perm, (size_t)A->nnz);
+    return rc;
+  }
+  *T_out = T;
+  *perm_out = perm;
+  return IIFE_OK;
+}
+
+int gather_vals_launch(const double *val, const int *perm, double *out, int64_t nnz) {
+  if (nnz > 0) IIFE_LAUNCH(k_gather_vals, grid_for(nnz), 256, 0, val, perm, out, nnz);
+  IIFE_CHECK_LAUNCH();
+  return IIFE_OK;
+}
+
+int mat_ensure_transpose(Mat *A) {
+  if (!A->T) {
+    IIFE_TRY(transpose_build(A, &A->T, &A->T_perm));
+    A->T_vals_valid = false;
+  }
+  if (!A->T_vals_valid) {
+    IIFE_TRY(gather_vals_launch(A->val, A->T_perm, A->T->val, A->nnz));
+    A->T->dinv_valid = false;
+    A->T->T_vals_valid = false;
+    A->T_vals_valid = true;
+  }
+  return IIFE_OK;
+}
+
+static int launch_diag(const Mat *A, double *out, int jacobi) {
+  if (A->n_rows == 0) return IIFE_OK;
+  int lpr = pick_lpr_mean(A);
+  int g = grid_for(A->n_rows * lpr);
+  switch (lpr) {
+    case 2: IIFE_LAUNCH(k_diag<2>, g, 256, 0, A->rowptr, A->colind, A->val, A->n_rows, out, jacobi); break;
+    case 4: IIFE_LAUNCH(k_diag<4>, g, 256, 0, A->rowptr, A->colind, A->val, A->n_rows, out, jacobi); break;
+    case 8: IIFE_LAUNCH(k_diag<8>, g, 256, 0, A->rowptr, A->colind, A->val, A->n_rows, out, jacobi); break;
+    case 16: IIFE_LAUNCH(k_diag<16>, g, 256, 0, A->rowptr, A->colind, A->val, A->n_rows, out, jacobi); break;
+    default: IIFE_LAUNCH(k_diag<32>, g, 256, 0, A->rowptr, A->colind, A->val, A->n_rows, out, jacobi); break;
+  }
+  IIFE_CHECK_LAUNCH();
+  return IIFE_OK;
+}
+
+int mat_ensure_dinv(Mat *A) {
+  if (!A->dinv) IIFE_TRY(dev_alloc_t(&A->dinv, (size_t)A->n_rows));
+  if (!A->dinv_valid) {
+    IIFE_TRY(launch_diag(A, A->dinv, 1));
+    A->dinv_valid = true;
+  }
+  return IIFE_OK;
+}
+
+static int copy_in(void *dst, const void *src, size_t bytes, int mem) {
+  IIFE_CUDA(cudaMemcpyAsync(dst, src, bytes, mem == IIFE_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                            ctx().stream));
+  return IIFE_OK;
+}
+static int copy_out(void *dst, const void *src, size_t bytes, int mem) {
+  IIFE_CUDA(cudaMemcpyAsync(dst, src, bytes, mem == IIFE_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                            ctx().stream));
+  return IIFE_OK;
+}
+
+// upload an index array of idx_bytes-wide entries into an int32 device array
+static int upload_idx(int *dst, const void *src, int64_t n, int idx_bytes, int mem, int *bad_flag_dev) {
+  if (n == 0) return IIFE_OK;
+  if (idx_bytes == 4) return copy_in(dst, src, (size_t)n * 4, mem);
+  const long long *wide = (const long long *)src;
+  Tmp<long long> stage;
+  if (mem == IIFE_MEM_HOST) {
+    IIFE_TRY(stage.alloc((size_t)n));
+    IIFE_TRY(copy_in(stage.p, src, (size_t)n * 8, mem));
+    wide = stage.p;
+  }
+  IIFE_LAUNCH(k_narrow_i64, grid_for(n), 256, 0, wide, dst, n, bad_flag_dev);
+  IIFE_CHECK_LAUNCH();
+  IIFE_CUDA(cudaStreamSynchronize(ctx().stream));  // stage is freed on return
+  return IIFE_OK;
+}
+
+static int download_idx(void *dst, const int *src, int64_t n, int idx_bytes, int mem) {
+  if (n == 0) return IIFE_OK;
+  if (idx_bytes == 4) return copy_out(dst, src, (size_t)n * 4, mem);
+  if (mem == IIFE_MEM_DEVICE) {
+    IIFE_LAUNCH(k_widen_i32, grid_for(n), 256, 0, src, (long long *)dst, n);
+    IIFE_CHECK_LAUNCH();
+    return IIFE_OK;
+  }
+  Tmp<long long> stage;
+  IIFE_TRY(stage.alloc((size_t)n));
+  IIFE_LAUNCH(k_widen_i32, grid_for(n), 256, 0, src, stage.p, n);
+  IIFE_CHECK_LAUNCH();
+  IIFE_TRY(copy_out(dst, stage.p, (size_t)n * 8, mem));
+  IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+  return IIFE_OK;
+}
+
+}  // namespace iife
+
+using namespace iife;
+
+extern "C" {
+
+int iife_mat_create_csr(int64_t n_rows, int64_t n_cols, const void *rowptr, const void *colind, const double *val,
+                        int idx_bytes, int mem, iife_mat *out) {
+  IIFE_NEED_INIT();
+  if (!out) return set_err(IIFE_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (n_rows < 0 || n_cols < 0) return set_err(IIFE_ERR_ARG, "negative shape %lld x %lld", (long long)n_rows, (long long)n_cols);
+  if (n_rows >= 0x7fffffffLL || n_cols >= 0x7fffffffLL)
+    return set_err(IIFE_ERR_UNSUPPORTED, "shape %lld x %lld exceeds int32 indices", (long long)n_rows, (long long)n_cols);
+  if (idx_bytes != 4 && idx_bytes != 8) return set_err(IIFE_ERR_ARG, "idx_bytes must be 4 or 8, got %d", idx_bytes);
+  if (mem != IIFE_MEM_HOST && mem != IIFE_MEM_DEVICE) return set_err(IIFE_ERR_ARG, "bad mem %d", mem);
+  if (!rowptr) return set_err(IIFE_ERR_ARG, "rowptr is NULL");
+  // nnz = rowptr[n_rows]
+  int64_t nnz = 0;
+  {
+    const char *last = (const char *)rowptr + (size_t)n_rows * idx_bytes;
+    long long v64 = 0;
+    int v32 = 0;
+    if (mem == IIFE_MEM_HOST) {
+      if (idx_bytes == 8) v64 = *(const long long *)last; else v32 = *(const int *)last;
+    } else {
+      IIFE_CUDA(cudaMemcpyAsync(idx_bytes == 8 ? (void *)&v64 : (void *)&v32, last, idx_bytes, cudaMemcpyDeviceToHost, ctx().stream));
+      IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
+    nnz = idx_bytes == 8 ? v64 : v32;
+  }
+  if (nnz < 0) return set_err(IIFE_ERR_ARG, "rowptr[n_rows] = %lld is negative", (long long)nnz);
+  if (nnz >= 0x7fffffffLL) return set_err(IIFE_ERR_UNSUPPORTED, "nnz %lld does not fit the int32 device indices", (long long)nnz);
+  if (nnz > 0 && !colind) return set_err(IIFE_ERR_ARG, "colind is NULL");
+  Mat *A = nullptr;
+  IIFE_TRY(mat_alloc(&A, n_rows, n_cols, nnz));
+  Tmp<int> bad;
+  int rc = bad.alloc(1);
+  if (rc == IIFE_OK) {
+    cudaMemsetAsync(bad.p, 0, sizeof(int), ctx().stream);
+    rc = upload_idx(A->rowptr, rowptr, n_rows + 1, idx_bytes, mem, bad.p);
+  }
+  if (rc == IIFE_OK) rc = upload_idx(A->colind, colind, nnz, idx_bytes, mem, bad.p);
+  if (rc == IIFE_OK) {
+    if (val) rc = copy_in(A->val, val, (size_t)nnz * sizeof(double), mem);
+    else if (nnz) cudaMemsetAsync(A->val, 0, (size_t)nnz * sizeof(double), ctx().stream);
+  }
+  if (rc == IIFE_OK) {
+    IIFE_LAUNCH(k_validate_rowptr, grid_for(n_rows + 1), 256, 0, A->rowptr, n_rows, nnz, bad.p);
+    int hb = 0;
+    cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream);
+    cudaError_t e = cudaStreamSynchronize(ctx().stream);
+    if (e != cudaSuccess) rc = set_err(IIFE_ERR_CUDA, "mat_create: %s", cudaGetErrorString(e));
+    else if (hb) rc = set_err(IIFE_ERR_ARG, "malformed CSR: rowptr is not a monotone offset array ending at nnz (or an index does not fit int32)");
+  }
+  if (rc == IIFE_OK && nnz > 0) {
+    IIFE_LAUNCH(k_validate_cols, grid_for(nnz > n_rows ? nnz : n_rows), 256, 0, A->rowptr, A->colind, n_rows, n_cols, nnz, bad.p);
+    int hb = 0;
+    cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream);
+    cudaError_t e = cudaStreamSynchronize(ctx().stream);
+    if (e != cudaSuccess) rc = set_err(IIFE_ERR_CUDA, "mat_create: %s", cudaGetErrorString(e));
+    else if (hb & 2) rc = set_err(IIFE_ERR_ARG, "malformed CSR: column index out of range [0,%lld)", (long long)n_cols);
+    else if (hb & 4) rc = set_err(IIFE_ERR_ARG, "malformed CSR: column indices must be strictly ascending inside each row");
+  }
+  if (rc != IIFE_OK) {
+    mat_free(A);
+    return rc;
+  }
+  *out = (iife_mat)A;
+  return IIFE_OK;
+}
+
+int iife_mat_update_values(iife_mat A_, const double *val, int mem) {
+  IIFE_NEED_INIT();
+  Mat *A = (Mat *)A_;
+  if (!A || !val) return set_err(IIFE_ERR_ARG, "NULL argument");
+  IIFE_TRY(copy_in(A->val, val, (size_t)A->nnz * sizeof(double), mem));
+  A->T_vals_valid = false;
+  A->dinv_valid = false;
+  if (mem == IIFE_MEM_HOST) IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+  return IIFE_OK;
+}
+
+int iife_mat_get_info(iife_mat A_, int64_t *n_rows, int64_t *n_cols, int64_t *nnz) {
+  Mat *A = (Mat *)A_;
+  if (!A) return set_err(IIFE_ERR_ARG, "NULL matrix");
+  if (n_rows) *n_rows = A->n_rows;
+  if (n_cols) *n_cols = A->n_cols;
+  if (nnz) *nnz = A->nnz;
+  return IIFE_OK;
+}
+
+int iife_mat_get_csr(iife_mat A_, void *rowptr, void *colind, double *val, int idx_bytes, int mem) {
+  IIFE_NEED_INIT();
+  Mat *A = (Mat *)A_;
+  if (!A) return set_err(IIFE_ERR_ARG, "NULL matrix");
+  if (idx_bytes != 4 && idx_bytes != 8) return set_err(IIFE_ERR_ARG, "idx_bytes must be 4 or 8");
+  if (rowptr) IIFE_TRY(download_idx(rowptr, A->rowptr, A->n_rows + 1, idx_bytes, mem));
+  if (colind) IIFE_TRY(download_idx(colind, A->colind, A->nnz, idx_bytes, mem));
+  if (val && A->nnz) IIFE_TRY(copy_out(val, A->val, (size_t)A->nnz * sizeof(double), mem));
+  if (mem == IIFE_MEM_HOST) IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+  return IIFE_OK;
+}
+
+int iife_mat_device_ptrs(iife_mat A_, void **rowptr, void **colind, void **val) {
+  Mat *A = (Mat *)A_;
+  if (!A) return set_err(IIFE_ERR_ARG, "NULL matrix");
+  if (rowptr) *rowptr = A->rowptr;
+  if (colind) *colind = A->colind;
+  if (val) *val = A->val;
+  return IIFE_OK;
+}
+
+int iife_mat_fingerprint(iife_mat A_, uint64_t *fp) {
+  IIFE_NEED_INIT();
+  Mat *A = (Mat *)A_;
+  if (!A || !fp) return set_err(IIFE_ERR_ARG, "NULL argument");
+  return mat_fingerprint(A, fp);
+}
+
+int iife_mat_transpose(iife_mat A_, iife_mat *out) {
+  IIFE_NEED_INIT();
+  Mat *A = (Mat *)A_;
+  if (!A || !out) return set_err(IIFE_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  IIFE_TRY(mat_ensure_transpose(A));
+  // hand out an independent copy (the cached transpose stays owned by A)
+  Mat *T = nullptr;
+  IIFE_TRY(mat_alloc(&T, A->T->n_rows, A->T->n_cols, A->T->nnz));
+  cudaStream_t s = ctx().stream;
+  cudaMemcpyAsync(T->rowptr, A->T->rowptr, ((size_t)T->n_rows + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s);
+  if (T->nnz) {
+    cudaMemcpyAsync(T->colind, A->T->colind, (size_t)T->nnz * sizeof(int), cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(T->val, A->T->val, (size_t)T->nnz * sizeof(double), cudaMemcpyDeviceToDevice, s);
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    mat_free(T);
+    return set_err(IIFE_ERR_CUDA, "transpose copy: %s", cudaGetErrorString(e));
+  }
+  *out = (iife_mat)T;
+  return IIFE_OK;
+}
+
+int iife_mat_get_diagonal(iife_mat A_, double *diag, int mem) {
+  IIFE_NEED_INIT();
+  Mat *A = (Mat *)A_;
+  if (!A || !diag) return set_err(IIFE_ERR_ARG, "NULL argument");
+  if (mem == IIFE_MEM_DEVICE) return launch_diag(A, diag, 0);
+  Tmp<double> d;
+  IIFE_TRY(d.alloc((size_t)A->n_rows));
+  IIFE_TRY(launch_diag(A, d.p, 0));
+  IIFE_CUDA(cudaMemcpyAsync(diag, d.p, (size_t)A->n_rows * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+  IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+  return IIFE_OK;
+}
+
+int iife_mat_destroy(iife_mat A_) {
+  Mat *A = (Mat *)A_;
+  if (!A) return IIFE_OK;
+  if (ctx().init) cudaStreamSynchronize(ctx().stream);
+  return mat_free(A);
+}
+
+}  // extern "C"

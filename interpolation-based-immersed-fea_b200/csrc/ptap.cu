@@ -1,0 +1,1031 @@
+// ptap.cu — two-phase sparse Galerkin triple product A_b = M^T A_f M.
+//
+// Replaces the reference's AT_R_A (la_utils.py:165-182): two in-place MatTranspose calls and two
+// MatMatMult(MAT_INITIAL_MATRIX) calls, i.e. ((M^T) A_f) M with the intermediate M^T A_f materialised
+// and both symbolic phases redone on every call.
+//
+// Here: one output row i of A_b is owned by one *team* (a warp for ordinary rows, a whole CTA for
+// fat rows).  The team runs both products back to back and keeps the intermediate row
+// (M^T A_f)[i,:] in a hash table in shared memory, so the intermediate never touches HBM:
+//
+//   stage 1   H1[k] += Mt[i,j] * A_f[j,k]     j in Mt row i (ascending), k in A_f row j
+//   stage 2   H2[l] += H1[k]   * M[k,l]       k in H1 (table order),     l in M row k
+//   write     C.val[row i] = H2[C.col[row i]] (columns ascending, as PETSc stores them)
+//
+// Within a team, G lanes cooperate on one operand row (G = power of two near the mean row length of
+// that operand), so a warp reads 32/G operand rows per step with coalesced (colind, val) runs.
+// The symbolic phase runs the same traversal on keys only (structural product: stored zeros count,
+// numeric cancellation never removes an entry — SURVEY A.2), first counting, then filling sorted
+// column lists.  Table sizes come from a ladder of levels; a row whose table overflows at one level
+// is retried at the next, the last level keeps its tables in global memory, so any input works.
+#include "common.cuh"
+#include <list>
+
+namespace iife {
+
+constexpr int EMPTY = 0x7fffffff;
+constexpr unsigned HASH_MUL = 2654435761u;
+
+struct Level {
+  int warp_team;      // 1: one warp per row, 0: one CTA per row
+  int threads;        // CTA size
+  int log_cap1, log_cap2;  // table sizes (0 = tables in global memory, sized per plan)
+};
+
+// symbolic ladder (keys only: 4 B per slot)
+static const Level SYM_LEVELS[4] = {{1, 256, 10, 8}, {1, 128, 12, 10}, {0, 256, 15, 14}, {0, 256, 0, 0}};
+// numeric ladder (key + fp64 value: 12 B per slot); load factor <= 0.5 from the exact counts
+static const Level NUM_LEVELS[5] = {{1, 256, 8, 6}, {1, 128, 10, 8}, {0, 128, 11, 10}, {0, 256, 13, 12}, {0, 256, 0, 0}};
+constexpr int N_SYM_LEVELS = 4;
+constexpr int N_NUM_LEVELS = 5;
+
+struct Plan {
+  uint64_t fpM = 0, fpA = 0;
+  int64_t n_f = 0, n_b = 0, nnzM = 0, nnzA = 0;
+  Mat *MT = nullptr;       // explicit transpose of M (pattern + values refreshed per numeric call)
+  int *mt_perm = nullptr;  // MT.val[p] = M.val[mt_perm[p]]
+  uint64_t mt_vals_uid = 0, mt_vals_version = 0;
+  int *c_rowptr = nullptr, *c_colind = nullptr;
+  int64_t nnz_c = 0, nnz_inter = 0;
+  int *n1 = nullptr;          // exact size of the intermediate row (M^T A_f)[i,:]
+  int *bin_rows = nullptr;    // rows grouped by numeric level, ascending inside a level
+  int64_t bin_off[N_NUM_LEVELS + 1] = {0};
+  int logG1 = 4, logG2 = 2;
+  // global-memory tables of the last numeric level
+  int g_log_cap1 = 0, g_log_cap2 = 0, g_ctas = 0;
+  int *g_keys = nullptr;
+  double *g_vals = nullptr;
+  size_t g_keys_n = 0, g_vals_n = 0;
+  int *err_flag = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+template <bool WARP>
+__device__ __forceinline__ void team_sync() {
+  if (WARP) __syncwarp();
+  else __syncthreads();
+}
+
+__device__ __forceinline__ int h_insert(int *hk, unsigned mask, int shift, int key) {
+  unsigned h = ((unsigned)key * HASH_MUL) >> shift;
+  for (unsigned probes = 0; probes <= mask; ++probes) {
+    int old = ((volatile int *)hk)[h];
+    if (old == key) return (int)h;
+    if (old == EMPTY) {
+      old = atomicCAS(&hk[h], EMPTY, key);
+      if (old == EMPTY || old == key) return (int)h;
+    }
+    h = (h + 1) & mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ int h_find(const int *hk, unsigned mask, int shift, int key) {
+  unsigned h = ((unsigned)key * HASH_MUL) >> shift;
+  for (unsigned probes = 0; probes <= mask; ++probes) {
+    int cur = hk[h];
+    if (cur == key) return (int)h;
+    if (cur == EMPTY) return -1;
+    h = (h + 1) & mask;
+  }
+  return -1;
+}
+
+// Accumulate  H[c] += w_q * X[r_q, c]  over the items q = 0..n_items-1, item q = (ik[q], iw[q]).
+// Items with key EMPTY are skipped (table walked without compaction).  T threads, thread index t.
+// G = 1 << logG lanes share one item.  INSERT: keys are created on demand (CAS); otherwise the key
+// must already be in the table.  NUMERIC: values are accumulated, otherwise keys only.
+// Returns (in *fail) nonzero if an insert/find could not be served (overflow or pattern mismatch).
+template <bool WARP, bool NUMERIC, bool INSERT>
+__device__ __forceinline__ void accumulate_items(int T, int t, int n_items, const int *ik, const double *iw,
+                                                 const int *__restrict__ x_rowptr, const int *__restrict__ x_col,
+                                                 const double *__restrict__ x_val, int logG, int *hk, double *hv,
+                                                 unsigned mask, int shift, int *st_beg, int *st_len, double *st_w,
+                                                 int *fail) {
+  const int G = 1 << logG;
+  const int g = t >> logG, lg = t & (G - 1), NG = T >> logG;
+  for (int base = 0; base < n_items; base += T) {
+    int q = base + t;
+    int len = 0;
+    if (q < n_items) {
+      int r = ik[q];
+      if (r != EMPTY) {
+        int b = __ldg(x_rowptr + r);
+        len = __ldg(x_rowptr + r + 1) - b;
+        st_beg[t] = b;
+        if (NUMERIC) st_w[t] = iw[q];
+      }
+    }
+    st_len[t] = len;
+    team_sync<WARP>();
+    int cnt = min(T, n_items - base);
+    for (int it = g; it < cnt; it += NG) {
+      int l = st_len[it];
+      if (l == 0) continue;
+      int b = st_beg[it];
+      double w = NUMERIC ? st_w[it] : 0.0;
+      for (int e = lg; e < l; e += G) {
+        int c = __ldg(x_col + b + e);
+        int slot = INSERT ? h_insert(hk, mask, shift, c) : h_find(hk, mask, shift, c);
+        if (slot < 0) {
+          *fail = 1;
+        } else if (NUMERIC) {
+          atomicAdd(&hv[slot], w * __ldg(x_val + b + e));
+        }
+      }
+    }
+    team_sync<WARP>();
+  }
+}
+
+// ordered in-place compaction of a table by one warp; returns the number of occupied slots
+__device__ __forceinline__ int warp_compact(int *hk, double *hv, int cap, int lane) {
+  int n = 0;
+  for (int base = 0; base < cap; base += 32) {
+    int k = hk[base + lane];
+    double v = hv ? hv[base + lane] : 0.0;
+    unsigned m = __ballot_sync(0xffffffffu, k != EMPTY);
+    __syncwarp();
+    if (k != EMPTY) {
+      int pos = n + __popc(m & ((1u << lane) - 1u));
+      hk[pos] = k;
+      if (hv) hv[pos] = v;
+    }
+    n += __popc(m);
+    __syncwarp();
+  }
+  return n;
+}
+
+// number of occupied slots, CTA team (result in every thread)
+__device__ __forceinline__ int cta_count(const int *hk, int cap, int *scratch) {
+  int c = 0;
+  for (int s = threadIdx.x; s < cap; s += blockDim.x) c += (hk[s] != EMPTY);
+  __syncthreads();
+  if (threadIdx.x == 0) *scratch = 0;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(scratch, c);
+  __syncthreads();
+  int r = *scratch;
+  __syncthreads();
+  return r;
+}
+
+// ascending bitonic sort of a[0..P), P a power of two
+template <bool WARP>
+__device__ __forceinline__ void team_bitonic(int *a, int P, int T, int t) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int x = t; x < (P >> 1); x += T) {
+        int lo = 2 * x - (x & (stride - 1));
+        int hi = lo + stride;
+        bool asc = ((lo & size) == 0);
+        int kl = a[lo], kh = a[hi];
+        if ((kl > kh) == asc) {
+          a[lo] = kh;
+          a[hi] = kl;
+        }
+      }
+      team_sync<WARP>();
+    }
+  }
+}
+
+struct RowTables {
+  int *h1k, *h2k;
+  double *h1v, *h2v;
+  int *st_beg, *st_len;
+  double *st_w;
+  int *scratch;
+};
+
+// carve the team's tables out of dynamic shared memory (or the global workspace)
+template <bool WARP, bool NUMERIC>
+__device__ __forceinline__ RowTables carve(unsigned char *smem, int cap1, int cap2, int T, int team_in_cta,
+                                           int *g_keys, double *g_vals, int team_global) {
+  RowTables rt;
+  // per-team shared layout: [st_w T doubles][h1v cap1][h2v cap2][h1k cap1][h2k cap2][st_beg T][st_len T][scratch 2]
+  bool global_tables = (g_keys != nullptr);
+  size_t c1 = global_tables ? 0 : (size_t)cap1, c2 = global_tables ? 0 : (size_t)cap2;
+  size_t per_team = (size_t)T * 8 + (NUMERIC ? (c1 + c2) * 8 : 0) + (c1 + c2) * 4 + (size_t)T * 8 + 8;
+  per_team = (per_team + 15) & ~(size_t)15;
+  unsigned char *p = smem + per_team * team_in_cta;
+  rt.st_w = (double *)p;
+  p += (size_t)T * 8;
+  if (!global_tables) {
+    if (NUMERIC) {
+      rt.h1v = (double *)p;
+      p += c1 * 8;
+      rt.h2v = (double *)p;
+      p += c2 * 8;
+    } else {
+      rt.h1v = rt.h2v = nullptr;
+    }
+    rt.h1k = (int *)p;
+    p += c1 * 4;
+    rt.h2k = (int *)p;
+    p += c2 * 4;
+  } else {
+    rt.h1k = g_keys + (size_t)team_global * ((size_t)cap1 + cap2);
+    rt.h2k = rt.h1k + cap1;
+    rt.h1v = NUMERIC ? g_vals + (size_t)team_global * ((size_t)cap1 + cap2) : nullptr;
+    rt.h2v = NUMERIC ? rt.h1v + cap1 : nullptr;
+  }
+  rt.st_beg = (int *)p;
+  p += (size_t)T * 4;
+  rt.st_len = (int *)p;
+  p += (size_t)T * 4;
+  rt.scratch = (int *)p;
+  return rt;
+}
+
+static size_t team_smem_bytes(bool numeric, bool global_tables, int cap1, int cap2, int T) {
+  size_t c1 = global_tables ? 0 : (size_t)cap1, c2 = global_tables ? 0 : (size_t)cap2;
+  size_t per_team = (size_t)T * 8 + (numeric ? (c1 + c2) * 8 : 0) + (c1 + c2) * 4 + (size_t)T * 8 + 8;
+  return (per_team + 15) & ~(size_t)15;
+}
+
+struct PtapArgs {
+  // operands
+  const int *mt_rowptr, *mt_col;
+  const double *mt_val;
+  const int *a_rowptr, *a_col;
+  const double *a_val;
+  const int *m_rowptr, *m_col;
+  const double *m_val;
+  // output pattern / values
+  const int *c_rowptr;
+  int *c_col;
+  double *c_val;
+  // row selection
+  const int *rows;      // list of rows (nullptr: all rows 0..n_rows)
+  const int *n_list;    // device count of the list (nullptr: use n_rows)
+  int64_t n_rows;
+  // symbolic outputs
+  int *n1, *n2;         // per-row counts
+  signed char *level;   // level at which the row was resolved (symbolic)
+  int this_level;
+  int *ovf_rows, *n_ovf;  // rows to retry at the next level
+  // geometry
+  int log_cap1, log_cap2, logG1, logG2;
+  int *g_keys;
+  double *g_vals;
+  int *err_flag;
+};
+
+// ------------------------------------------------------------------------------------------------
+// symbolic kernels.  MODE 0: count (n1, n2, overflow list);  MODE 1: fill sorted C.col
+// ------------------------------------------------------------------------------------------------
+template <bool WARP, int MODE>
+__global__ void k_ptap_symbolic(PtapArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int T = WARP ? 32 : blockDim.x;
+  const int t = WARP ? (threadIdx.x & 31) : threadIdx.x;
+  const int team_in_cta = WARP ? (threadIdx.x >> 5) : 0;
+  const int teams_per_cta = WARP ? (blockDim.x >> 5) : 1;
+  const int64_t team_global = (int64_t)blockIdx.x * teams_per_cta + team_in_cta;
+  const int64_t n_teams = (int64_t)gridDim.x * teams_per_cta;
+  const int cap1 = 1 << a.log_cap1, cap2 = 1 << a.log_cap2;
+  const unsigned mask1 = cap1 - 1, mask2 = cap2 - 1;
+  const int shift1 = 32 - a.log_cap1, shift2 = 32 - a.log_cap2;
+  RowTables rt = carve<WARP, false>(smem, cap1, cap2, T, team_in_cta, a.g_keys, nullptr, (int)team_global);
+  const int64_t n_work = a.n_list ? (int64_t)*a.n_list : a.n_rows;
+
+  for (int64_t wi = team_global; wi < n_work; wi += n_teams) {
+    const int i = a.rows ? a.rows[wi] : (int)wi;
+    if (MODE == 1 && a.level[i] != a.this_level) continue;
+    if (MODE == 0 && a.rows == nullptr && a.level[i] != -1) continue;
+    const int mt_b = a.mt_rowptr[i], mt_n = a.mt_rowptr[i + 1] - mt_b;
+    if (mt_n == 0) {
+      if (MODE == 0 && t == 0) {
+        a.n1[i] = 0;
+        a.n2[i] = 0;
+        a.level[i] = (signed char)a.this_level;
+      }
+      continue;
+    }
+    for (int s = t; s < cap1; s += T) rt.h1k[s] = EMPTY;
+    for (int s = t; s < cap2; s += T) rt.h2k[s] = EMPTY;
+    if (t == 0) rt.scratch[1] = 0;
+    team_sync<WARP>();
+    // stage 1: keys of (M^T A)[i,:]
+    accumulate_items<WARP, false, true>(T, t, mt_n, a.mt_col + mt_b, nullptr, a.a_rowptr, a.a_col, nullptr, a.logG1,
+                                        rt.h1k, nullptr, mask1, shift1, rt.st_beg, rt.st_len, rt.st_w, &rt.scratch[1]);
+    int n1;
+    if (WARP) n1 = warp_compact(rt.h1k, nullptr, cap1, t);
+    else n1 = cta_count(rt.h1k, cap1, rt.scratch);
+    bool ovf = (rt.scratch[1] != 0) || (n1 > (cap1 / 4) * 3);
+    int n2 = 0;
+    if (!ovf) {
+      // stage 2: keys of ((M^T A) M)[i,:]
+      accumulate_items<WARP, false, true>(T, t, WARP ? n1 : cap1, rt.h1k, nullptr, a.m_rowptr, a.m_col, nullptr,
+                                          a.logG2, rt.h2k, nullptr, mask2, shift2, rt.st_beg, rt.st_len, rt.st_w,
+                                          &rt.scratch[1]);
+      if (WARP) n2 = warp_compact(rt.h2k, nullptr, cap2, t);
+      else n2 = cta_count(rt.h2k, cap2, rt.scratch);
+      ovf = (rt.scratch[1] != 0) || (n2 > (cap2 / 4) * 3);
+    }
+    if (MODE == 0) {
+      if (t == 0) {
+        if (ovf) {
+          a.ovf_rows[atomicAdd(a.n_ovf, 1)] = i;
+        } else {
+          a.n1[i] = n1;
+          a.n2[i] = n2;
+          a.level[i] = (signed char)a.this_level;
+        }
+      }
+    } else {
+      // sorted column list of row i
+      if (ovf) {
+        if (t == 0) atomicExch(a.err_flag, 2);
+      } else {
+        int P;
+        if (WARP) {
+          P = 32;
+          while (P < n2) P <<= 1;
+          for (int s = n2 + t; s < P; s += T) rt.h2k[s] = EMPTY;
+          team_sync<WARP>();
+        } else {
+          P = cap2;  // uncompacted table: EMPTY (= INT_MAX) sorts to the end
+        }
+        team_bitonic<WARP>(rt.h2k, P, T, t);
+        const int cb = a.c_rowptr[i];
+        if (a.c_rowptr[i + 1] - cb != n2) {
+          if (t == 0) atomicExch(a.err_flag, 3);
+        } else {
+          for (int s = t; s < n2; s += T) a.c_col[cb + s] = rt.h2k[s];
+        }
+      }
+    }
+    team_sync<WARP>();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// numeric kernel
+// ------------------------------------------------------------------------------------------------
+template <bool WARP>
+__global__ void k_ptap_numeric(PtapArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int T = WARP ? 32 : blockDim.x;
+  const int t = WARP ? (threadIdx.x & 31) : threadIdx.x;
+  const int team_in_cta = WARP ? (threadIdx.x >> 5) : 0;
+  const int teams_per_cta = WARP ? (blockDim.x >> 5) : 1;
+  const int64_t team_global = (int64_t)blockIdx.x * teams_per_cta + team_in_cta;
+  const int64_t n_teams = (int64_t)gridDim.x * teams_per_cta;
+  const int cap1 = 1 << a.log_cap1, cap2 = 1 << a.log_cap2;
+  const unsigned mask1 = cap1 - 1, mask2 = cap2 - 1;
+  const int shift1 = 32 - a.log_cap1, shift2 = 32 - a.log_cap2;
+  RowTables rt = carve<WARP, true>(smem, cap1, cap2, T, team_in_cta, a.g_keys, a.g_vals, (int)team_global);
+
+  for (int64_t wi = team_global; wi < a.n_rows; wi += n_teams) {
+    const int i = a.rows[wi];
+    const int mt_b = a.mt_rowptr[i], mt_n = a.mt_rowptr[i + 1] - mt_b;
+    const int cb = a.c_rowptr[i], n2 = a.c_rowptr[i + 1] - cb;
+    for (int s = t; s < cap1; s += T) {
+      rt.h1k[s] = EMPTY;
+      rt.h1v[s] = 0.0;
+    }
+    for (int s = t; s < cap2; s += T) {
+      rt.h2k[s] = EMPTY;
+      rt.h2v[s] = 0.0;
+    }
+    if (t == 0) rt.scratch[1] = 0;
+    team_sync<WARP>();
+    // output keys are known from the symbolic phase: stage 2 only looks them up
+    for (int s = t; s < n2; s += T)
+      if (h_insert(rt.h2k, mask2, shift2, a.c_col[cb + s]) < 0) rt.scratch[1] = 1;
+    // stage 1: H1 = sum_j Mt[i,j] A[j,:]
+    accumulate_items<WARP, true, true>(T, t, mt_n, a.mt_col + mt_b, a.mt_val + mt_b, a.a_rowptr, a.a_col, a.a_val,
+                                       a.logG1, rt.h1k, rt.h1v, mask1, shift1, rt.st_beg, rt.st_len, rt.st_w,
+                                       &rt.scratch[1]);
+    int n_items = cap1;
+    if (WARP) n_items = warp_compact(rt.h1k, rt.h1v, cap1, t);
+    // stage 2: H2 = sum_k H1[k] M[k,:]
+    accumulate_items<WARP, true, false>(T, t, n_items, rt.h1k, rt.h1v, a.m_rowptr, a.m_col, a.m_val, a.logG2,
+                                        rt.h2k, rt.h2v, mask2, shift2, rt.st_beg, rt.st_len, rt.st_w, &rt.scratch[1]);
+    for (int s = t; s < n2; s += T) {
+      int slot = h_find(rt.h2k, mask2, shift2, a.c_col[cb + s]);
+      a.c_val[cb + s] = slot >= 0 ? rt.h2v[slot] : 0.0;
+    }
+    if (t == 0 && rt.scratch[1]) atomicExch(a.err_flag, 1);
+    team_sync<WARP>();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helper kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_schar(signed char *p, int64_t n, signed char v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+// numeric level of each row from the exact counts; -1 for empty output rows
+__global__ void k_numeric_level(const int *__restrict__ n1, const int *__restrict__ n2, int64_t n,
+                                signed char *__restrict__ lvl, int c10, int c20, int c11, int c21, int c12, int c22,
+                                int c13, int c23) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int a = n1[i], b = n2[i];
+    signed char l;
+    if (b == 0) l = -1;
+    else if (2 * a <= c10 && 2 * b <= c20) l = 0;
+    else if (2 * a <= c11 && 2 * b <= c21) l = 1;
+    else if (2 * a <= c12 && 2 * b <= c22) l = 2;
+    else if (2 * a <= c13 && 2 * b <= c23) l = 3;
+    else l = 4;
+    lvl[i] = l;
+  }
+}
+
+__global__ void k_level_flag(const signed char *__restrict__ lvl, int64_t n, int which, int *__restrict__ flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) flag[i] = (lvl[i] == which);
+}
+
+__global__ void k_level_scatter(const signed char *__restrict__ lvl, const int *__restrict__ off, int64_t n, int which,
+                                int *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    if (lvl[i] == which) out[off[i]] = (int)i;
+}
+
+// max and sum of selected counts
+__global__ void k_list_max(const int *__restrict__ v, const int *__restrict__ rows, int64_t n, int *__restrict__ out) {
+  int m = 0;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) m = max(m, v[rows ? rows[i] : i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+__global__ void k_sum_i32(const int *__restrict__ v, int64_t n, unsigned long long *__restrict__ out) {
+  unsigned long long s = 0;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) s += (unsigned long long)v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// upper bound of the intermediate row size for listed rows: sum of A row lengths over Mt row
+__global__ void k_ub1_list(const int *__restrict__ mt_rowptr, const int *__restrict__ mt_col,
+                           const int *__restrict__ a_rowptr, const int *__restrict__ rows, int n,
+                           unsigned long long *__restrict__ out_max) {
+  for (int r = blockIdx.x; r < n; r += gridDim.x) {
+    int i = rows[r];
+    unsigned long long s = 0;
+    for (int q = mt_rowptr[i] + threadIdx.x; q < mt_rowptr[i + 1]; q += blockDim.x) {
+      int j = mt_col[q];
+      s += (unsigned long long)(a_rowptr[j + 1] - a_rowptr[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __shared__ unsigned long long acc;
+    if (threadIdx.x == 0) acc = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicAdd(&acc, s);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(out_max, acc);
+    __syncthreads();
+  }
+}
+
+static int grid_for(int64_t n, int threads = 256) {
+  int64_t g = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)ctx().sm_count * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static int log2_ceil(int64_t v) {
+  int l = 0;
+  while (((int64_t)1 << l) < v) ++l;
+  return l;
+}
+
+// mean length of the NON-EMPTY rows decides G (M has many empty rows in real data)
+__global__ void k_count_nonempty(const int *__restrict__ rowptr, int64_t n, unsigned long long *__restrict__ out) {
+  unsigned long long s = 0;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) s += (rowptr[i + 1] > rowptr[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+static int mean_nonempty_logG(const Mat *X, int *logG) {
+  Tmp<unsigned long long> d;
+  IIFE_TRY(d.alloc(1));
+  IIFE_CUDA(cudaMemsetAsync(d.p, 0, 8, ctx().stream));
+  if (X->n_rows) IIFE_LAUNCH(k_count_nonempty, grid_for(X->n_rows), 256, 0, X->rowptr, X->n_rows, d.p);
+  IIFE_CHECK_LAUNCH();
+  unsigned long long h = 0;
+  IIFE_CUDA(cudaMemcpyAsync(&h, d.p, 8, cudaMemcpyDeviceToHost, ctx().stream));
+  IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+  double mean = h ? (double)X->nnz / (double)h : 1.0;
+  int l = 1;
+  while ((1 << l) < mean && l < 5) ++l;
+  *logG = l;
+  return IIFE_OK;
+}
+
+int transpose_build(const Mat *A, Mat **T_out, int **perm_out);  // mat.cu
+
+static int plan_free(Plan *P) {
+  if (!P) return IIFE_OK;
+  if (P->MT) mat_free(P->MT);
+  if (P->mt_perm) dev_free_t(P->mt_perm, (size_t)P->nnzM);
+  if (P->c_rowptr) dev_free_t(P->c_rowptr, (size_t)P->n_b + 1);
+  if (P->c_colind) dev_free_t(P->c_colind, (size_t)P->nnz_c);
+  if (P->n1) dev_free_t(P->n1, (size_t)P->n_b);
+  if (P->bin_rows) dev_free_t(P->bin_rows, (size_t)P->n_b);
+  if (P->g_keys) dev_free_t(P->g_keys, P->g_keys_n);
+  if (P->g_vals) dev_free_t(P->g_vals, P->g_vals_n);
+  if (P->err_flag) dev_free_t(P->err_flag, 1);
+  delete P;
+  return IIFE_OK;
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) IIFE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return IIFE_OK;
+}
+
+static int read_int(const int *dev, int *host) {
+  IIFE_CUDA(cudaMemcpyAsync(host, dev, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+  IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+  return IIFE_OK;
+}
+
+// launch one symbolic level.  mode 0 count / 1 fill
+static int launch_symbolic(const Level &L, int mode, PtapArgs &a, int64_t n_work_host, size_t g_keys_per_team,
+                           int *ctas_out) {
+  Ctx &c = ctx();
+  bool global_tables = (L.log_cap1 == 0);
+  int teams_per_cta = L.warp_team ? L.threads / 32 : 1;
+  int T = L.warp_team ? 32 : L.threads;
+  size_t smem = team_smem_bytes(false, global_tables, 1 << a.log_cap1, 1 << a.log_cap2, T) * teams_per_cta;
+  int max_ctas_sm = (int)((size_t)(c.max_smem_optin ? c.max_smem_optin : 227 * 1024) / (smem + 1024));
+  if (max_ctas_sm < 1) return set_err(IIFE_ERR_UNSUPPORTED, "symbolic level needs %zu bytes of shared memory", smem);
+  int by_threads = 2048 / L.threads;
+  if (max_ctas_sm > by_threads) max_ctas_sm = by_threads;
+  int64_t ctas = (n_work_host + teams_per_cta - 1) / teams_per_cta;
+  int64_t cap = (int64_t)c.sm_count * max_ctas_sm;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  if (global_tables && ctas_out && *ctas_out > 0 && ctas > *ctas_out) ctas = *ctas_out;
+  (void)g_keys_per_team;
+  if (L.warp_team) {
+    if (mode == 0) {
+      IIFE_TRY(set_smem(k_ptap_symbolic<true, 0>, smem));
+      IIFE_LAUNCH((k_ptap_symbolic<true, 0>), (int)ctas, L.threads, smem, a);
+    } else {
+      IIFE_TRY(set_smem(k_ptap_symbolic<true, 1>, smem));
+      IIFE_LAUNCH((k_ptap_symbolic<true, 1>), (int)ctas, L.threads, smem, a);
+    }
+  } else {
+    if (mode == 0) {
+      IIFE_TRY(set_smem(k_ptap_symbolic<false, 0>, smem));
+      IIFE_LAUNCH((k_ptap_symbolic<false, 0>), (int)ctas, L.threads, smem, a);
+    } else {
+      IIFE_TRY(set_smem(k_ptap_symbolic<false, 1>, smem));
+      IIFE_LAUNCH((k_ptap_symbolic<false, 1>), (int)ctas, L.threads, smem, a);
+    }
+  }
+  IIFE_CHECK_LAUNCH();
+  if (ctas_out) *ctas_out = (int)ctas;
+  return IIFE_OK;
+}
+
+static int ptap_symbolic_impl(Mat *M, Mat *A, Plan **out) {
+  Ctx &c = ctx();
+  if (M->n_rows != A->n_rows || A->n_rows != A->n_cols)
+    return set_err(IIFE_ERR_ARG, "PtAP shape mismatch: M is %lld x %lld, A is %lld x %lld", (long long)M->n_rows,
+                   (long long)M->n_cols, (long long)A->n_rows, (long long)A->n_cols);
+  Plan *P = new Plan();
+  P->n_f = M->n_rows;
+  P->n_b = M->n_cols;
+  P->nnzM = M->nnz;
+  P->nnzA = A->nnz;
+  int rc = IIFE_OK;
+  const int64_t n_b = P->n_b;
+  Tmp<int> n2, ovf_a, ovf_b, n_ovf, flag, off;
+  Tmp<signed char> level, nlevel;
+  Tmp<int> sym_keys;  // global tables of the last symbolic level
+  Tmp<unsigned long long> u64;
+  std::vector<int> level_list_n(N_SYM_LEVELS, 0);
+  do {
+    if ((rc = mat_fingerprint(M, &P->fpM)) != IIFE_OK) break;
+    if ((rc = mat_fingerprint(A, &P->fpA)) != IIFE_OK) break;
+    if ((rc = transpose_build(M, &P->MT, &P->mt_perm)) != IIFE_OK) break;
+    if ((rc = mean_nonempty_logG(A, &P->logG1)) != IIFE_OK) break;
+    if ((rc = mean_nonempty_logG(M, &P->logG2)) != IIFE_OK) break;
+    if ((rc = dev_alloc_t(&P->n1, (size_t)n_b)) != IIFE_OK) break;
+    if ((rc = dev_alloc_t(&P->c_rowptr, (size_t)n_b + 1)) != IIFE_OK) break;
+    if ((rc = dev_alloc_t(&P->err_flag, 1)) != IIFE_OK) break;
+    if ((rc = n2.alloc((size_t)n_b + 1)) != IIFE_OK) break;
+    if ((rc = level.alloc((size_t)n_b)) != IIFE_OK) break;
+    if ((rc = ovf_a.alloc((size_t)n_b)) != IIFE_OK) break;
+    if ((rc = ovf_b.alloc((size_t)n_b)) != IIFE_OK) break;
+    if ((rc = n_ovf.alloc(2)) != IIFE_OK) break;
+    if ((rc = u64.alloc(1)) != IIFE_OK) break;
+    cudaMemsetAsync(P->err_flag, 0, sizeof(int), c.stream);
+    cudaMemsetAsync(n_ovf.p, 0, 2 * sizeof(int), c.stream);
+    cudaMemsetAsync(n2.p, 0, ((size_t)n_b + 1) * sizeof(int), c.stream);
+    cudaMemsetAsync(P->n1, 0, (size_t)(n_b ? n_b : 1) * sizeof(int), c.stream);
+    if (n_b) IIFE_LAUNCH(k_fill_schar, grid_for(n_b), 256, 0, level.p, n_b, (signed char)-1);
+
+    PtapArgs a{};
+    a.mt_rowptr = P->MT->rowptr;
+    a.mt_col = P->MT->colind;
+    a.mt_val = nullptr;
+    a.a_rowptr = A->rowptr;
+    a.a_col = A->colind;
+    a.a_val = nullptr;
+    a.m_rowptr = M->rowptr;
+    a.m_col = M->colind;
+    a.m_val = nullptr;
+    a.n1 = P->n1;
+    a.n2 = n2.p;
+    a.level = level.p;
+    a.logG1 = P->logG1;
+    a.logG2 = P->logG2;
+    a.err_flag = P->err_flag;
+
+    // ---- count pass down the ladder
+    int *lists[2] = {ovf_a.p, ovf_b.p};
+    int *level_lists[N_SYM_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
+    // the overflow list of level l is the work list of level l+1; lists of levels >= 1 must survive
+    // until the fill pass, so each gets its own buffer (ovf_a for level 1; levels 2, 3 reuse ovf_b
+    // halves — a level-2 list can never be longer than the level-1 list).
+    int64_t work = n_b;
+    int sym_g_log1 = 0, sym_g_log2 = 0, sym_g_ctas = 0;
+    Tmp<int> list2, list3;
+    for (int l = 0; l < N_SYM_LEVELS && work > 0; ++l) {
+      const Level &L = SYM_LEVELS[l];
+      a.this_level = l;
+      a.rows = l == 0 ? nullptr : level_lists[l];
+      a.n_list = nullptr;
+      a.n_rows = work;
+      a.g_keys = nullptr;
+      a.log_cap1 = L.log_cap1;
+      a.log_cap2 = L.log_cap2;
+      int ctas = 0;
+      if (L.log_cap1 == 0) {
+        // global tables: size from an upper bound of the intermediate row and from n_b
+        cudaMemsetAsync(u64.p, 0, 8, c.stream);
+        IIFE_LAUNCH(k_ub1_list, (int)(work < 1024 ? work : 1024), 256, 0, P->MT->rowptr, P->MT->colind, A->rowptr, a.rows, (int)work, u64.p);
+        unsigned long long ub = 0;
+        cudaMemcpyAsync(&ub, u64.p, 8, cudaMemcpyDeviceToHost, c.stream);
+        if (cudaStreamSynchronize(c.stream) != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "ub1: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        int64_t b1 = (int64_t)ub < P->n_f ? (int64_t)ub : P->n_f;
+        sym_g_log1 = log2_ceil(2 * b1 + 2);
+        sym_g_log2 = log2_ceil(2 * n_b + 2);
+        if (sym_g_log1 > 30 || sym_g_log2 > 30) { rc = set_err(IIFE_ERR_UNSUPPORTED, "PtAP row too large for the global hash level"); break; }
+        size_t per_team = ((size_t)1 << sym_g_log1) + ((size_t)1 << sym_g_log2);
+        size_t budget = (size_t)4 << 30;  // 4 GiB of table workspace at most
+        int64_t teams = (int64_t)(budget / (per_team * 4));
+        if (teams < 1) teams = 1;
+        if (teams > work) teams = work;
+        if (teams > c.sm_count * 2) teams = c.sm_count * 2;
+        if ((rc = sym_keys.alloc(per_team * (size_t)teams)) != IIFE_OK) break;
+        a.g_keys = sym_keys.p;
+        a.log_cap1 = sym_g_log1;
+        a.log_cap2 = sym_g_log2;
+        sym_g_ctas = (int)teams;
+        ctas = sym_g_ctas;
+      }
+      // overflow destination
+      int *dst = nullptr;
+      if (l + 1 < N_SYM_LEVELS) {
+        if (l == 0) dst = ovf_a.p;
+        else if (l == 1) { if ((rc = list2.alloc((size_t)work)) != IIFE_OK) break; dst = list2.p; }
+        else { if ((rc = list3.alloc((size_t)work)) != IIFE_OK) break; dst = list3.p; }
+      } else {
+        dst = lists[1];  // last level cannot overflow by construction; any report is an error
+      }
+      a.ovf_rows = dst;
+      a.n_ovf = n_ovf.p;
+      cudaMemsetAsync(n_ovf.p, 0, sizeof(int), c.stream);
+      if ((rc = launch_symbolic(L, 0, a, work, 0, &ctas)) != IIFE_OK) break;
+      int h_ovf = 0;
+      if ((rc = read_int(n_ovf.p, &h_ovf)) != IIFE_OK) break;
+      level_list_n[l] = (int)work;
+      if (l + 1 < N_SYM_LEVELS) level_lists[l + 1] = dst;
+      else if (h_ovf) { rc = set_err(IIFE_ERR_STATE, "PtAP symbolic: %d rows overflowed the global level", h_ovf); break; }
+      work = h_ovf;
+    }
+    if (rc != IIFE_OK) break;
+
+    // ---- row pointers of C
+    int64_t total = 0;
+    if ((rc = exclusive_scan_i32(n2.p, P->c_rowptr, n_b, &total)) != IIFE_OK) break;
+    P->nnz_c = total;
+    if ((rc = dev_alloc_t(&P->c_colind, (size_t)total)) != IIFE_OK) break;
+    cudaMemsetAsync(u64.p, 0, 8, c.stream);
+    if (n_b) IIFE_LAUNCH(k_sum_i32, grid_for(n_b), 256, 0, P->n1, n_b, u64.p);
+    {
+      unsigned long long s = 0;
+      cudaMemcpyAsync(&s, u64.p, 8, cudaMemcpyDeviceToHost, c.stream);
+      cudaStreamSynchronize(c.stream);
+      P->nnz_inter = (int64_t)s;
+    }
+
+    // ---- fill pass: same traversal, same level per row, sorted columns written
+    a.c_rowptr = P->c_rowptr;
+    a.c_col = P->c_colind;
+    for (int l = 0; l < N_SYM_LEVELS; ++l) {
+      if (level_list_n[l] == 0) continue;
+      const Level &L = SYM_LEVELS[l];
+      a.this_level = l;
+      a.rows = l == 0 ? nullptr : level_lists[l];
+      a.n_list = nullptr;
+      a.n_rows = level_list_n[l];
+      a.g_keys = nullptr;
+      a.log_cap1 = L.log_cap1;
+      a.log_cap2 = L.log_cap2;
+      int ctas = 0;
+      if (L.log_cap1 == 0) {
+        a.g_keys = sym_keys.p;
+        a.log_cap1 = sym_g_log1;
+        a.log_cap2 = sym_g_log2;
+        ctas = sym_g_ctas;
+      }
+      if ((rc = launch_symbolic(L, 1, a, a.n_rows, 0, &ctas)) != IIFE_OK) break;
+    }
+    if (rc != IIFE_OK) break;
+    int h_err = 0;
+    if ((rc = read_int(P->err_flag, &h_err)) != IIFE_OK) break;
+    if (h_err) { rc = set_err(IIFE_ERR_STATE, "PtAP symbolic fill pass inconsistent with count pass (code %d)", h_err); break; }
+
+    // ---- numeric row bins from the exact counts
+    if ((rc = nlevel.alloc((size_t)n_b)) != IIFE_OK) break;
+    if ((rc = flag.alloc((size_t)n_b + 1)) != IIFE_OK) break;
+    if ((rc = off.alloc((size_t)n_b + 1)) != IIFE_OK) break;
+    if ((rc = dev_alloc_t(&P->bin_rows, (size_t)n_b)) != IIFE_OK) break;
+    if (n_b)
+      IIFE_LAUNCH(k_numeric_level, grid_for(n_b), 256, 0, P->n1, n2.p, n_b, nlevel.p, 1 << NUM_LEVELS[0].log_cap1,
+                  1 << NUM_LEVELS[0].log_cap2, 1 << NUM_LEVELS[1].log_cap1, 1 << NUM_LEVELS[1].log_cap2,
+                  1 << NUM_LEVELS[2].log_cap1, 1 << NUM_LEVELS[2].log_cap2, 1 << NUM_LEVELS[3].log_cap1,
+                  1 << NUM_LEVELS[3].log_cap2);
+    P->bin_off[0] = 0;
+    for (int l = 0; l < N_NUM_LEVELS; ++l) {
+      int64_t cnt = 0;
+      if (n_b) {
+        IIFE_LAUNCH(k_level_flag, grid_for(n_b), 256, 0, nlevel.p, n_b, l, flag.p);
+        if ((rc = exclusive_scan_i32(flag.p, off.p, n_b, &cnt)) != IIFE_OK) break;
+        if (cnt) IIFE_LAUNCH(k_level_scatter, grid_for(n_b), 256, 0, nlevel.p, off.p, n_b, l, P->bin_rows + P->bin_off[l]);
+      }
+      P->bin_off[l + 1] = P->bin_off[l] + cnt;
+    }
+    if (rc != IIFE_OK) break;
+    // global tables of the last numeric level
+    int64_t n_last = P->bin_off[N_NUM_LEVELS] - P->bin_off[N_NUM_LEVELS - 1];
+    if (n_last > 0) {
+      const int *rows = P->bin_rows + P->bin_off[N_NUM_LEVELS - 1];
+      int m1 = 0, m2 = 0;
+      cudaMemsetAsync(n_ovf.p, 0, 2 * sizeof(int), c.stream);
+      IIFE_LAUNCH(k_list_max, grid_for(n_last), 256, 0, P->n1, rows, n_last, n_ovf.p);
+      IIFE_LAUNCH(k_list_max, grid_for(n_last), 256, 0, n2.p, rows, n_last, n_ovf.p + 1);
+      if ((rc = read_int(n_ovf.p, &m1)) != IIFE_OK) break;
+      if ((rc = read_int(n_ovf.p + 1, &m2)) != IIFE_OK) break;
+      P->g_log_cap1 = log2_ceil(2 * (int64_t)m1 + 2);
+      P->g_log_cap2 = log2_ceil(2 * (int64_t)m2 + 2);
+      size_t per_team = ((size_t)1 << P->g_log_cap1) + ((size_t)1 << P->g_log_cap2);
+      size_t budget = (size_t)4 << 30;
+      int64_t teams = (int64_t)(budget / (per_team * 12));
+      if (teams < 1) teams = 1;
+      if (teams > n_last) teams = n_last;
+      if (teams > c.sm_count * 2) teams = c.sm_count * 2;
+      P->g_ctas = (int)teams;
+      P->g_keys_n = per_team * (size_t)teams;
+      P->g_vals_n = per_team * (size_t)teams;
+      if ((rc = dev_alloc_t(&P->g_keys, P->g_keys_n)) != IIFE_OK) break;
+      if ((rc = dev_alloc_t(&P->g_vals, P->g_vals_n)) != IIFE_OK) break;
+    }
+    cudaError_t e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) rc = set_err(IIFE_ERR_CUDA, "PtAP symbolic: %s", cudaGetErrorString(e));
+  } while (0);
+  if (rc != IIFE_OK) {
+    cudaStreamSynchronize(c.stream);
+    plan_free(P);
+    return rc;
+  }
+  *out = P;
+  return IIFE_OK;
+}
+
+int gather_vals_launch(const double *val, const int *perm, double *out, int64_t nnz);  // mat.cu
+
+static int ptap_numeric_impl(Plan *P, Mat *M, Mat *A, Mat **C_io) {
+  Ctx &c = ctx();
+  if (M->n_rows != P->n_f || M->n_cols != P->n_b || M->nnz != P->nnzM || A->n_rows != P->n_f || A->nnz != P->nnzA)
+    return set_err(IIFE_ERR_STATE, "PtAP numeric: operands do not match the symbolic plan (shape/nnz)");
+  Mat *C = *C_io;
+  bool created = false;
+  if (!C) {
+    IIFE_TRY(mat_alloc(&C, P->n_b, P->n_b, P->nnz_c));
+    created = true;
+    cudaMemcpyAsync(C->rowptr, P->c_rowptr, ((size_t)P->n_b + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c.stream);
+    if (P->nnz_c) cudaMemcpyAsync(C->colind, P->c_colind, (size_t)P->nnz_c * sizeof(int), cudaMemcpyDeviceToDevice, c.stream);
+  } else if (C->n_rows != P->n_b || C->nnz != P->nnz_c) {
+    return set_err(IIFE_ERR_STATE, "PtAP numeric: result matrix does not match the plan");
+  }
+  int rc = IIFE_OK;
+  do {
+    // refresh the values of M^T unless they are already those of this M
+    if ((rc = gather_vals_launch(M->val, P->mt_perm, P->MT->val, P->nnzM)) != IIFE_OK) break;
+    PtapArgs a{};
+    a.mt_rowptr = P->MT->rowptr;
+    a.mt_col = P->MT->colind;
+    a.mt_val = P->MT->val;
+    a.a_rowptr = A->rowptr;
+    a.a_col = A->colind;
+    a.a_val = A->val;
+    a.m_rowptr = M->rowptr;
+    a.m_col = M->colind;
+    a.m_val = M->val;
+    a.c_rowptr = P->c_rowptr;
+    a.c_col = P->c_colind;
+    a.c_val = C->val;
+    a.logG1 = P->logG1;
+    a.logG2 = P->logG2;
+    a.err_flag = P->err_flag;
+    for (int l = 0; l < N_NUM_LEVELS; ++l) {
+      int64_t cnt = P->bin_off[l + 1] - P->bin_off[l];
+      if (cnt == 0) continue;
+      const Level &L = NUM_LEVELS[l];
+      bool global_tables = (L.log_cap1 == 0);
+      a.rows = P->bin_rows + P->bin_off[l];
+      a.n_rows = cnt;
+      a.log_cap1 = global_tables ? P->g_log_cap1 : L.log_cap1;
+      a.log_cap2 = global_tables ? P->g_log_cap2 : L.log_cap2;
+      a.g_keys = global_tables ? P->g_keys : nullptr;
+      a.g_vals = global_tables ? P->g_vals : nullptr;
+      int teams_per_cta = L.warp_team ? L.threads / 32 : 1;
+      int T = L.warp_team ? 32 : L.threads;
+      size_t smem = team_smem_bytes(true, global_tables, 1 << a.log_cap1, 1 << a.log_cap2, T) * teams_per_cta;
+      int max_ctas_sm = (int)((size_t)(c.max_smem_optin ? c.max_smem_optin : 227 * 1024) / (smem + 1024));
+      if (max_ctas_sm < 1) { rc = set_err(IIFE_ERR_UNSUPPORTED, "numeric level %d needs %zu B of shared memory", l, smem); break; }
+      int by_threads = 2048 / L.threads;
+      if (max_ctas_sm > by_threads) max_ctas_sm = by_threads;
+      int64_t ctas = (cnt + teams_per_cta - 1) / teams_per_cta;
+      int64_t cap = (int64_t)c.sm_count * max_ctas_sm;
+      if (ctas > cap) ctas = cap;
+      if (global_tables && ctas > P->g_ctas) ctas = P->g_ctas;
+      if (L.warp_team) {
+        if ((rc = set_smem(k_ptap_numeric<true>, smem)) != IIFE_OK) break;
+        IIFE_LAUNCH(k_ptap_numeric<true>, (int)ctas, L.threads, smem, a);
+      } else {
+        if ((rc = set_smem(k_ptap_numeric<false>, smem)) != IIFE_OK) break;
+        IIFE_LAUNCH(k_ptap_numeric<false>, (int)ctas, L.threads, smem, a);
+      }
+    }
+    if (rc != IIFE_OK) break;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "PtAP numeric launch: %s", cudaGetErrorString(e)); break; }
+    C->T_vals_valid = false;
+    C->dinv_valid = false;
+  } while (0);
+  if (rc != IIFE_OK) {
+    if (created) mat_free(C);
+    return rc;
+  }
+  *C_io = C;
+  return IIFE_OK;
+}
+
+// LRU cache of plans for the handle-less AT_R_A entry point
+struct CacheEntry {
+  uint64_t fpM, fpA;
+  Plan *plan;
+};
+static std::list<CacheEntry> g_cache;
+constexpr size_t CACHE_MAX = 8;
+
+}  // namespace iife
+
+using namespace iife;
+
+extern "C" {
+
+int iife_ptap_symbolic(iife_mat M_, iife_mat A_, iife_plan *out) {
+  IIFE_NEED_INIT();
+  if (!M_ || !A_ || !out) return set_err(IIFE_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  Plan *P = nullptr;
+  IIFE_TRY(ptap_symbolic_impl((Mat *)M_, (Mat *)A_, &P));
+  *out = (iife_plan)P;
+  return IIFE_OK;
+}
+
+int iife_plan_matches(iife_plan P_, iife_mat M_, iife_mat A_, int *matches) {
+  IIFE_NEED_INIT();
+  Plan *P = (Plan *)P_;
+  if (!P || !M_ || !A_ || !matches) return set_err(IIFE_ERR_ARG, "NULL argument");
+  uint64_t fm = 0, fa = 0;
+  IIFE_TRY(mat_fingerprint((Mat *)M_, &fm));
+  IIFE_TRY(mat_fingerprint((Mat *)A_, &fa));
+  *matches = (fm == P->fpM && fa == P->fpA) ? 1 : 0;
+  return IIFE_OK;
+}
+
+int iife_plan_get_info(iife_plan P_, int64_t *n_b, int64_t *nnz_c, int64_t *nnz_inter) {
+  Plan *P = (Plan *)P_;
+  if (!P) return set_err(IIFE_ERR_ARG, "NULL plan");
+  if (n_b) *n_b = P->n_b;
+  if (nnz_c) *nnz_c = P->nnz_c;
+  if (nnz_inter) *nnz_inter = P->nnz_inter;
+  return IIFE_OK;
+}
+
+int iife_ptap_numeric(iife_plan P_, iife_mat M_, iife_mat A_, iife_mat *C) {
+  IIFE_NEED_INIT();
+  if (!P_ || !M_ || !A_ || !C) return set_err(IIFE_ERR_ARG, "NULL argument");
+  Mat *Cm = (Mat *)*C;
+  IIFE_TRY(ptap_numeric_impl((Plan *)P_, (Mat *)M_, (Mat *)A_, &Cm));
+  *C = (iife_mat)Cm;
+  return IIFE_OK;
+}
+
+int iife_plan_check(iife_plan P_) {
+  IIFE_NEED_INIT();
+  Plan *P = (Plan *)P_;
+  if (!P) return set_err(IIFE_ERR_ARG, "NULL plan");
+  int h = 0;
+  IIFE_CUDA(cudaMemcpyAsync(&h, P->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+  IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+  if (h) {
+    cudaMemsetAsync(P->err_flag, 0, sizeof(int), ctx().stream);
+    return set_err(IIFE_ERR_STATE, "PtAP numeric: a product term had no slot in the plan's pattern (code %d): operands do not match the plan", h);
+  }
+  return IIFE_OK;
+}
+
+int iife_plan_destroy(iife_plan P_) {
+  Plan *P = (Plan *)P_;
+  if (!P) return IIFE_OK;
+  if (ctx().init) cudaStreamSynchronize(ctx().stream);
+  for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+    if (it->plan == P) {
+      g_cache.erase(it);
+      break;
+    }
+  return plan_free(P);
+}
+
+int iife_ptap(iife_mat M_, iife_mat A_, iife_mat *C, int *plan_was_cached) {
+  IIFE_NEED_INIT();
+  if (!M_ || !A_ || !C) return set_err(IIFE_ERR_ARG, "NULL argument");
+  *C = nullptr;
+  Mat *M = (Mat *)M_, *A = (Mat *)A_;
+  uint64_t fm = 0, fa = 0;
+  IIFE_TRY(mat_fingerprint(M, &fm));
+  IIFE_TRY(mat_fingerprint(A, &fa));
+  Plan *P = nullptr;
+  for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+    if (it->fpM == fm && it->fpA == fa) {
+      P = it->plan;
+      g_cache.splice(g_cache.begin(), g_cache, it);
+      break;
+    }
+  if (plan_was_cached) *plan_was_cached = P ? 1 : 0;
+  if (!P) {
+    IIFE_TRY(ptap_symbolic_impl(M, A, &P));
+    g_cache.push_front({fm, fa, P});
+    while (g_cache.size() > CACHE_MAX) {
+      plan_free(g_cache.back().plan);
+      g_cache.pop_back();
+    }
+  }
+  Mat *Cm = nullptr;
+  IIFE_TRY(ptap_numeric_impl(P, M, A, &Cm));
+  *C = (iife_mat)Cm;
+  return IIFE_OK;
+}
+
+int iife_plan_cache_clear(void) {
+  if (ctx().init) cudaStreamSynchronize(ctx().stream);
+  for (auto &e : g_cache) plan_free(e.plan);
+  g_cache.clear();
+  return IIFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,367 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same inputs.
+
+Bars (BASELINE.json north_star): sparsity pattern of A_b bit-exact; values within 1e-12 relative,
+measured as |dC_ij| <= 1e-12 * (|M|^T |A_f| |M|)_ij (per-entry relative error is meaningless on
+structurally present, numerically cancelled entries — SURVEY.md §8c); solutions within 1e-8 relative
+at matched KSP tolerances; integer/index work bit-exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import rand_csr
+
+pytestmark = pytest.mark.gpu
+
+VAL_TOL = 1e-12
+SOL_TOL = 1e-8
+
+
+def ocsr(O, n_rows, n_cols, t):
+    return O.CSR(n_rows, n_cols, t[0], t[1], t[2])
+
+
+def dmat(I, A):
+    return I.DeviceMat.from_csr(A.n_rows, A.n_cols, A.rowptr, A.colind, A.val)
+
+
+def abs_csr(O, A):
+    return O.CSR(A.n_rows, A.n_cols, A.rowptr, A.colind, np.abs(A.val))
+
+
+def check_ptap(I, O, M, A, plan=None):
+    """Runs the CUDA PtAP and the oracle on (M, A); asserts pattern identity and the value bound."""
+    dM, dA = dmat(I, M), dmat(I, A)
+    own = plan is None
+    if own:
+        plan = I.PtapPlan(dM, dA)
+    dC = plan.numeric(dM, dA, check_errors=True)
+    rp, ci, v = dC.to_csr(np.int64)
+    C, ATR = O.AT_R_A(M, A, return_intermediate=True)
+    assert np.array_equal(rp, C.rowptr), "row pointers of A_b differ from the structural product"
+    assert np.array_equal(ci, C.colind.astype(np.int64)), "column indices of A_b differ"
+    info = plan.info()
+    assert info["nnz_c"] == C.nnz and info["nnz_intermediate"] == ATR.nnz and info["n_b"] == M.n_cols
+    bound = O.AT_R_A(abs_csr(O, M), abs_csr(O, A))
+    assert np.array_equal(bound.colind, C.colind)
+    err = np.abs(v - C.val)
+    assert np.all(err <= VAL_TOL * bound.val + 1e-300), f"max scaled error {np.max(err / (bound.val + 1e-300))}"
+    nf = np.linalg.norm(C.val)
+    assert np.linalg.norm(v - C.val) <= VAL_TOL * nf + 1e-300
+    return dM, dA, dC, C, plan
+
+
+def test_library_is_native(iife):
+    assert iife.device_count() >= 1
+    assert iife.LIB_PATH.endswith("libiife.so")
+    n0 = iife.launch_count(reset=True)
+    A = iife.DeviceMat.from_csr(2, 2, np.array([0, 1, 2]), np.array([0, 1]), np.array([1.0, 2.0]))
+    y = A.spmv(np.array([1.0, 1.0]))
+    assert np.array_equal(y, [1.0, 2.0])
+    assert iife.launch_count() > 0
+
+
+def test_mat_roundtrip_and_validation(iife):
+    rng = np.random.default_rng(0)
+    for dt in (np.int32, np.int64):
+        rp, ci, v = rand_csr(rng, 300, 211, 5, empty_frac=0.3, dtype=dt)
+        A = iife.DeviceMat.from_csr(300, 211, rp, ci, v)
+        assert A.shape == (300, 211) and A.nnz == len(v)
+        for odt in (np.int32, np.int64):
+            rp2, ci2, v2 = A.to_csr(odt)
+            assert np.array_equal(rp2, rp) and np.array_equal(ci2, ci) and np.array_equal(v2, v)
+    # empty matrix, empty rows
+    E = iife.DeviceMat.from_csr(4, 3, np.zeros(5, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0))
+    assert E.nnz == 0 and np.array_equal(E.spmv(np.ones(3)), np.zeros(4))
+    Z = iife.DeviceMat.from_csr(0, 0, np.zeros(1, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0))
+    assert Z.shape == (0, 0)
+    # malformed inputs are refused with IIFE_ERR_ARG
+    with pytest.raises(iife.IifeError):
+        iife.DeviceMat.from_csr(2, 2, np.array([0, 2, 1]), np.array([0, 1]), np.array([1.0, 2.0]))
+    with pytest.raises(iife.IifeError):
+        iife.DeviceMat.from_csr(2, 2, np.array([0, 1, 2]), np.array([0, 5]), np.array([1.0, 2.0]))
+    with pytest.raises(iife.IifeError):
+        iife.DeviceMat.from_csr(1, 3, np.array([0, 2]), np.array([2, 1]), np.array([1.0, 2.0]))
+
+
+def test_fingerprint_depends_on_pattern_only(iife):
+    rng = np.random.default_rng(1)
+    rp, ci, v = rand_csr(rng, 100, 100, 6)
+    A = iife.DeviceMat.from_csr(100, 100, rp, ci, v)
+    B = iife.DeviceMat.from_csr(100, 100, rp, ci, v * 2 + 1)
+    assert A.fingerprint() == B.fingerprint()
+    ci2 = ci.copy()
+    # move one entry to a different (still sorted, unique) column if possible
+    for i in range(100):
+        row = ci2[rp[i]:rp[i + 1]]
+        if len(row) and row[-1] < 99:
+            row[-1] += 1
+            break
+    C = iife.DeviceMat.from_csr(100, 100, rp, ci2, v)
+    assert C.fingerprint() != A.fingerprint()
+    D = iife.DeviceMat.from_csr(100, 101, rp, ci, v)
+    assert D.fingerprint() != A.fingerprint()
+
+
+@pytest.mark.parametrize("shape", [(500, 37, 3.0), (64, 4000, 40.0), (3000, 5, 2.0), (200, 200, 90.0)])
+def test_transpose_matches_oracle(iife, oracle, shape):
+    n_rows, n_cols, mean = shape
+    rng = np.random.default_rng(2)
+    A = ocsr(oracle, n_rows, n_cols, rand_csr(rng, n_rows, n_cols, mean, empty_frac=0.1))
+    T = oracle.transpose(A)
+    dT = dmat(iife, A).transpose()
+    rp, ci, v = dT.to_csr(np.int64)
+    assert np.array_equal(rp, T.rowptr) and np.array_equal(ci, T.colind) and np.array_equal(v, T.val)
+
+
+def test_transpose_very_long_rows(iife, oracle):
+    """columns with > 4096 entries take the global-memory sort path (cf. cube/Quadratic/R0: 5672)."""
+    rng = np.random.default_rng(3)
+    n_rows, n_cols = 12000, 3
+    lens = rng.integers(1, 4, n_rows)
+    rp = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum(lens, out=rp[1:])
+    ci = np.concatenate([np.sort(rng.choice(3, l, replace=False)) for l in lens])
+    A = oracle.CSR(n_rows, n_cols, rp, ci, rng.standard_normal(rp[-1]))
+    T = oracle.transpose(A)
+    rp2, ci2, v2 = dmat(iife, A).transpose().to_csr(np.int64)
+    assert np.array_equal(rp2, T.rowptr) and np.array_equal(ci2, T.colind) and np.array_equal(v2, T.val)
+
+
+@pytest.mark.parametrize("mean", [1.5, 4.0, 9.0, 18.0, 60.0])
+def test_spmv_matches_oracle(iife, oracle, mean):
+    rng = np.random.default_rng(4)
+    A = ocsr(oracle, 2000, 1500, rand_csr(rng, 2000, 1500, mean, empty_frac=0.2))
+    dA = dmat(iife, A)
+    x = rng.standard_normal(1500)
+    y = dA.spmv(x)
+    yo = oracle.spmv(A, x)
+    scale = oracle.spmv(abs_csr(oracle, A), np.abs(x)) + 1e-300
+    assert np.all(np.abs(y - yo) <= 1e-14 * scale)
+    # transpose product (AT_x) and the alpha/beta form (multAdd)
+    xt = rng.standard_normal(2000)
+    yt = dA.spmv(xt, trans=True)
+    yto = oracle.AT_x(A, xt)
+    scale_t = oracle.AT_x(abs_csr(oracle, A), np.abs(xt)) + 1e-300
+    assert np.all(np.abs(yt - yto) <= 1e-14 * scale_t)
+    y0 = rng.standard_normal(2000)
+    y2 = dA.spmv(x, y=y0.copy(), alpha=-2.0, beta=0.5)
+    assert np.all(np.abs(y2 - (-2.0 * yo + 0.5 * y0)) <= 1e-13 * (2 * scale + np.abs(y0)))
+
+
+def test_diagonal(iife, oracle):
+    rng = np.random.default_rng(5)
+    A = ocsr(oracle, 400, 400, rand_csr(rng, 400, 400, 7, empty_frac=0.1))
+    d = dmat(iife, A).diagonal()
+    assert np.array_equal(d, np.diag(A.todense()))
+
+
+@pytest.mark.parametrize("n_cells,sigma", [(2, 1.0), (5, 1.0), (4, 0.0)])
+def test_ptap_cube(iife, oracle, n_cells, sigma):
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, _ = assemble_cube(n_cells, sigma)
+    check_ptap(iife, oracle, M, A)
+
+
+def test_ptap_known_answers(iife, oracle):
+    rng = np.random.default_rng(6)
+    n = 300
+    A = ocsr(oracle, n, n, rand_csr(rng, n, n, 7, empty_frac=0.1))
+    I = oracle.CSR(n, n, np.arange(n + 1), np.arange(n), np.ones(n))
+    # (i) M = I  =>  A_b == A_f bit for bit
+    dI, dA = dmat(iife, I), dmat(iife, A)
+    dC, cached = iife.ptap(dI, dA)
+    rp, ci, v = dC.to_csr(np.int64)
+    assert np.array_equal(rp, A.rowptr) and np.array_equal(ci, A.colind) and np.array_equal(v, A.val)
+    # (ii) A_f = I  =>  A_b = M^T M
+    M = ocsr(oracle, n, 40, rand_csr(rng, n, 40, 3, empty_frac=0.4))
+    check_ptap(iife, oracle, M, I)
+    # (v) exact cancellation and stored zeros stay in the pattern
+    M2 = oracle.CSR(2, 1, [0, 1, 2], [0, 0], [1.0, 1.0])
+    A2 = oracle.CSR(2, 2, [0, 2, 4], [0, 1, 0, 1], [1.0, -1.0, -1.0, 1.0])
+    _, _, dC2, _, _ = check_ptap(iife, oracle, M2, A2)
+    assert dC2.nnz == 1 and dC2.values()[0] == 0.0
+
+
+@pytest.mark.parametrize("case", [
+    dict(n_f=2000, n_b=700, m_mean=3, a_mean=7, m_empty=0.4, a_empty=0.05),     # shipped-data-like
+    dict(n_f=3000, n_b=40, m_mean=8, a_mean=20, m_empty=0.0, a_empty=0.0),      # fat rows: upper levels
+    dict(n_f=1500, n_b=1500, m_mean=1, a_mean=2, m_empty=0.5, a_empty=0.5),     # hypersparse, many empties
+    dict(n_f=6000, n_b=6, m_mean=2, a_mean=30, m_empty=0.0, a_empty=0.0),       # huge Mt rows: global level
+    dict(n_f=900, n_b=300, m_mean=27, a_mean=60, m_empty=0.1, a_empty=0.0),     # quadratic-like widths
+])
+def test_ptap_random(iife, oracle, case):
+    rng = np.random.default_rng(7)
+    M = ocsr(oracle, case["n_f"], case["n_b"], rand_csr(rng, case["n_f"], case["n_b"], case["m_mean"], empty_frac=case["m_empty"]))
+    A = ocsr(oracle, case["n_f"], case["n_f"], rand_csr(rng, case["n_f"], case["n_f"], case["a_mean"], empty_frac=case["a_empty"]))
+    check_ptap(iife, oracle, M, A)
+
+
+def test_ptap_numeric_reuse_and_cache(iife, oracle):
+    """config 4 pattern: same M, same A_f pattern, new values many times on one symbolic plan."""
+    from oracle.synthetic_cube import assemble_cube
+
+    rng = np.random.default_rng(8)
+    A, M, _ = assemble_cube(4)
+    dM, dA, dC, C, plan = check_ptap(iife, oracle, M, A)
+    for step in range(3):
+        A2 = oracle.CSR(A.n_rows, A.n_cols, A.rowptr, A.colind, A.val * (1 + 0.1 * rng.standard_normal(A.nnz)))
+        dA.update_values(A2.val)
+        plan.numeric(dM, dA, C=dC, check_errors=True)
+        C2 = oracle.AT_R_A(M, A2)
+        bound = oracle.AT_R_A(abs_csr(oracle, M), abs_csr(oracle, A2))
+        assert np.all(np.abs(dC.values() - C2.val) <= VAL_TOL * bound.val)
+    # handle-less AT_R_A entry: second call with a fresh upload of the same pattern hits the plan cache
+    iife.plan_cache_clear()
+    c1, cached1 = iife.ptap(dmat(iife, M), dmat(iife, A))
+    c2, cached2 = iife.ptap(dmat(iife, M), dmat(iife, A2))
+    assert not cached1 and cached2
+    assert np.all(np.abs(c2.values() - C2.val) <= VAL_TOL * bound.val)
+    # a plan refuses operands of another shape
+    other = dmat(iife, oracle.CSR(3, 3, [0, 1, 2, 3], [0, 1, 2], [1.0, 1.0, 1.0]))
+    with pytest.raises(iife.IifeError):
+        plan.numeric(dM, other)
+
+
+def test_ptap_is_deterministic(iife, oracle):
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, _ = assemble_cube(5)
+    dM, dA = dmat(iife, M), dmat(iife, A)
+    plan = iife.PtapPlan(dM, dA)
+    v1 = plan.numeric(dM, dA).values()
+    v2 = plan.numeric(dM, dA).values()
+    assert np.array_equal(v1, v2)
+
+
+@pytest.mark.parametrize("method", ["cg", "gmres"])
+def test_ksp_matches_oracle(iife, oracle, method):
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, b = assemble_cube(6)
+    C = oracle.AT_R_A(M, A)
+    bb = oracle.AT_x(M, b)
+    kt = iife.KSP_CG if method == "cg" else iife.KSP_FGMRES
+    for rtol, atol in ((1e-8, 1e-9), (1e-12, 1e-50)):
+        ro = oracle.solve_ksp(C, bb, method=method, rtol=rtol, atol=atol, hist_len=500)
+        x = np.zeros(C.n_rows)
+        info = iife.ksp_solve(dmat(iife, C), bb, x, kt, iife.PC_JACOBI, rtol=rtol, atol=atol, hist_len=500)
+        assert info.reason == ro.reason, (info.reason_name, ro.reason)
+        assert abs(info.iterations - ro.iterations) <= 1
+        k = min(info.iterations, ro.iterations) + 1
+        assert np.allclose(info.history[:k], ro.history[:k], rtol=1e-6, atol=1e-30)
+        assert np.linalg.norm(x - ro.x) <= SOL_TOL * np.linalg.norm(ro.x)
+
+
+def test_ksp_singular_rows_and_nonzero_guess(iife, oracle):
+    """A_b of real data has structurally empty rows (unsupported background functions): Jacobi maps the
+    zero diagonal to 1 and those unknowns keep their initial value."""
+    rng = np.random.default_rng(9)
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M0, b = assemble_cube(4)
+    # drop the support of a few background functions: empty columns of M -> empty rows/cols of A_b
+    S = M0.to_scipy().tolil()
+    dead = [3, 17, 60]
+    for k in dead:
+        S[:, k] = 0
+    S = S.tocsr()
+    S.eliminate_zeros()
+    M = oracle.CSR.from_scipy(S)
+    C = oracle.AT_R_A(M, A)
+    bb = oracle.AT_x(M, b)
+    x0 = rng.standard_normal(C.n_rows) * 1e-3
+    for method, kt in (("cg", iife.KSP_CG), ("gmres", iife.KSP_FGMRES)):
+        ro = oracle.solve_ksp(C, bb, x0=x0, method=method, rtol=1e-10, atol=1e-50, hist_len=300)
+        x = x0.copy()
+        info = iife.ksp_solve(dmat(iife, C), bb, x, kt, iife.PC_JACOBI, rtol=1e-10, atol=1e-50, hist_len=300)
+        assert info.reason == ro.reason and abs(info.iterations - ro.iterations) <= 1
+        assert np.array_equal(x[dead], x0[dead])
+        live = np.setdiff1d(np.arange(C.n_rows), dead)
+        assert np.linalg.norm(x[live] - ro.x[live]) <= SOL_TOL * np.linalg.norm(ro.x[live])
+
+
+def test_ksp_reasons(iife, oracle):
+    import scipy.sparse as sp
+
+    n = 50
+    # max_it exhaustion never raises (error_on_nonconvergence=False, reference common.py:635)
+    rng = np.random.default_rng(10)
+    B = rng.standard_normal((n, n))
+    S = sp.csr_matrix(B @ B.T + 1e-3 * np.eye(n))
+    A = oracle.CSR.from_scipy(S)
+    b = rng.standard_normal(n)
+    for method, kt in (("cg", iife.KSP_CG), ("gmres", iife.KSP_FGMRES)):
+        ro = oracle.solve_ksp(A, b, method=method, rtol=1e-14, atol=1e-50, max_it=7)
+        x = np.zeros(n)
+        info = iife.ksp_solve(dmat(iife, A), b, x, kt, iife.PC_JACOBI, rtol=1e-14, atol=1e-50, max_it=7)
+        assert info.reason == ro.reason == -3 and info.iterations == ro.iterations == 7
+        assert np.allclose(x, ro.x, rtol=1e-8, atol=1e-12)
+    # indefinite operator: CG reports DIVERGED_INDEFINITE_MAT (-10) or INDEFINITE_PC (-8) like the oracle
+    Dm = sp.diags(np.concatenate([np.ones(n // 2), -np.ones(n - n // 2)])).tocsr()
+    Ai = oracle.CSR.from_scipy(Dm)
+    ro = oracle.solve_ksp(Ai, b, method="cg", PC="none")
+    x = np.zeros(n)
+    info = iife.ksp_solve(dmat(iife, Ai), b, x, iife.KSP_CG, iife.PC_NONE)
+    assert info.reason == ro.reason and info.reason < 0
+    # zero right-hand side with zero guess converges immediately
+    x = np.zeros(n)
+    info = iife.ksp_solve(dmat(iife, A), np.zeros(n), x, iife.KSP_CG, iife.PC_JACOBI)
+    assert info.reason > 0 and info.iterations == 0 and np.all(x == 0)
+
+
+def test_fgmres_restart(iife, oracle):
+    """restart shorter than the iteration count exercises the cycle logic (true residual at restart)."""
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, b = assemble_cube(5)
+    C = oracle.AT_R_A(M, A)
+    bb = oracle.AT_x(M, b)
+    ro = oracle.solve_ksp(C, bb, method="gmres", rtol=1e-10, atol=1e-50, restart=5, hist_len=400)
+    x = np.zeros(C.n_rows)
+    info = iife.ksp_solve(dmat(iife, C), bb, x, iife.KSP_FGMRES, iife.PC_JACOBI, rtol=1e-10, atol=1e-50, restart=5,
+                          hist_len=400)
+    assert info.reason == ro.reason == 2
+    assert abs(info.iterations - ro.iterations) <= 2
+    assert np.linalg.norm(x - ro.x) <= SOL_TOL * np.linalg.norm(ro.x)
+
+
+def test_synthetic_device_generator_is_bit_exact(iife):
+    from iife_b200 import synthetic
+
+    for n_cells, sigma in ((3, 1.0), (6, 0.0)):
+        g = synthetic.cube_operators(n_cells, sigma)
+        import torch
+
+        bf = torch.empty(g["n_f"], dtype=torch.float64, device="cuda:0")
+        dA, dM = iife.synth_cube(n_cells, sigma, b_f=bf)
+        iife.sync()
+        for d, h in ((dA, g["A"]), (dM, g["M"])):
+            rp, ci, v = d.to_csr(np.int64)
+            assert np.array_equal(rp, h[0]) and np.array_equal(ci, h[1]) and np.array_equal(v, h[2])
+        assert np.array_equal(bf.cpu().numpy(), g["b_f"])
+    # a row slab carries global column ids
+    g = synthetic.cube_operators(4, 1.0, 100, 300)
+    dA, dM = iife.synth_cube(4, 1.0, 100, 300)
+    rp, ci, v = dA.to_csr(np.int64)
+    assert np.array_equal(rp, g["A"][0]) and np.array_equal(ci, g["A"][1]) and np.array_equal(v, g["A"][2])
+
+
+def test_end_to_end_cube_pipeline(iife, oracle):
+    """extraction + solve, device path end to end, against the oracle (N_b = 12: 15 625 fg dofs)."""
+    from iife_b200 import synthetic
+
+    g = synthetic.cube_operators(12)
+    A = oracle.CSR(g["n_f"], g["n_f"], *g["A"])
+    M = oracle.CSR(g["n_f"], g["n_b"], *g["M"])
+    dM, dA, dC, C, plan = check_ptap(iife, oracle, M, A)
+    bb = dM.spmv(g["b_f"], trans=True)
+    bbo = oracle.AT_x(M, g["b_f"])
+    assert np.allclose(bb, bbo, rtol=1e-13, atol=0)
+    x = np.zeros(C.n_rows)
+    info = iife.ksp_solve(dC, bb, x, iife.KSP_CG, iife.PC_JACOBI, rtol=1e-10, atol=1e-50)
+    ro = oracle.solve_ksp(C, bbo, method="cg", rtol=1e-10, atol=1e-50)
+    assert info.reason == ro.reason == 2 and abs(info.iterations - ro.iterations) <= 1
+    assert np.linalg.norm(x - ro.x) <= SOL_TOL * np.linalg.norm(ro.x)
+    uf = dM.spmv(x)  # transferToForeground (reference common.py:123-140)
+    assert np.allclose(uf, oracle.spmv(M, ro.x), rtol=1e-7, atol=1e-12)

@@ -1,0 +1,153 @@
+"""CPU tests of the oracle (the restatement of the reference path) against dense numpy, its
+known-answer tests and the committed golden fixtures.  PARITY UNPINNED: no PETSc."""
+import numpy as np
+import pytest
+
+from conftest import rand_csr
+
+
+def _csr(O, n_rows, n_cols, t):
+    return O.CSR(n_rows, n_cols, t[0], t[1], t[2])
+
+
+def test_transpose_sorted_and_dense(oracle):
+    rng = np.random.default_rng(0)
+    A = _csr(oracle, 37, 23, rand_csr(rng, 37, 23, 4, empty_frac=0.2))
+    T = oracle.transpose(A)
+    assert np.array_equal(T.todense(), A.todense().T)
+    for i in range(T.n_rows):
+        c = T.colind[T.rowptr[i]:T.rowptr[i + 1]]
+        assert np.all(np.diff(c) > 0)
+
+
+def test_ptap_dense_small(oracle):
+    rng = np.random.default_rng(1)
+    M = _csr(oracle, 60, 17, rand_csr(rng, 60, 17, 3, empty_frac=0.3))
+    A = _csr(oracle, 60, 60, rand_csr(rng, 60, 60, 6, empty_frac=0.1))
+    C = oracle.AT_R_A(M, A)
+    Cd = M.todense().T @ A.todense() @ M.todense()
+    assert np.allclose(C.todense(), Cd, rtol=0, atol=1e-13 * np.abs(Cd).max())
+    pat = (M.pattern_dense().T.astype(int) @ A.pattern_dense().astype(int) @ M.pattern_dense().astype(int)) > 0
+    assert np.array_equal(C.pattern_dense(), pat)
+
+
+def test_identity_extraction_is_bit_exact(oracle):
+    """M = I  =>  A_b == A_f bit for bit (mirrors getIdentity, reference common.py:254-258)."""
+    rng = np.random.default_rng(2)
+    A = _csr(oracle, 40, 40, rand_csr(rng, 40, 40, 5))
+    n = 40
+    I = oracle.CSR(n, n, np.arange(n + 1), np.arange(n), np.ones(n))
+    C = oracle.AT_R_A(I, A)
+    assert np.array_equal(C.rowptr, A.rowptr) and np.array_equal(C.colind, A.colind) and np.array_equal(C.val, A.val)
+
+
+def test_structural_zeros_and_cancellation_stay(oracle):
+    """[1,-1] . [1,1]^T cancels numerically but stays in the pattern; stored zeros count."""
+    M = oracle.CSR(2, 1, [0, 1, 2], [0, 0], [1.0, 1.0])
+    A = oracle.CSR(2, 2, [0, 2, 4], [0, 1, 0, 1], [1.0, -1.0, -1.0, 1.0])
+    C = oracle.AT_R_A(M, A)
+    assert C.nnz == 1 and C.val[0] == 0.0
+    A0 = oracle.CSR(2, 2, [0, 2, 4], [0, 1, 0, 1], [0.0, 0.0, 0.0, 0.0])
+    C0 = oracle.AT_R_A(M, A0)
+    assert C0.nnz == 1
+
+
+def test_empty_rows_and_cols_propagate(oracle):
+    rng = np.random.default_rng(3)
+    rp, ci, v = rand_csr(rng, 50, 20, 2, empty_frac=0.5)
+    ci = ci.copy()
+    ci[ci == 7] = 8  # leave column 7 unsupported (may create duplicates; rebuild cleanly)
+    M = oracle.CSR.from_scipy(oracle.CSR(50, 20, rp, np.sort(ci), v).to_scipy().tocoo().tocsr())
+    A = _csr(oracle, 50, 50, rand_csr(rng, 50, 50, 5))
+    C = oracle.AT_R_A(M, A)
+    unsupported = np.setdiff1d(np.arange(20), M.colind)
+    for k in unsupported:
+        assert C.rowptr[k + 1] == C.rowptr[k]
+        assert not np.any(C.colind == k)
+
+
+def test_symmetry_and_partition_of_unity(oracle):
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, b = assemble_cube(3)
+    C = oracle.AT_R_A(M, A)
+    D = C.todense()
+    assert np.allclose(D, D.T, rtol=0, atol=1e-14 * np.abs(D).max())
+    ones_f = np.ones(A.n_rows)
+    assert np.allclose(oracle.spmv(M, np.ones(M.n_cols)), 1.0)
+    assert np.isclose(np.ones(C.n_rows) @ D @ np.ones(C.n_rows), ones_f @ A.todense() @ ones_f, rtol=1e-12)
+    assert np.allclose(oracle.AT_x(M, b), M.todense().T @ b)
+
+
+def test_synthetic_generators_agree(oracle):
+    from iife_b200 import synthetic
+    from oracle.synthetic_cube import assemble_cube
+
+    for sigma in (1.0, 0.0):
+        A, M, b = assemble_cube(4, sigma)
+        g = synthetic.cube_operators(4, sigma)
+        assert np.array_equal(A.rowptr, g["A"][0]) and np.array_equal(A.colind, g["A"][1])
+        assert np.allclose(A.val, g["A"][2], rtol=0, atol=1e-14 * np.abs(A.val).max())
+        assert np.array_equal(M.rowptr, g["M"][0]) and np.array_equal(M.colind, g["M"][1])
+        assert np.array_equal(M.val, g["M"][2])
+        assert np.allclose(b, g["b_f"], rtol=1e-13, atol=0)
+        assert (A.nnz, M.nnz) == synthetic.cube_nnz(4)[:2]
+    # sigma = 0: the face/body diagonal couplings of the Kuhn stiffness are stored exact zeros
+    A0, _, _ = assemble_cube(3, 0.0)
+    assert np.count_nonzero(A0.val == 0.0) > 0
+
+
+@pytest.mark.parametrize("method", ["cg", "gmres"])
+def test_ksp_against_dense_solve(oracle, method):
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, b = assemble_cube(4)
+    C = oracle.AT_R_A(M, A)
+    bb = oracle.AT_x(M, b)
+    r = oracle.solve_ksp(C, bb, method=method, rtol=1e-12, atol=1e-30, hist_len=400)
+    xs = np.linalg.solve(C.todense(), bb)
+    assert r.reason == 2
+    assert np.linalg.norm(r.x - xs) <= 1e-9 * np.linalg.norm(xs)
+    h = r.history[: r.iterations + 1]
+    assert h[-1] <= 1e-12 * h[0] * 1.0000001 or r.reason == 2
+
+
+def test_cg_textbook_iteration_by_iteration(oracle):
+    """The C CG equals a line-by-line numpy transcription of SURVEY A.6 (preconditioned norm)."""
+    rng = np.random.default_rng(5)
+    n = 30
+    B = rng.standard_normal((n, n))
+    S = B @ B.T + n * np.eye(n)
+    S[np.abs(S) < 0.5] = 0.0
+    import scipy.sparse as sp
+
+    A = oracle.CSR.from_scipy(sp.csr_matrix(S))
+    b = rng.standard_normal(n)
+    r = oracle.solve_ksp(A, b, method="cg", rtol=1e-10, atol=1e-50, hist_len=100)
+    d = 1.0 / np.diag(S)
+    x = np.zeros(n)
+    res = b.copy()
+    z = d * res
+    hist = [np.linalg.norm(z)]
+    ttol = 1e-10 * np.linalg.norm(d * b)
+    p = None
+    beta_old = None
+    while hist[-1] > ttol:
+        beta = z @ res
+        p = z.copy() if p is None else z + beta / beta_old * p
+        w = S @ p
+        a = beta / (p @ w)
+        x += a * p
+        res -= a * w
+        z = d * res
+        hist.append(np.linalg.norm(z))
+        beta_old = beta
+    assert r.iterations == len(hist) - 1
+    assert np.allclose(r.history[: len(hist)], hist, rtol=1e-9)
+    assert np.allclose(r.x, x, rtol=1e-9, atol=1e-14)
+
+
+def test_jacobi_zero_diagonal_becomes_one(oracle):
+    A = oracle.CSR(3, 3, [0, 1, 1, 3], [0, 1, 2], [2.0, 5.0, 4.0])  # row 1 empty, row 2 has a 0-diag? no: (2,1),(2,2)
+    d = oracle.jacobi_inverse(A)
+    assert d[0] == 0.5 and d[1] == 1.0 and d[2] == 0.25
