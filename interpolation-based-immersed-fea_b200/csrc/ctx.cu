@@ -1,6 +1,8 @@
 // ctx.cu — process context (one GPU per process), error strings, device allocation accounting and
 // the device-wide exclusive scan used by the symbolic phases.
 #include "common.cuh"
+#include <map>
+#include <unordered_map>
 
 namespace iife {
 
@@ -8,6 +10,7 @@ static Ctx g_ctx;
 Ctx &ctx() { return g_ctx; }
 
 static thread_local char g_err[1024] = "";
+static std::unordered_map<void *, size_t> g_block_sizes;
 
 int set_err(int code, const char *fmt, ...) {
   va_list ap;
@@ -18,24 +21,67 @@ int set_err(int code, const char *fmt, ...) {
 }
 const char *get_err() { return g_err; }
 
+// ------------------------------------------------------------------ caching device allocator
+// cudaMalloc / cudaFree cost tens of microseconds to milliseconds each and cudaFree synchronises the
+// device, which would put a host round trip into every call of the hot path (work vectors of the KSP,
+// temporaries of the symbolic phase, the FGMRES basis).  Freed blocks are therefore kept in a
+// size-indexed free list and reused; everything runs on ONE stream, so reuse is stream-ordered and
+// needs no event.  Blocks go back to the driver at iife_finalize or when cudaMalloc runs out.
+static std::multimap<size_t, void *> g_free_blocks;
+static int64_t g_cached_bytes = 0;
+
+static size_t round_size(size_t bytes) {
+  if (bytes < 512) return 512;
+  if (bytes < (1u << 20)) return (bytes + 511) & ~(size_t)511;
+  return (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+}
+
+void dev_release_cached() {
+  for (auto &kv : g_free_blocks) cudaFree(kv.second);
+  g_free_blocks.clear();
+  g_cached_bytes = 0;
+}
+
 int dev_alloc(void **p, size_t bytes) {
   *p = nullptr;
-  cudaError_t e = cudaMalloc(p, bytes);
+  size_t want = round_size(bytes);
+  auto it = g_free_blocks.lower_bound(want);
+  if (it != g_free_blocks.end() && it->first <= want + want / 4) {
+    *p = it->second;
+    g_cached_bytes -= (int64_t)it->first;
+    g_ctx.dev_bytes += (int64_t)it->first;
+    g_block_sizes[*p] = it->first;
+    g_free_blocks.erase(it);
+    return IIFE_OK;
+  }
+  cudaError_t e = cudaMalloc(p, want);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    return set_err(IIFE_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s (library holds %lld bytes)", bytes,
+    cudaStreamSynchronize(g_ctx.stream);
+    dev_release_cached();
+    e = cudaMalloc(p, want);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *p = nullptr;
+    return set_err(IIFE_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s (library holds %lld bytes)", want,
                    cudaGetErrorString(e), (long long)g_ctx.dev_bytes);
   }
-  g_ctx.dev_bytes += (int64_t)bytes;
+  g_ctx.dev_bytes += (int64_t)want;
+  g_block_sizes[*p] = want;
   return IIFE_OK;
 }
 
 int dev_free(void *p, size_t bytes) {
+  (void)bytes;
   if (!p) return IIFE_OK;
-  // cudaFree synchronises implicitly with outstanding work on the buffer
-  cudaError_t e = cudaFree(p);
-  g_ctx.dev_bytes -= (int64_t)bytes;
-  if (e != cudaSuccess) return set_err(IIFE_ERR_CUDA, "cudaFree failed: %s", cudaGetErrorString(e));
+  auto it = g_block_sizes.find(p);
+  if (it == g_block_sizes.end()) return set_err(IIFE_ERR_STATE, "dev_free of an unknown pointer");
+  size_t sz = it->second;
+  g_block_sizes.erase(it);
+  g_ctx.dev_bytes -= (int64_t)sz;
+  g_free_blocks.emplace(sz, p);
+  g_cached_bytes += (int64_t)sz;
   return IIFE_OK;
 }
 
@@ -209,11 +255,13 @@ int iife_init(int device) {
 
 int iife_plan_cache_clear(void);
 
+
 int iife_finalize(void) {
   Ctx &c = ctx();
   if (!c.init) return IIFE_OK;
   iife_plan_cache_clear();
   cudaStreamSynchronize(c.stream);
+  dev_release_cached();
   if (c.own_stream) cudaStreamDestroy(c.own_stream);
   c.own_stream = nullptr;
   c.stream = nullptr;

@@ -594,31 +594,30 @@ static int fgmres_solve(Mat *A, const double *dinv, const double *b, double *x, 
   IIFE_TRY(mpart.alloc((size_t)(m + 1) * g));
   int rc = IIFE_OK;
   // grow the basis up to V[upto_v], Z[upto_z]; called only at points where the stream is idle
+  // grow the basis up to V[upto_v], Z[upto_z] with ONE slab allocation per call; called only at points
+  // where the stream is idle (cycle start / chunk polls)
+  std::vector<std::pair<double *, size_t>> slabs;
   auto ensure_vecs = [&](int upto_v, int upto_z) -> int {
-    bool grew = false;
-    while ((int)V.size() <= upto_v) {
-      double *pnew = nullptr;
-      IIFE_TRY(dev_alloc_t(&pnew, (size_t)n));
-      V.push_back(pnew);
-      grew = true;
-    }
-    while ((int)Z.size() <= upto_z) {
-      double *pnew = nullptr;
-      IIFE_TRY(dev_alloc_t(&pnew, (size_t)n));
-      Z.push_back(pnew);
-      grew = true;
-    }
-    if (grew) {
-      IIFE_CUDA(cudaStreamSynchronize(c.stream));
-      IIFE_CUDA(cudaMemcpy(vtab.p, V.data(), V.size() * sizeof(double *), cudaMemcpyHostToDevice));
-      IIFE_CUDA(cudaMemcpy(ztab.p, Z.data(), Z.size() * sizeof(double *), cudaMemcpyHostToDevice));
-    }
+    int need_v = upto_v + 1 - (int)V.size(), need_z = upto_z + 1 - (int)Z.size();
+    if (need_v < 0) need_v = 0;
+    if (need_z < 0) need_z = 0;
+    if (need_v + need_z == 0) return IIFE_OK;
+    size_t n_pad = ((size_t)n + 31) & ~(size_t)31;  // keep every vector 256-byte aligned
+    size_t count = (size_t)(need_v + need_z) * n_pad;
+    double *slab = nullptr;
+    IIFE_TRY(dev_alloc_t(&slab, count));
+    slabs.emplace_back(slab, count);
+    double *cur = slab;
+    for (int k = 0; k < need_v; ++k, cur += n_pad) V.push_back(cur);
+    for (int k = 0; k < need_z; ++k, cur += n_pad) Z.push_back(cur);
+    IIFE_CUDA(cudaStreamSynchronize(c.stream));
+    IIFE_CUDA(cudaMemcpy(vtab.p, V.data(), V.size() * sizeof(double *), cudaMemcpyHostToDevice));
+    IIFE_CUDA(cudaMemcpy(ztab.p, Z.data(), Z.size() * sizeof(double *), cudaMemcpyHostToDevice));
     return IIFE_OK;
   };
   auto cleanup = [&]() {
     cudaStreamSynchronize(c.stream);
-    for (double *pv : V) dev_free_t(pv, (size_t)n);
-    for (double *pz : Z) dev_free_t(pz, (size_t)n);
+    for (auto &sl : slabs) dev_free_t(sl.first, sl.second);
   };
   int chunk = env_int("IIFE_KSP_CHUNK", 16);
   if (chunk < 1) chunk = 1;

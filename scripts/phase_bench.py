@@ -15,7 +15,8 @@ from iife_b200 import synthetic
 
 I.init(0)
 torch.cuda.set_device(0)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
 I.set_stream(stream.cuda_stream)
 PEAK = 6544.3
 try:

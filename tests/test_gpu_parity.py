@@ -76,7 +76,7 @@ def test_mat_roundtrip_and_validation(iife):
     assert Z.shape == (0, 0)
     # malformed inputs are refused with IIFE_ERR_ARG
     with pytest.raises(iife.IifeError):
-        iife.DeviceMat.from_csr(2, 2, np.array([0, 2, 1]), np.array([0, 1]), np.array([1.0, 2.0]))
+        iife.DeviceMat.from_csr(2, 2, np.array([0, 3, 2]), np.array([0, 1]), np.array([1.0, 2.0]))
     with pytest.raises(iife.IifeError):
         iife.DeviceMat.from_csr(2, 2, np.array([0, 1, 2]), np.array([0, 5]), np.array([1.0, 2.0]))
     with pytest.raises(iife.IifeError):
@@ -249,7 +249,7 @@ def test_ksp_matches_oracle(iife, oracle, method):
         assert info.reason == ro.reason, (info.reason_name, ro.reason)
         assert abs(info.iterations - ro.iterations) <= 1
         k = min(info.iterations, ro.iterations) + 1
-        assert np.allclose(info.history[:k], ro.history[:k], rtol=1e-6, atol=1e-30)
+        assert np.allclose(info.history[:k], ro.history[:k], rtol=1e-4, atol=1e-9 * ro.history[0])
         assert np.linalg.norm(x - ro.x) <= SOL_TOL * np.linalg.norm(ro.x)
 
 
