@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the extraction hot path (BASELINE.json).
+
+One *step* = one pass of the hot path on the synthetic fitted cube (BASELINE config 5):
+    A_b = AT_R_A(M, A_f)      PtAP through the cached symbolic plan (pattern fingerprint + numeric phase)
+    b_b = AT_x(M, b_f)        M^T b_f
+    solveKSP(A_b, b_b, u)     Jacobi-CG from a zero guess to rtol 1e-8 / atol 1e-9 (the reference's tolerances)
+`value` is foreground DOFs per second through that step with the operands resident in HBM; `e2e` is the
+same step through the reference-facing la_utils/common mirror with HOST (pinned) CSR arrays, i.e. with
+the host->device copies of A_f, M, b_f and the device->host read of b_b, u_b inside the timed region.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3          # our arm
+    python bench.py --impl reference --steps 2 --warmup 1  # CPU arm (oracle port, host cores)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "interpolation-based-immersed-fea_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "extraction_ptap_plus_cg_throughput"
+UNIT = "Mdof/s"  # foreground DOFs through PtAP + M^T b + Jacobi-CG(rtol 1e-8, atol 1e-9) per second
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# --------------------------------------------------------------------------------------------------
+def pick_threads(O, C, x):
+    """Fastest OpenMP thread count for the SpMV on this host (vCPU counts over-promise on shared boxes)."""
+    best, best_t = 1, float("inf")
+    n = O.max_threads()
+    cand = sorted({1, 2, 4, 8, 16, 32, 64, n, max(1, n // 2)})
+    for th in [c for c in cand if c <= n]:
+        O.set_threads(th)
+        O.spmv(C, x)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            O.spmv(C, x)
+        t = time.perf_counter() - t0
+        if t < best_t:
+            best, best_t = th, t
+    O.set_threads(best)
+    return best
+
+
+def cpu_step(O, M, A, b_f, method="cg"):
+    C = O.AT_R_A(M, A)
+    bb = O.AT_x(M, b_f)
+    r = O.solve_ksp(C, bb, method=method, PC="jacobi", rtol=1e-8, atol=1e-9)
+    return C, bb, r
+
+
+def cpu_operands(n_cells):
+    from iife_b200 import synthetic
+    from oracle import oracle as O
+
+    g = synthetic.cube_operators(n_cells)
+    A = O.CSR(g["n_f"], g["n_f"], *g["A"])
+    M = O.CSR(g["n_f"], g["n_b"], *g["M"])
+    return O, A, M, g["b_f"], g
+
+
+def run_reference(args):
+    """`--impl reference`: PETSc is not installable here, so the reference arm is the
+    oracle port of the reference's own call sequence on all usable host threads, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total_steps = args.steps + args.warmup
+    n_cells = args.cpu_cells or (92 if total_steps <= 8 else (64 if total_steps <= 30 else 46))
+    O, A, M, b_f, g = cpu_operands(n_cells)
+    C, bb, r = cpu_step(O, M, A, b_f)
+    threads = pick_threads(O, C, np.ones(C.n_rows))
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_step(O, M, A, b_f)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        C, bb, r = cpu_step(O, M, A, b_f)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = g["n_f"] / dt / 1e6
+    sample = f"synthetic S1 cube N_b={n_cells} (n_f={g['n_f']}, nnz(A_f)={A.nnz}), {r.iterations} CG iterations per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"S1 fitted cube, bounded CPU sample N_b={n_cells}", "n_f": g["n_f"], "n_b": g["n_b"],
+                   "ksp": "cg+jacobi rtol=1e-8 atol=1e-9", "note": "CPU restatement (oracle port), not PETSc"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.t = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=10)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for s in self.samples if len(s) >= 7 for k in range(4) if s[3 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import iife_b200 as I
+    from iife_b200 import synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    I.init(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    I.set_stream(stream.cuda_stream)
+    peak, peak_src = measured_peak()
+
+    if world > 1:
+        from iife_b200 import dist as idist
+
+        return idist.bench_distributed(args, I, stream, peak, peak_src, METRIC, UNIT)
+
+    N = args.cells
+    sz = synthetic.cube_sizes(N)
+    n_f, n_b = sz["n_f"], sz["n_b"]
+    nnzA, nnzM, nnzC = synthetic.cube_nnz(N)
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    # ---- operands resident in HBM
+    b_f = torch.empty(n_f, dtype=torch.float64, device="cuda")
+    A, M = I.synth_cube(N, 1.0, b_f=b_f)
+    I.sync()
+    x = torch.zeros(n_b, dtype=torch.float64, device="cuda")
+    bb = torch.empty(n_b, dtype=torch.float64, device="cuda")
+    t0 = time.perf_counter()
+    C, cached = I.ptap(M, A)  # cold call: builds the symbolic plan
+    I.sync()
+    t_cold = time.perf_counter() - t0
+    state = {}
+
+    def step():
+        Cn, was_cached = I.ptap(M, A)
+        M.spmv(b_f, bb, trans=True)
+        x.zero_()
+        info = I.ksp_solve(Cn, bb, x, I.KSP_CG, I.PC_JACOBI, rtol=1e-8, atol=1e-9)
+        state["info"], state["cached"], state["C"] = info, was_cached, Cn
+        return info
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    I.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+    launches = I.launch_count()
+    total_ms = ev0.elapsed_time(ev1)
+    ms_step = total_ms / args.steps
+    info = state["info"]
+    value = n_f / (ms_step * 1e-3) / 1e6
+
+    # ---- per-phase device timings (explain `value`; inputs larger than L2, so no flush needed)
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    Cw = state["C"]
+    plan = I.PtapPlan(M, A)  # separate plan object to time the numeric phase alone
+    Cn = plan.numeric(M, A)
+    t_numeric = timed(lambda: plan.numeric(M, A, C=Cn), 3)
+    y = torch.empty(n_b, dtype=torch.float64, device="cuda")
+    xs = torch.ones(n_b, dtype=torch.float64, device="cuda")
+    t_spmv = timed(lambda: Cw.spmv(xs, y), 20)
+    B_spmv = 12 * nnzC + 4 * (n_b + 1) + 16 * n_b
+    B_ptap_numeric = 12 * (nnzA + 2 * nnzM + nnzC) + 4 * (2 * (n_f + 1) + 2 * (n_b + 1)) - 4 * nnzC
+    B_cg_it = B_spmv + 88 * n_b
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x.zero_()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    info_cg = I.ksp_solve(Cw, bb, x, I.KSP_CG, I.PC_JACOBI, rtol=1e-8, atol=1e-9)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t_cg = e0.elapsed_time(e1)
+    del plan, Cn
+
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("n_bg_cells") == N:
+            traffic = tj.get("spmv_dot_dram_bytes_per_launch")
+    except Exception:
+        pass
+    achieved = B_spmv / (t_spmv * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_spmv<32> / k_spmv_dot<32> (A_b SpMV of the CG iteration)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": B_spmv, "launch_ms": t_spmv,
+                "cg_iteration": {"algorithmic_bytes": B_cg_it, "ms": t_cg / max(info_cg.iterations, 1),
+                                 "gbs": B_cg_it * max(info_cg.iterations, 1) / (t_cg * 1e-3) / 1e9,
+                                 "frac": B_cg_it * max(info_cg.iterations, 1) / (t_cg * 1e-3) / 1e9 / peak},
+                "ptap_numeric": {"algorithmic_bytes": B_ptap_numeric, "ms": t_numeric,
+                                 "gbs": B_ptap_numeric / (t_numeric * 1e-3) / 1e9,
+                                 "frac": B_ptap_numeric / (t_numeric * 1e-3) / 1e9 / peak}}
+
+    # ---- end to end through the la_utils/common mirror with HOST (pinned) buffers
+    e2e = None
+    if not args.no_e2e:
+        from InterpolationBasedImmersedFEA import common as ref_api
+
+        def pinned(n, dtype):
+            return torch.empty(n, dtype=dtype).pin_memory()
+
+        hA = (pinned(n_f + 1, torch.int32), pinned(nnzA, torch.int32), pinned(nnzA, torch.float64))
+        hM = (pinned(n_f + 1, torch.int32), pinned(nnzM, torch.int32), pinned(nnzM, torch.float64))
+        A.to_csr(np.int32, out=tuple(t.numpy() for t in hA))
+        M.to_csr(np.int32, out=tuple(t.numpy() for t in hM))
+        hb = pinned(n_f, torch.float64)
+        hb.copy_(b_f)
+        torch.cuda.synchronize()
+        h2d = sum(t.numel() * t.element_size() for t in hA + hM) + hb.numel() * 8
+        d2h = 2 * n_b * 8
+        u_host = np.zeros(n_b)
+
+        def e2e_step():
+            Mh = ref_api.CSRMat((n_f, n_b), *(t.numpy() for t in hM))
+            Ah = ref_api.CSRMat((n_f, n_f), *(t.numpy() for t in hA))
+            A_b, b_b = ref_api.assembleLinearSystemBackground(Ah, hb.numpy(), Mh)
+            u_host[:] = 0.0
+            u = ref_api.Vec(u_host)
+            ref_api.solveKSP(A_b, b_b, u, method="cg", PC="jacobi", monitor=False)
+            return u
+
+        n_e2e = max(1, min(args.steps, args.e2e_steps))
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": n_f / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3, "steps": n_e2e, "api": "InterpolationBasedImmersedFEA.common."
+               "assembleLinearSystemBackground + solveKSP (host CSR arrays, pinned)"}
+        del hA, hM
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
+    cpu = None
+    if not args.no_cpu:
+        try:
+            n_cpu = args.cpu_cells or 64
+            O, Ac, Mc, bfc, g = cpu_operands(n_cpu)
+            Cc, bbc, rc = cpu_step(O, Mc, Ac, bfc)
+            threads = pick_threads(O, Cc, np.ones(Cc.n_rows))
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 3 and (time.perf_counter() - t0) < 20.0:
+                Cc, bbc, rc = cpu_step(O, Mc, Ac, bfc)
+                reps += 1
+            dt = (time.perf_counter() - t0) / reps
+            cpu = {"value": g["n_f"] / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"S1 cube N_b={n_cpu} (n_f={g['n_f']}), {rc.iterations} CG its, {dt:.2f} s/step, "
+                             "oracle port of the reference call sequence (not PETSc)"}
+        except Exception as exc:  # the CPU leg must never take the GPU numbers down with it
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"BASELINE config 5: synthetic S1 fitted cube N_b={N}", "n_f": n_f, "n_b": n_b,
+                   "nnz_A_f": nnzA, "nnz_M": nnzM, "nnz_A_b": nnzC, "ksp": "cg+jacobi rtol=1e-8 atol=1e-9 zero guess",
+                   "cg_iterations": info.iterations, "cg_reason": info.reason_name, "plan_cached": bool(state["cached"]),
+                   "cold_ptap_symbolic_plus_numeric_ms": t_cold * 1e3, "l2": "inputs larger than L2 (no flush)",
+                   "parallelism": "1 GPU"},
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=int(os.environ.get("IIFE_BENCH_CELLS", "184")),
+                    help="background cells per direction of the S1 cube (184 = ~50 M foreground DOFs)")
+    ap.add_argument("--cpu-cells", type=int, default=0, help="size of the bounded CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

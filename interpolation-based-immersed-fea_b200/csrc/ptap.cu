@@ -20,6 +20,7 @@
 // is retried at the next, the last level keeps its tables in global memory, so any input works.
 #include "common.cuh"
 #include <list>
+#include <stdlib.h>
 
 namespace iife {
 
@@ -417,6 +418,10 @@ __global__ void k_ptap_numeric(PtapArgs a) {
     team_sync<WARP>();
   }
 }
+
+}  // namespace iife
+#include "ptap_warp.cuh"
+namespace iife {
 
 // ------------------------------------------------------------------------------------------------
 // small helper kernels
@@ -879,6 +884,36 @@ static int ptap_numeric_impl(Plan *P, Mat *M, Mat *A, Mat **C_io) {
       a.log_cap2 = global_tables ? P->g_log_cap2 : L.log_cap2;
       a.g_keys = global_tables ? P->g_keys : nullptr;
       a.g_vals = global_tables ? P->g_vals : nullptr;
+      static const bool use_old = getenv("IIFE_PTAP_OLD") != nullptr;
+      if (L.warp_team && !use_old) {
+        // privatised-table warp kernel (ptap_warp.cuh)
+        int lg1 = a.logG1 < 3 ? 3 : (a.logG1 > 5 ? 5 : a.logG1);
+        int lg2 = a.logG2 < 2 ? 2 : (a.logG2 > 5 ? 5 : a.logG2);
+        if (const char *e1 = getenv("IIFE_PTAP_LG1")) lg1 = atoi(e1);
+        if (const char *e2 = getenv("IIFE_PTAP_LG2")) lg2 = atoi(e2);
+        warp_kernel_t kern = pick_warp_kernel(lg1, lg2);
+        if (!kern) { rc = set_err(IIFE_ERR_ARG, "no warp kernel for group sizes 2^%d / 2^%d", lg1, lg2); break; }
+        size_t per_warp = warp_kernel_smem_per_warp(lg1, lg2, a.log_cap1, a.log_cap2);
+        size_t smem_max = (size_t)(c.max_smem_optin ? c.max_smem_optin : 227 * 1024);
+        int wpc = 4;
+        if (const char *ew = getenv("IIFE_PTAP_WPC")) wpc = atoi(ew);
+        while (wpc > 1 && per_warp * wpc > smem_max / 2) wpc >>= 1;
+        size_t smem = per_warp * wpc;
+        if (smem > smem_max) { rc = set_err(IIFE_ERR_UNSUPPORTED, "numeric level %d needs %zu B of shared memory", l, smem); break; }
+        int ctas_sm = (int)((smem_max + 1024) / (smem + 1024));
+        if (ctas_sm * wpc > 64) ctas_sm = 64 / wpc;
+        if (ctas_sm > 32) ctas_sm = 32;
+        int64_t ctas = (cnt + wpc - 1) / wpc;
+        int64_t cap = (int64_t)c.sm_count * ctas_sm;
+        if (ctas > cap) ctas = cap;
+        if (smem > 48 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e)); break; }
+        }
+        kern<<<(int)ctas, wpc * 32, smem, c.stream>>>(a);
+        c.launches++;
+        continue;
+      }
       int teams_per_cta = L.warp_team ? L.threads / 32 : 1;
       int T = L.warp_team ? 32 : L.threads;
       size_t smem = team_smem_bytes(true, global_tables, 1 << a.log_cap1, 1 << a.log_cap2, T) * teams_per_cta;
