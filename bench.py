@@ -198,11 +198,25 @@ def run_ours(args):
     t_cold = time.perf_counter() - t0
     state = {}
 
+    debug = bool(os.environ.get("IIFE_BENCH_DEBUG"))
+
     def step():
+        if debug:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            evs[0].record(stream)
         Cn, was_cached = I.ptap(M, A)
+        if debug:
+            evs[1].record(stream)
         M.spmv(b_f, bb, trans=True)
         x.zero_()
+        if debug:
+            evs[2].record(stream)
         info = I.ksp_solve(Cn, bb, x, I.KSP_CG, I.PC_JACOBI, rtol=1e-8, atol=1e-9)
+        if debug:
+            evs[3].record(stream)
+            torch.cuda.synchronize()
+            print(f"[step] ptap {evs[0].elapsed_time(evs[1]):.2f} ms, Mtb {evs[1].elapsed_time(evs[2]):.2f} ms, "
+                  f"ksp {evs[2].elapsed_time(evs[3]):.2f} ms ({info.iterations} its)", file=sys.stderr)
         state["info"], state["cached"], state["C"] = info, was_cached, Cn
         return info
 

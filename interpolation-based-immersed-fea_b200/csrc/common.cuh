@@ -103,6 +103,13 @@ struct Mat {
   uint64_t fp = 0;
   bool fp_valid = false;
   int max_row_len = -1;  // lazily computed
+  // SELL-32 copy used by the KSP operator (spmv.cu): slices of 32 rows, column-major inside a slice
+  int sell_state = 0;  // 0 not tried, 1 built, -1 rejected (padding too large)
+  int64_t sell_slices = 0, sell_padded = 0;
+  int *sell_ptr = nullptr;  // [sell_slices+1] entry offsets
+  int *sell_col = nullptr;
+  double *sell_val = nullptr;
+  bool sell_vals_valid = false;
 };
 
 int mat_alloc(Mat **out, int64_t n_rows, int64_t n_cols, int64_t nnz);
@@ -123,6 +130,10 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
 int spmv_dot_launch(const Mat *A, const double *p, double *w, double *dot_out, double *partials,
                     unsigned int *counter, const int *flag);
 int spmv_pick_lpr(const Mat *A);
+// SELL-32 operator copy: builds it on first use (returns IIFE_OK with A->sell_state == -1 if the
+// padding would exceed 1.25x nnz, in which case callers stay on CSR) and refreshes values.
+int mat_ensure_sell(Mat *A);
+void mat_free_sell(Mat *A);
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <chrono>
 
 namespace iife {
 
@@ -479,6 +480,23 @@ static int poll_flags(const KspWork &w, HostFlags *pinned) {
   return IIFE_OK;
 }
 
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static bool ksp_debug() {
+  static int v = -1;
+  if (v < 0) v = getenv("IIFE_KSP_DEBUG") ? 1 : 0;
+  return v == 1;
+}
+#define KSP_DBG(tag)                                                          \
+  do {                                                                        \
+    if (ksp_debug()) {                                                        \
+      double _t = now_ms();                                                   \
+      fprintf(stderr, "[ksp] %-22s +%.3f ms\n", tag, _t - dbg_t0);            \
+      dbg_t0 = _t;                                                            \
+    }                                                                         \
+  } while (0)
+
 static int env_int(const char *name, int dflt) {
   const char *s = getenv(name);
   return s ? atoi(s) : dflt;
@@ -491,6 +509,7 @@ static int cg_solve(Mat *A, const double *dinv, const double *b, double *x, int6
                     HostFlags *hf) {
   Ctx &c = ctx();
   const int64_t n = A->n_rows;
+  double dbg_t0 = now_ms();
   Tmp<double> r, p, wv;
   IIFE_TRY(r.alloc((size_t)n));
   IIFE_TRY(p.alloc((size_t)n));
@@ -502,7 +521,9 @@ static int cg_solve(Mat *A, const double *dinv, const double *b, double *x, int6
   IIFE_LAUNCH(k_cg_init, g, VEC_THREADS, 0, r.p, b, dinv, n, w.sc, w.fl, w.partials, w.counters, w.hist,
               (long long)w.hist_len);
   IIFE_CHECK_LAUNCH();
+  KSP_DBG("alloc+init enqueue");
   IIFE_TRY(poll_flags(w, hf));
+  KSP_DBG("init poll");
   if (hf->fl[F_REASON] != 0) return IIFE_OK;
 
   int chunk = env_int("IIFE_KSP_CHUNK", 32);
@@ -538,6 +559,7 @@ static int cg_solve(Mat *A, const double *dinv, const double *b, double *x, int6
     launches_per_chunk = c.launches - before;
     c.launches = before;  // captured, not launched yet
   }
+  KSP_DBG("graph capture+inst");
   int rc = IIFE_OK;
   int64_t enq = 0;
   while (rc == IIFE_OK) {
@@ -552,7 +574,9 @@ static int cg_solve(Mat *A, const double *dinv, const double *b, double *x, int6
       if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "CG launch: %s", cudaGetErrorString(e)); break; }
     }
     enq += chunk;
+    KSP_DBG("chunk enqueue");
     if ((rc = poll_flags(w, hf)) != IIFE_OK) break;
+    KSP_DBG("chunk poll");
     if (hf->fl[F_REASON] != 0) break;
     if (enq > max_it + chunk) { rc = set_err(IIFE_ERR_STATE, "CG driver ran past max_it without a reason"); break; }
   }
@@ -702,6 +726,7 @@ extern "C" int iife_ksp_solve(iife_mat A_, int ksp_type, int pc_type, double rto
     IIFE_TRY(mat_ensure_dinv(A));
     dinv = A->dinv;
   }
+  IIFE_TRY(mat_ensure_sell(A));  // SELL-32 copy of the operator for the iteration (CSR if rejected)
   KspWork w;
   Tmp<double> sc, partials, dhist, dx, db;
   Tmp<int> fl;

@@ -26,6 +26,7 @@ int mat_free(Mat *A) {
   if (A->T) mat_free(A->T);
   if (A->T_perm) dev_free_t(A->T_perm, (size_t)A->nnz);
   if (A->dinv) dev_free_t(A->dinv, (size_t)A->n_rows);
+  mat_free_sell(A);
   if (A->rowptr) dev_free_t(A->rowptr, (size_t)A->n_rows + 1);
   if (A->colind) dev_free_t(A->colind, (size_t)A->nnz);
   if (A->val) dev_free_t(A->val, (size_t)A->nnz);
@@ -590,6 +591,7 @@ int iife_mat_update_values(iife_mat A_, const double *val, int mem) {
   IIFE_TRY(copy_in(A->val, val, (size_t)A->nnz * sizeof(double), mem));
   A->T_vals_valid = false;
   A->dinv_valid = false;
+  A->sell_vals_valid = false;
   if (mem == IIFE_MEM_HOST) IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
   return IIFE_OK;
 }

@@ -938,6 +938,7 @@ static int ptap_numeric_impl(Plan *P, Mat *M, Mat *A, Mat **C_io) {
     if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "PtAP numeric launch: %s", cudaGetErrorString(e)); break; }
     C->T_vals_valid = false;
     C->dinv_valid = false;
+    C->sell_vals_valid = false;
   } while (0);
   if (rc != IIFE_OK) {
     if (created) mat_free(C);

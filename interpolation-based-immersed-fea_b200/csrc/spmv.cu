@@ -10,6 +10,7 @@
 // variant need a bounded scratch array and are reduced in a fixed order by the last CTA to finish
 // (bit-reproducible for a given launch geometry).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace iife {
 
@@ -106,6 +107,184 @@ k_spmv_dot(const int *__restrict__ rowptr, const int *__restrict__ colind, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SELL-32 operator copy for the Krylov loop.
+// The CSR kernels above give one row to LPR lanes: every row costs a chain of three dependent global
+// loads (rowptr -> colind/val -> x) and a shuffle reduction, which the ncu profile showed to be
+// latency bound (long-scoreboard stalls, 24 % DRAM utilisation at full occupancy).  A_b is solved with
+// hundreds of times per extraction and has near-uniform rows ((2p+1)^d B-spline stencils), so it is
+// re-laid out once per value update as sliced ELLPACK: slices of 32 consecutive rows, entries stored
+// column-major inside a slice.  One THREAD owns one row: the warp's loads of (colind, val) are 128-
+// and 256-byte coalesced streams, four of them are in flight per thread, there is no reduction, and
+// the only irregular access is the gather of x (L2 resident).  Padding entries carry val = 0 and the
+// row's own column.  Rejected (CSR stays in use) when padding exceeds 25 % of nnz.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sell_widths(const int *__restrict__ rowptr, int64_t n_rows, int64_t n_slices, int *__restrict__ entries) {
+  int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = w; s < n_slices; s += nw) {
+    int64_t i = s * 32 + lane;
+    int len = i < n_rows ? rowptr[i + 1] - rowptr[i] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane == 0) entries[s] = len * 32;
+  }
+}
+
+__global__ void k_sell_fill(const int *__restrict__ rowptr, const int *__restrict__ colind, const double *__restrict__ val,
+                            int64_t n_rows, int64_t n_cols, int64_t n_slices, const int *__restrict__ sell_ptr,
+                            int *__restrict__ sell_col, double *__restrict__ sell_val, int fill_cols) {
+  int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = w; s < n_slices; s += nw) {
+    int64_t i = s * 32 + lane;
+    int b = 0, len = 0;
+    if (i < n_rows) {
+      b = rowptr[i];
+      len = rowptr[i + 1] - b;
+    }
+    int sb = sell_ptr[s], width = (sell_ptr[s + 1] - sb) >> 5;
+    int pad_col = (i < n_cols) ? (int)i : 0;
+    for (int k = 0; k < width; ++k) {
+      bool in = k < len;
+      if (fill_cols) sell_col[sb + k * 32 + lane] = in ? colind[b + k] : pad_col;
+      sell_val[sb + k * 32 + lane] = in ? val[b + k] : 0.0;
+    }
+  }
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, const double *__restrict__ sell_val,
+            int64_t n_rows, int64_t n_slices, const double *__restrict__ x, double *__restrict__ y,
+            double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *__restrict__ counter,
+            const int *__restrict__ flag) {
+  if (DOT && flag && *flag != 0) return;
+  __shared__ double red[32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double dsum = 0.0;
+  for (int64_t s = w0; s < n_slices; s += nw) {
+    const int sb = __ldg(sell_ptr + s), se = __ldg(sell_ptr + s + 1);
+    const int *cp = sell_col + sb + lane;
+    const double *vp = sell_val + sb + lane;
+    const int width = (se - sb) >> 5;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= width; k += 4) {
+      int c0 = ld_stream(cp + (k + 0) * 32), c1 = ld_stream(cp + (k + 1) * 32);
+      int c2 = ld_stream(cp + (k + 2) * 32), c3 = ld_stream(cp + (k + 3) * 32);
+      double v0 = ld_stream(vp + (k + 0) * 32), v1 = ld_stream(vp + (k + 1) * 32);
+      double v2 = ld_stream(vp + (k + 2) * 32), v3 = ld_stream(vp + (k + 3) * 32);
+      a0 = fma(v0, __ldg(x + c0), a0);
+      a1 = fma(v1, __ldg(x + c1), a1);
+      a2 = fma(v2, __ldg(x + c2), a2);
+      a3 = fma(v3, __ldg(x + c3), a3);
+    }
+    for (; k < width; ++k) a0 = fma(ld_stream(vp + k * 32), __ldg(x + ld_stream(cp + k * 32)), a0);
+    const double acc = (a0 + a1) + (a2 + a3);
+    const int64_t i = s * 32 + lane;
+    if (i < n_rows) {
+      y[i] = acc;
+      if (DOT) dsum = fma(acc, __ldg(x + i), dsum);
+    }
+  }
+  if (DOT) {
+    double bs = block_sum(dsum, red);
+    if (threadIdx.x == 0) {
+      partials[blockIdx.x] = bs;
+      __threadfence();
+      unsigned int t = atomicAdd(counter, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      double sacc = 0.0;
+      for (int kk = threadIdx.x; kk < (int)gridDim.x; kk += blockDim.x) sacc += __ldcg(partials + kk);
+      sacc = block_sum(sacc, red);
+      if (threadIdx.x == 0) {
+        *dot_out = sacc;
+        *counter = 0u;
+      }
+    }
+  }
+}
+
+void mat_free_sell(Mat *A) {
+  if (A->sell_ptr) dev_free_t(A->sell_ptr, (size_t)A->sell_slices + 1);
+  if (A->sell_col) dev_free_t(A->sell_col, (size_t)A->sell_padded);
+  if (A->sell_val) dev_free_t(A->sell_val, (size_t)A->sell_padded);
+  A->sell_ptr = A->sell_col = nullptr;
+  A->sell_val = nullptr;
+  A->sell_state = 0;
+  A->sell_vals_valid = false;
+}
+
+static int sell_grid(int64_t n_slices) {
+  int64_t need = (n_slices + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
+  int64_t cap = (int64_t)ctx().sm_count * 8;
+  if (need > cap) need = cap;
+  if (need < 1) need = 1;
+  return (int)need;
+}
+
+int mat_ensure_sell(Mat *A) {
+  static const bool disabled = getenv("IIFE_NO_SELL") != nullptr;
+  if (A->sell_state == -1 || disabled || A->n_rows == 0 || A->nnz == 0) {
+    A->sell_state = -1;
+    return IIFE_OK;
+  }
+  Ctx &c = ctx();
+  bool fill_cols = false;
+  if (A->sell_state == 0) {
+    int64_t n_slices = (A->n_rows + 31) / 32;
+    Tmp<int> entries;
+    IIFE_TRY(entries.alloc((size_t)n_slices + 1));
+    IIFE_LAUNCH(k_sell_widths, sell_grid(n_slices), SPMV_THREADS, 0, A->rowptr, A->n_rows, n_slices, entries.p);
+    IIFE_CHECK_LAUNCH();
+    int *ptr = nullptr;
+    IIFE_TRY(dev_alloc_t(&ptr, (size_t)n_slices + 1));
+    int64_t padded = 0;
+    int rc = exclusive_scan_i32(entries.p, ptr, n_slices, &padded);
+    if (rc == IIFE_ERR_UNSUPPORTED || (rc == IIFE_OK && padded > A->nnz + A->nnz / 4 + 1024)) {
+      dev_free_t(ptr, (size_t)n_slices + 1);
+      A->sell_state = -1;  // too much padding (or > int32): stay on CSR
+      return IIFE_OK;
+    }
+    if (rc != IIFE_OK) {
+      dev_free_t(ptr, (size_t)n_slices + 1);
+      return rc;
+    }
+    A->sell_ptr = ptr;
+    A->sell_slices = n_slices;
+    A->sell_padded = padded;
+    rc = dev_alloc_t(&A->sell_col, (size_t)padded);
+    if (rc == IIFE_OK) rc = dev_alloc_t(&A->sell_val, (size_t)padded);
+    if (rc != IIFE_OK) {
+      mat_free_sell(A);
+      return rc;
+    }
+    A->sell_state = 1;
+    fill_cols = true;
+    A->sell_vals_valid = false;
+  }
+  if (!A->sell_vals_valid) {
+    IIFE_LAUNCH(k_sell_fill, sell_grid(A->sell_slices), SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, A->n_cols,
+                A->sell_slices, A->sell_ptr, A->sell_col, A->sell_val, fill_cols ? 1 : 0);
+    IIFE_CHECK_LAUNCH();
+    A->sell_vals_valid = true;
+  }
+  (void)c;
+  return IIFE_OK;
+}
+
+static bool sell_ready(const Mat *A) { return A->sell_state == 1 && A->sell_vals_valid; }
+
 int spmv_pick_lpr(const Mat *A) {
   double mean = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
   if (mean <= 2.5) return 2;
@@ -126,6 +305,13 @@ static int spmv_grid(int64_t n_rows, int lpr) {
 
 int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double *y) {
   if (A->n_rows == 0) return IIFE_OK;
+  if (sell_ready(A) && alpha == 1.0 && beta == 0.0) {
+    IIFE_LAUNCH((k_spmv_sell<false>), sell_grid(A->sell_slices), SPMV_THREADS, 0, A->sell_ptr, A->sell_col, A->sell_val,
+                A->n_rows, A->sell_slices, x, y, (double *)nullptr, (double *)nullptr, (unsigned int *)nullptr,
+                (const int *)nullptr);
+    IIFE_CHECK_LAUNCH();
+    return IIFE_OK;
+  }
   int lpr = spmv_pick_lpr(A);
   int g = spmv_grid(A->n_rows, lpr);
   bool plain = (alpha == 1.0 && beta == 0.0);
@@ -149,6 +335,12 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
 
 int spmv_dot_launch(const Mat *A, const double *p, double *w, double *dot_out, double *partials,
                     unsigned int *counter, const int *flag) {
+  if (sell_ready(A)) {
+    IIFE_LAUNCH((k_spmv_sell<true>), sell_grid(A->sell_slices), SPMV_THREADS, 0, A->sell_ptr, A->sell_col, A->sell_val,
+                A->n_rows, A->sell_slices, p, w, dot_out, partials, counter, flag);
+    IIFE_CHECK_LAUNCH();
+    return IIFE_OK;
+  }
   int lpr = spmv_pick_lpr(A);
   int g = spmv_grid(A->n_rows, lpr);
 #define SPMVD_CASE(L)                                                                                            \

@@ -89,4 +89,6 @@ for N in [int(a) for a in sys.argv[1:]] or [23]:
         B_it = B_spmv + 88 * n_b
         extra = f" cg-iter alg {B_it/1e9:.3f} GB -> {B_it*its/ms/1e6:.0f} GB/s = {B_it*its/ms/1e6/PEAK:.3f}" if name == "cg" else ""
         print(f"  {name}: {info.iterations} its, reason {info.reason_name}, {ms:.2f} ms, {ms/its:.4f} ms/it{extra}", flush=True)
+    tmin, tmed = timed(lambda: C.spmv(x, y), reps=10, warm=2)
+    print(f"  spmv(A_b) after KSP (SELL-32 if accepted) {tmin:.3f} ms  {B_spmv/tmin/1e6:.0f} GB/s = {B_spmv/tmin/1e6/PEAK:.3f}", flush=True)
     del plan, C, A, M
