@@ -100,6 +100,11 @@ int iife_launch_count(int64_t *n, int reset);
 /* val may be NULL (pattern only; values zero until iife_mat_update_values). */
 int iife_mat_create_csr(int64_t n_rows, int64_t n_cols, const void *rowptr, const void *colind,
                         const double *val, int idx_bytes, int mem, iife_mat *out);
+/* flags: IIFE_CSR_UNSORTED_OK accepts rows whose columns are not ascending (the [owned | ghost]
+ * renumbered operator block of the row-partitioned solver; SpMV and Jacobi do not need the order) */
+#define IIFE_CSR_UNSORTED_OK 1
+int iife_mat_create_csr_ex(int64_t n_rows, int64_t n_cols, const void *rowptr, const void *colind,
+                           const double *val, int idx_bytes, int mem, int flags, iife_mat *out);
 /* new values on the same pattern (the per-Newton-step path, common.py:432-435) */
 int iife_mat_update_values(iife_mat A, const double *val, int mem);
 int iife_mat_get_info(iife_mat A, int64_t *n_rows, int64_t *n_cols, int64_t *nnz);
@@ -129,6 +134,11 @@ int iife_plan_matches(iife_plan P, iife_mat M, iife_mat A, int *matches);
 int iife_plan_get_info(iife_plan P, int64_t *n_b, int64_t *nnz_c, int64_t *nnz_inter);
 /* numeric phase; *C == NULL creates the result matrix, otherwise refills its values (reuse) */
 int iife_ptap_numeric(iife_plan P, iife_mat M, iife_mat A, iife_mat *C);
+/* general triple product C = R A P with an explicit restriction R (n_out x nJ), A (nJ x nK), P (nK x n_cols):
+ * what one rank of the row-partitioned PtAP computes after gathering its block of M^T, the A_f rows
+ * that block touches and the M rows those touch (MPIAIJ MatMatMult fetches off-process rows the same way) */
+int iife_rap_symbolic(iife_mat R, iife_mat A, iife_mat P, iife_plan *out);
+int iife_rap_numeric(iife_plan plan, iife_mat R, iife_mat A, iife_mat P, iife_mat *C);
 /* synchronises and reports a numeric-phase inconsistency (operands whose pattern differs from the
  * plan's: a product term found no slot) as IIFE_ERR_STATE */
 int iife_plan_check(iife_plan P);

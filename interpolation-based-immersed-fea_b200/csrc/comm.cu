@@ -66,15 +66,6 @@ static int nccl_load() {
     if (_r != 0) return set_err(IIFE_ERR_COMM, "%s:%d: %s: %s", __FILE__, __LINE__, #expr, g_nccl.GetErrorString(_r)); \
   } while (0)
 
-struct Halo {
-  int64_t n_owned = 0, n_ghost = 0;
-  int nranks = 1;
-  std::vector<int64_t> send_counts, recv_counts, send_off, recv_off;
-  int *send_idx = nullptr;     // device [total_send]
-  double *send_buf = nullptr;  // device [total_send]
-  int64_t total_send = 0;
-};
-
 __global__ void k_pack(const double *__restrict__ x, const int *__restrict__ idx, double *__restrict__ buf, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -246,14 +237,6 @@ int iife_spmv_dist(iife_mat A_, iife_halo H_, double *x_dev, double *y_dev) {
                    (long long)A->n_cols, (long long)H->n_owned, (long long)H->n_ghost);
   IIFE_TRY(halo_exchange(H, x_dev));
   return spmv_launch(A, 1.0, x_dev, 0.0, y_dev);
-}
-
-int iife_ksp_solve_dist(iife_mat A_local, iife_halo H, int ksp_type, int pc_type, double rtol, double atol,
-                        double dtol, int64_t max_it, int restart, const double *b_dev, double *x_dev,
-                        iife_ksp_result *res, double *hist, int64_t hist_len) {
-  (void)A_local; (void)H; (void)ksp_type; (void)pc_type; (void)rtol; (void)atol; (void)dtol; (void)max_it;
-  (void)restart; (void)b_dev; (void)x_dev; (void)res; (void)hist; (void)hist_len;
-  return set_err(IIFE_ERR_UNSUPPORTED, "distributed KSP not built yet");
 }
 
 int iife_allreduce_sum(double *buf_dev, int64_t n) {

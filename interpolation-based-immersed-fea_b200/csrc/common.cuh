@@ -135,6 +135,18 @@ int spmv_pick_lpr(const Mat *A);
 int mat_ensure_sell(Mat *A);
 void mat_free_sell(Mat *A);
 
+// ghost-entry exchange plan of a row-partitioned operator (comm.cu)
+struct Halo {
+  int64_t n_owned = 0, n_ghost = 0;
+  int nranks = 1;
+  std::vector<int64_t> send_counts, recv_counts, send_off, recv_off;
+  int *send_idx = nullptr;     // device [total_send]
+  double *send_buf = nullptr;  // device [total_send]
+  int64_t total_send = 0;
+};
+int halo_exchange(Halo *H, double *x_dev);     // fills x[n_owned .. n_owned+n_ghost)
+int allreduce_sum(double *buf_dev, int64_t n);  // in place, on the library stream
+
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------- device helpers

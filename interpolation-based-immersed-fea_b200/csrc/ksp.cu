@@ -23,6 +23,7 @@ namespace iife {
 // scalar slots
 enum {
   S_BETA = 0, S_BETA_OLD, S_DELTA, S_DP, S_TTOL, S_RHO0, S_RTOL, S_ATOL, S_DTOL, S_SCALE, S_RES, S_TT,
+  S_RAW = 12,  // 3 raw (rank-local) sums awaiting the allreduce in the row-partitioned solver
   S_COUNT = 16
 };
 // flag slots
@@ -89,7 +90,46 @@ __device__ __forceinline__ bool grid_reduce(double (&acc)[NR], double *partials,
 // ------------------------------------------------------------------------------------------------
 // CG kernels
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cg_init_scalars(double *sc, int *fl, double zz, double zr, double zbzb, double *hist,
+                                                long long hist_len) {
+  double dp = sqrt(zz), beta = zr, rho0 = sqrt(zbzb);
+  sc[S_DP] = dp;
+  sc[S_BETA] = beta;
+  sc[S_BETA_OLD] = beta;
+  sc[S_RHO0] = rho0;
+  sc[S_TTOL] = fmax(sc[S_RTOL] * rho0, sc[S_ATOL]);
+  fl[F_ITS] = 0;
+  log_hist(hist, hist_len, 0, dp);
+  converged_default(sc, fl, 0, dp);
+  if (fl[F_REASON] == 0) {
+    // checks PETSc makes at the top of iteration i (KSPSolve_CG): its is already i+1 there
+    if (beta == 0.0) { fl[F_REASON] = IIFE_KSP_CONVERGED_ATOL; fl[F_ITS] = 1; }
+    else if (beta < 0.0) { fl[F_REASON] = IIFE_KSP_DIVERGED_INDEFINITE_PC; fl[F_ITS] = 1; }
+    else if (isnan(beta) || isinf(beta)) { fl[F_REASON] = IIFE_KSP_DIVERGED_NANORINF; fl[F_ITS] = 1; }
+    else if (fl[F_MAXIT] <= 0) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
+  }
+}
+
+__device__ __forceinline__ void cg_update_scalars(double *sc, int *fl, double zr, double zz, double *hist,
+                                                  long long hist_len) {
+  double beta = zr, dp = sqrt(zz);
+  int its = fl[F_ITS] + 1;
+  sc[S_BETA_OLD] = sc[S_BETA];
+  sc[S_BETA] = beta;
+  sc[S_DP] = dp;
+  fl[F_ITS] = its;
+  log_hist(hist, hist_len, its, dp);
+  converged_default(sc, fl, its, dp);
+  if (fl[F_REASON] == 0) {
+    if (its >= fl[F_MAXIT]) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
+    else if (beta == 0.0) { fl[F_REASON] = IIFE_KSP_CONVERGED_ATOL; fl[F_ITS] = its + 1; }
+    else if (beta < 0.0) { fl[F_REASON] = IIFE_KSP_DIVERGED_INDEFINITE_PC; fl[F_ITS] = its + 1; }
+    else if (isnan(beta) || isinf(beta)) { fl[F_REASON] = IIFE_KSP_DIVERGED_NANORINF; fl[F_ITS] = its + 1; }
+  }
+}
+
 // after r = b - A x0:  dp = ||D^-1 r||, beta = (D^-1 r, r), rho0 = ||D^-1 b||, test(0)
+template <bool DIST>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_init(const double *__restrict__ r, const double *__restrict__ b, const double *__restrict__ dinv, int64_t n,
           double *sc, int *fl, double *partials, unsigned int *counter, double *hist, long long hist_len) {
@@ -106,23 +146,18 @@ k_cg_init(const double *__restrict__ r, const double *__restrict__ b, const doub
     acc[2] = fma(zb, zb, acc[2]);
   }
   if (grid_reduce<3>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
-    double dp = sqrt(out[0]), beta = out[1], rho0 = sqrt(out[2]);
-    sc[S_DP] = dp;
-    sc[S_BETA] = beta;
-    sc[S_BETA_OLD] = beta;
-    sc[S_RHO0] = rho0;
-    sc[S_TTOL] = fmax(sc[S_RTOL] * rho0, sc[S_ATOL]);
-    fl[F_ITS] = 0;
-    log_hist(hist, hist_len, 0, dp);
-    converged_default(sc, fl, 0, dp);
-    if (fl[F_REASON] == 0) {
-      // checks PETSc makes at the top of iteration i (KSPSolve_CG): its is already i+1 there
-      if (beta == 0.0) { fl[F_REASON] = IIFE_KSP_CONVERGED_ATOL; fl[F_ITS] = 1; }
-      else if (beta < 0.0) { fl[F_REASON] = IIFE_KSP_DIVERGED_INDEFINITE_PC; fl[F_ITS] = 1; }
-      else if (isnan(beta) || isinf(beta)) { fl[F_REASON] = IIFE_KSP_DIVERGED_NANORINF; fl[F_ITS] = 1; }
-      else if (fl[F_MAXIT] <= 0) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
+    if (DIST) {
+      sc[S_RAW + 0] = out[0];
+      sc[S_RAW + 1] = out[1];
+      sc[S_RAW + 2] = out[2];
+    } else {
+      cg_init_scalars(sc, fl, out[0], out[1], out[2], hist, hist_len);
     }
   }
+}
+
+__global__ void k_cg_init_scalars(double *sc, int *fl, double *hist, long long hist_len) {
+  cg_init_scalars(sc, fl, sc[S_RAW + 0], sc[S_RAW + 1], sc[S_RAW + 2], hist, hist_len);
 }
 
 // p = z (first iteration) or p = z + (beta/beta_old) p, with z = D^-1 r recomputed (never stored)
@@ -140,6 +175,7 @@ k_cg_p(const double *__restrict__ r, const double *__restrict__ dinv, double *__
 }
 
 // alpha = beta/delta; x += alpha p; r -= alpha w; z = D^-1 r; (z,r), (z,z) -> beta, dp, test(i+1)
+template <bool DIST>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
             const double *__restrict__ w, const double *__restrict__ dinv, int64_t n, double *sc, int *fl,
@@ -172,21 +208,20 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
     acc[1] = fma(z, z, acc[1]);
   }
   if (grid_reduce<2>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
-    double beta = out[0], dp = sqrt(out[1]);
-    int its = fl[F_ITS] + 1;
-    sc[S_BETA_OLD] = sc[S_BETA];
-    sc[S_BETA] = beta;
-    sc[S_DP] = dp;
-    fl[F_ITS] = its;
-    log_hist(hist, hist_len, its, dp);
-    converged_default(sc, fl, its, dp);
-    if (fl[F_REASON] == 0) {
-      if (its >= fl[F_MAXIT]) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
-      else if (beta == 0.0) { fl[F_REASON] = IIFE_KSP_CONVERGED_ATOL; fl[F_ITS] = its + 1; }
-      else if (beta < 0.0) { fl[F_REASON] = IIFE_KSP_DIVERGED_INDEFINITE_PC; fl[F_ITS] = its + 1; }
-      else if (isnan(beta) || isinf(beta)) { fl[F_REASON] = IIFE_KSP_DIVERGED_NANORINF; fl[F_ITS] = its + 1; }
+    if (DIST) {
+      sc[S_RAW + 0] = out[0];
+      sc[S_RAW + 1] = out[1];
+    } else {
+      cg_update_scalars(sc, fl, out[0], out[1], hist, hist_len);
     }
   }
+}
+
+// row-partitioned solver: scalar step after the allreduce of the two raw sums
+__global__ void k_cg_update_scalars(double *sc, int *fl, double *hist, long long hist_len) {
+  if (fl[F_REASON] != 0) return;
+  if (!(sc[S_DELTA] > 0.0)) return;  // reason was set by k_cg_update
+  cg_update_scalars(sc, fl, sc[S_RAW + 0], sc[S_RAW + 1], hist, hist_len);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -505,21 +540,36 @@ static int env_int(const char *name, int dflt) {
 // ------------------------------------------------------------------------------------------------
 // CG driver (device pointers)
 // ------------------------------------------------------------------------------------------------
-static int cg_solve(Mat *A, const double *dinv, const double *b, double *x, int64_t max_it, KspWork &w,
+static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double *x, int64_t max_it, KspWork &w,
                     HostFlags *hf) {
   Ctx &c = ctx();
   const int64_t n = A->n_rows;
+  const bool dist = (H != nullptr) && c.nranks > 1;
+  const int64_t n_ext = H ? H->n_owned + H->n_ghost : n;  // owned + ghost entries of a multiplied vector
   double dbg_t0 = now_ms();
   Tmp<double> r, p, wv;
   IIFE_TRY(r.alloc((size_t)n));
-  IIFE_TRY(p.alloc((size_t)n));
+  IIFE_TRY(p.alloc((size_t)n_ext));
   IIFE_TRY(wv.alloc((size_t)n));
   const int g = vec_grid(n);
-  // r = b - A x0
+  // r = b - A x0   (row-partitioned: x0 is staged in p to receive its ghost entries)
   IIFE_LAUNCH(k_copy_gated, g, VEC_THREADS, 0, b, r.p, n, (const int *)nullptr);
-  IIFE_TRY(spmv_launch(A, -1.0, x, 1.0, r.p));
-  IIFE_LAUNCH(k_cg_init, g, VEC_THREADS, 0, r.p, b, dinv, n, w.sc, w.fl, w.partials, w.counters, w.hist,
-              (long long)w.hist_len);
+  if (H) {
+    IIFE_LAUNCH(k_copy_gated, g, VEC_THREADS, 0, (const double *)x, p.p, n, (const int *)nullptr);
+    if (dist) IIFE_TRY(halo_exchange(H, p.p));
+    IIFE_TRY(spmv_launch(A, -1.0, p.p, 1.0, r.p));
+  } else {
+    IIFE_TRY(spmv_launch(A, -1.0, x, 1.0, r.p));
+  }
+  if (dist) {
+    IIFE_LAUNCH(k_cg_init<true>, g, VEC_THREADS, 0, r.p, b, dinv, n, w.sc, w.fl, w.partials, w.counters, w.hist,
+                (long long)w.hist_len);
+    IIFE_TRY(allreduce_sum(w.sc + S_RAW, 3));
+    IIFE_LAUNCH(k_cg_init_scalars, 1, 1, 0, w.sc, w.fl, w.hist, (long long)w.hist_len);
+  } else {
+    IIFE_LAUNCH(k_cg_init<false>, g, VEC_THREADS, 0, r.p, b, dinv, n, w.sc, w.fl, w.partials, w.counters, w.hist,
+                (long long)w.hist_len);
+  }
   IIFE_CHECK_LAUNCH();
   KSP_DBG("alloc+init enqueue");
   IIFE_TRY(poll_flags(w, hf));
@@ -528,12 +578,22 @@ static int cg_solve(Mat *A, const double *dinv, const double *b, double *x, int6
 
   int chunk = env_int("IIFE_KSP_CHUNK", 32);
   if (chunk < 1) chunk = 1;
-  const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0;
+  // NCCL calls inside the loop: keep to plain stream launches (no graph capture) in that case
+  const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && !dist;
   auto enqueue_iteration = [&]() -> int {
     IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl);
+    if (dist) IIFE_TRY(halo_exchange(H, p.p));
     IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl));
-    IIFE_LAUNCH(k_cg_update, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
-                w.hist, (long long)w.hist_len);
+    if (dist) {
+      IIFE_TRY(allreduce_sum(w.sc + S_DELTA, 1));
+      IIFE_LAUNCH(k_cg_update<true>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
+                  w.hist, (long long)w.hist_len);
+      IIFE_TRY(allreduce_sum(w.sc + S_RAW, 2));
+      IIFE_LAUNCH(k_cg_update_scalars, 1, 1, 0, w.sc, w.fl, w.hist, (long long)w.hist_len);
+    } else {
+      IIFE_LAUNCH(k_cg_update<false>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
+                  w.hist, (long long)w.hist_len);
+    }
     return IIFE_OK;
   };
   cudaGraph_t graph = nullptr;
@@ -706,15 +766,17 @@ __global__ void k_ksp_setup(double *sc, int *fl, double rtol, double atol, doubl
 
 using namespace iife;
 
-extern "C" int iife_ksp_solve(iife_mat A_, int ksp_type, int pc_type, double rtol, double atol, double dtol,
-                              int64_t max_it, int restart, const double *b, double *x, int mem, iife_halo halo,
-                              iife_ksp_result *res, double *hist, int64_t hist_len) {
-  IIFE_NEED_INIT();
+static int ksp_solve_common(Mat *A, Halo *H, int ksp_type, int pc_type, double rtol, double atol, double dtol,
+                            int64_t max_it, int restart, const double *b, double *x, int mem, iife_ksp_result *res,
+                            double *hist, int64_t hist_len) {
   Ctx &c = ctx();
-  Mat *A = (Mat *)A_;
   if (!A || !b || !x) return set_err(IIFE_ERR_ARG, "NULL argument");
-  if (halo) return set_err(IIFE_ERR_UNSUPPORTED, "distributed KSP goes through iife_ksp_solve_dist");
-  if (A->n_rows != A->n_cols) return set_err(IIFE_ERR_ARG, "KSP needs a square operator, got %lld x %lld", (long long)A->n_rows, (long long)A->n_cols);
+  if (!H && A->n_rows != A->n_cols) return set_err(IIFE_ERR_ARG, "KSP needs a square operator, got %lld x %lld", (long long)A->n_rows, (long long)A->n_cols);
+  if (H && (A->n_rows != H->n_owned || A->n_cols != H->n_owned + H->n_ghost))
+    return set_err(IIFE_ERR_ARG, "local operator %lld x %lld does not match the halo (%lld owned + %lld ghost)", (long long)A->n_rows,
+                   (long long)A->n_cols, (long long)H->n_owned, (long long)H->n_ghost);
+  if (H && ksp_type != IIFE_KSP_CG) return set_err(IIFE_ERR_UNSUPPORTED, "the row-partitioned solver implements CG; FGMRES is single-GPU in this round");
+  if (H && mem != IIFE_MEM_DEVICE) return set_err(IIFE_ERR_ARG, "the row-partitioned solver takes device vectors");
   if (ksp_type != IIFE_KSP_CG && ksp_type != IIFE_KSP_FGMRES) return set_err(IIFE_ERR_ARG, "unknown ksp_type %d", ksp_type);
   if (pc_type != IIFE_PC_NONE && pc_type != IIFE_PC_JACOBI) return set_err(IIFE_ERR_ARG, "unknown pc_type %d", pc_type);
   if (max_it < 0) max_it = 0;
@@ -761,18 +823,18 @@ extern "C" int iife_ksp_solve(iife_mat A_, int ksp_type, int pc_type, double rto
   HostFlags *hf = nullptr;
   IIFE_CUDA(cudaMallocHost((void **)&hf, sizeof(HostFlags)));
   int rc;
-  if (n == 0) {
+  if (n == 0 && !H) {
     rc = IIFE_OK;
     for (int k = 0; k < F_COUNT; ++k) hf->fl[k] = 0;
     hf->fl[F_REASON] = IIFE_KSP_CONVERGED_ATOL;
   } else if (ksp_type == IIFE_KSP_CG) {
-    rc = cg_solve(A, dinv, bd, xd, max_it, w, hf);
+    rc = cg_solve(A, H, dinv, bd, xd, max_it, w, hf);
   } else {
     rc = fgmres_solve(A, dinv, bd, xd, max_it, restart, w, hf);
   }
   if (rc == IIFE_OK) {
     double hsc[S_COUNT] = {0};
-    if (n > 0) {
+    if (n > 0 || H) {
       cudaMemcpyAsync(hsc, w.sc, sizeof(hsc), cudaMemcpyDeviceToHost, c.stream);
       cudaMemcpyAsync(hf->fl, w.fl, sizeof(int) * F_COUNT, cudaMemcpyDeviceToHost, c.stream);
     }
@@ -790,4 +852,21 @@ extern "C" int iife_ksp_solve(iife_mat A_, int ksp_type, int pc_type, double rto
   }
   cudaFreeHost(hf);
   return rc;
+}
+
+extern "C" int iife_ksp_solve(iife_mat A_, int ksp_type, int pc_type, double rtol, double atol, double dtol,
+                              int64_t max_it, int restart, const double *b, double *x, int mem, iife_halo halo,
+                              iife_ksp_result *res, double *hist, int64_t hist_len) {
+  IIFE_NEED_INIT();
+  return ksp_solve_common((Mat *)A_, (Halo *)halo, ksp_type, pc_type, rtol, atol, dtol, max_it, restart, b, x, mem, res,
+                          hist, hist_len);
+}
+
+extern "C" int iife_ksp_solve_dist(iife_mat A_local, iife_halo H, int ksp_type, int pc_type, double rtol, double atol,
+                                   double dtol, int64_t max_it, int restart, const double *b_dev, double *x_dev,
+                                   iife_ksp_result *res, double *hist, int64_t hist_len) {
+  IIFE_NEED_INIT();
+  if (!H) return set_err(IIFE_ERR_ARG, "halo is NULL");
+  return ksp_solve_common((Mat *)A_local, (Halo *)H, ksp_type, pc_type, rtol, atol, dtol, max_it, restart, b_dev, x_dev,
+                          IIFE_MEM_DEVICE, res, hist, hist_len);
 }

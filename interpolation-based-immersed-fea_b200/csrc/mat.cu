@@ -518,8 +518,21 @@ using namespace iife;
 
 extern "C" {
 
+static int mat_create_csr_impl(int64_t n_rows, int64_t n_cols, const void *rowptr, const void *colind, const double *val,
+                               int idx_bytes, int mem, int flags, iife_mat *out);
+
 int iife_mat_create_csr(int64_t n_rows, int64_t n_cols, const void *rowptr, const void *colind, const double *val,
                         int idx_bytes, int mem, iife_mat *out) {
+  return mat_create_csr_impl(n_rows, n_cols, rowptr, colind, val, idx_bytes, mem, 0, out);
+}
+
+int iife_mat_create_csr_ex(int64_t n_rows, int64_t n_cols, const void *rowptr, const void *colind, const double *val,
+                           int idx_bytes, int mem, int flags, iife_mat *out) {
+  return mat_create_csr_impl(n_rows, n_cols, rowptr, colind, val, idx_bytes, mem, flags, out);
+}
+
+static int mat_create_csr_impl(int64_t n_rows, int64_t n_cols, const void *rowptr, const void *colind, const double *val,
+                               int idx_bytes, int mem, int flags, iife_mat *out) {
   IIFE_NEED_INIT();
   if (!out) return set_err(IIFE_ERR_ARG, "out is NULL");
   *out = nullptr;
@@ -574,7 +587,8 @@ int iife_mat_create_csr(int64_t n_rows, int64_t n_cols, const void *rowptr, cons
     cudaError_t e = cudaStreamSynchronize(ctx().stream);
     if (e != cudaSuccess) rc = set_err(IIFE_ERR_CUDA, "mat_create: %s", cudaGetErrorString(e));
     else if (hb & 2) rc = set_err(IIFE_ERR_ARG, "malformed CSR: column index out of range [0,%lld)", (long long)n_cols);
-    else if (hb & 4) rc = set_err(IIFE_ERR_ARG, "malformed CSR: column indices must be strictly ascending inside each row");
+    else if ((hb & 4) && !(flags & IIFE_CSR_UNSORTED_OK))
+      rc = set_err(IIFE_ERR_ARG, "malformed CSR: column indices must be strictly ascending inside each row");
   }
   if (rc != IIFE_OK) {
     mat_free(A);

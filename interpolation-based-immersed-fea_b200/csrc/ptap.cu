@@ -41,9 +41,11 @@ constexpr int N_SYM_LEVELS = 4;
 constexpr int N_NUM_LEVELS = 5;
 
 struct Plan {
-  uint64_t fpM = 0, fpA = 0;
-  int64_t n_f = 0, n_b = 0, nnzM = 0, nnzA = 0;
-  Mat *MT = nullptr;       // explicit transpose of M (pattern + values refreshed per numeric call)
+  uint64_t fpM = 0, fpA = 0, fpR = 0;
+  int64_t n_f = 0, n_b = 0, nnzM = 0, nnzA = 0;  // n_b = rows of the result; n_f = rows of A
+  int64_t n_k = 0, n_ccols = 0, nnzR = 0;         // columns of A (= rows of P), columns of the result
+  bool general_rap = false;  // true: C = R A P with an explicit restriction R given by the caller
+  Mat *MT = nullptr;       // PtAP: explicit transpose of M (pattern + values refreshed per numeric call)
   int *mt_perm = nullptr;  // MT.val[p] = M.val[mt_perm[p]]
   uint64_t mt_vals_uid = 0, mt_vals_version = 0;
   int *c_rowptr = nullptr, *c_colind = nullptr;
@@ -619,16 +621,28 @@ static int launch_symbolic(const Level &L, int mode, PtapArgs &a, int64_t n_work
   return IIFE_OK;
 }
 
-static int ptap_symbolic_impl(Mat *M, Mat *A, Plan **out) {
+// R == nullptr: PtAP (the restriction is the transpose of M, built here).  R != nullptr: general triple
+// product C = R A M with R: n_out x nJ, A: nJ x nK, M: nK x n_ccols (the row-partitioned path, where a
+// rank's block of M^T, the A_f rows it touches and the M rows those touch are gathered first).
+static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
   Ctx &c = ctx();
-  if (M->n_rows != A->n_rows || A->n_rows != A->n_cols)
-    return set_err(IIFE_ERR_ARG, "PtAP shape mismatch: M is %lld x %lld, A is %lld x %lld", (long long)M->n_rows,
-                   (long long)M->n_cols, (long long)A->n_rows, (long long)A->n_cols);
+  if (!R) {
+    if (M->n_rows != A->n_rows || A->n_rows != A->n_cols)
+      return set_err(IIFE_ERR_ARG, "PtAP shape mismatch: M is %lld x %lld, A is %lld x %lld", (long long)M->n_rows,
+                     (long long)M->n_cols, (long long)A->n_rows, (long long)A->n_cols);
+  } else if (R->n_cols != A->n_rows || A->n_cols != M->n_rows) {
+    return set_err(IIFE_ERR_ARG, "RAP shape mismatch: R %lld x %lld, A %lld x %lld, P %lld x %lld", (long long)R->n_rows,
+                   (long long)R->n_cols, (long long)A->n_rows, (long long)A->n_cols, (long long)M->n_rows, (long long)M->n_cols);
+  }
   Plan *P = new Plan();
-  P->n_f = M->n_rows;
-  P->n_b = M->n_cols;
+  P->general_rap = (R != nullptr);
+  P->n_f = A->n_rows;
+  P->n_k = A->n_cols;
+  P->n_b = R ? R->n_rows : M->n_cols;
+  P->n_ccols = M->n_cols;
   P->nnzM = M->nnz;
   P->nnzA = A->nnz;
+  P->nnzR = R ? R->nnz : M->nnz;
   int rc = IIFE_OK;
   const int64_t n_b = P->n_b;
   Tmp<int> n2, ovf_a, ovf_b, n_ovf, flag, off;
@@ -639,7 +653,10 @@ static int ptap_symbolic_impl(Mat *M, Mat *A, Plan **out) {
   do {
     if ((rc = mat_fingerprint(M, &P->fpM)) != IIFE_OK) break;
     if ((rc = mat_fingerprint(A, &P->fpA)) != IIFE_OK) break;
-    if ((rc = transpose_build(M, &P->MT, &P->mt_perm)) != IIFE_OK) break;
+    if (!R) {
+      if ((rc = transpose_build(M, &P->MT, &P->mt_perm)) != IIFE_OK) break;
+    } else if ((rc = mat_fingerprint(R, &P->fpR)) != IIFE_OK) break;
+    Mat *Rm = R ? R : P->MT;
     if ((rc = mean_nonempty_logG(A, &P->logG1)) != IIFE_OK) break;
     if ((rc = mean_nonempty_logG(M, &P->logG2)) != IIFE_OK) break;
     if ((rc = dev_alloc_t(&P->n1, (size_t)n_b)) != IIFE_OK) break;
@@ -658,8 +675,8 @@ static int ptap_symbolic_impl(Mat *M, Mat *A, Plan **out) {
     if (n_b) IIFE_LAUNCH(k_fill_schar, grid_for(n_b), 256, 0, level.p, n_b, (signed char)-1);
 
     PtapArgs a{};
-    a.mt_rowptr = P->MT->rowptr;
-    a.mt_col = P->MT->colind;
+    a.mt_rowptr = Rm->rowptr;
+    a.mt_col = Rm->colind;
     a.mt_val = nullptr;
     a.a_rowptr = A->rowptr;
     a.a_col = A->colind;
@@ -696,13 +713,13 @@ static int ptap_symbolic_impl(Mat *M, Mat *A, Plan **out) {
       if (L.log_cap1 == 0) {
         // global tables: size from an upper bound of the intermediate row and from n_b
         cudaMemsetAsync(u64.p, 0, 8, c.stream);
-        IIFE_LAUNCH(k_ub1_list, (int)(work < 1024 ? work : 1024), 256, 0, P->MT->rowptr, P->MT->colind, A->rowptr, a.rows, (int)work, u64.p);
+        IIFE_LAUNCH(k_ub1_list, (int)(work < 1024 ? work : 1024), 256, 0, Rm->rowptr, Rm->colind, A->rowptr, a.rows, (int)work, u64.p);
         unsigned long long ub = 0;
         cudaMemcpyAsync(&ub, u64.p, 8, cudaMemcpyDeviceToHost, c.stream);
         if (cudaStreamSynchronize(c.stream) != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "ub1: %s", cudaGetErrorString(cudaGetLastError())); break; }
-        int64_t b1 = (int64_t)ub < P->n_f ? (int64_t)ub : P->n_f;
+        int64_t b1 = (int64_t)ub < P->n_k ? (int64_t)ub : P->n_k;
         sym_g_log1 = log2_ceil(2 * b1 + 2);
-        sym_g_log2 = log2_ceil(2 * n_b + 2);
+        sym_g_log2 = log2_ceil(2 * P->n_ccols + 2);
         if (sym_g_log1 > 30 || sym_g_log2 > 30) { rc = set_err(IIFE_ERR_UNSUPPORTED, "PtAP row too large for the global hash level"); break; }
         size_t per_team = ((size_t)1 << sym_g_log1) + ((size_t)1 << sym_g_log2);
         size_t budget = (size_t)4 << 30;  // 4 GiB of table workspace at most
@@ -839,14 +856,16 @@ static int ptap_symbolic_impl(Mat *M, Mat *A, Plan **out) {
 
 int gather_vals_launch(const double *val, const int *perm, double *out, int64_t nnz);  // mat.cu
 
-static int ptap_numeric_impl(Plan *P, Mat *M, Mat *A, Mat **C_io) {
+static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
   Ctx &c = ctx();
-  if (M->n_rows != P->n_f || M->n_cols != P->n_b || M->nnz != P->nnzM || A->n_rows != P->n_f || A->nnz != P->nnzA)
+  if (M->n_rows != P->n_k || M->n_cols != P->n_ccols || M->nnz != P->nnzM || A->n_rows != P->n_f || A->nnz != P->nnzA)
     return set_err(IIFE_ERR_STATE, "PtAP numeric: operands do not match the symbolic plan (shape/nnz)");
+  if (P->general_rap != (R != nullptr) || (R && (R->n_rows != P->n_b || R->nnz != P->nnzR)))
+    return set_err(IIFE_ERR_STATE, "PtAP numeric: restriction operand does not match the symbolic plan");
   Mat *C = *C_io;
   bool created = false;
   if (!C) {
-    IIFE_TRY(mat_alloc(&C, P->n_b, P->n_b, P->nnz_c));
+    IIFE_TRY(mat_alloc(&C, P->n_b, P->n_ccols, P->nnz_c));
     created = true;
     cudaMemcpyAsync(C->rowptr, P->c_rowptr, ((size_t)P->n_b + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c.stream);
     if (P->nnz_c) cudaMemcpyAsync(C->colind, P->c_colind, (size_t)P->nnz_c * sizeof(int), cudaMemcpyDeviceToDevice, c.stream);
@@ -856,11 +875,12 @@ static int ptap_numeric_impl(Plan *P, Mat *M, Mat *A, Mat **C_io) {
   int rc = IIFE_OK;
   do {
     // refresh the values of M^T unless they are already those of this M
-    if ((rc = gather_vals_launch(M->val, P->mt_perm, P->MT->val, P->nnzM)) != IIFE_OK) break;
+    if (!R && (rc = gather_vals_launch(M->val, P->mt_perm, P->MT->val, P->nnzM)) != IIFE_OK) break;
+    Mat *Rm = R ? R : P->MT;
     PtapArgs a{};
-    a.mt_rowptr = P->MT->rowptr;
-    a.mt_col = P->MT->colind;
-    a.mt_val = P->MT->val;
+    a.mt_rowptr = Rm->rowptr;
+    a.mt_col = Rm->colind;
+    a.mt_val = Rm->val;
     a.a_rowptr = A->rowptr;
     a.a_col = A->colind;
     a.a_val = A->val;
@@ -967,7 +987,7 @@ int iife_ptap_symbolic(iife_mat M_, iife_mat A_, iife_plan *out) {
   if (!M_ || !A_ || !out) return set_err(IIFE_ERR_ARG, "NULL argument");
   *out = nullptr;
   Plan *P = nullptr;
-  IIFE_TRY(ptap_symbolic_impl((Mat *)M_, (Mat *)A_, &P));
+  IIFE_TRY(ptap_symbolic_impl(nullptr, (Mat *)M_, (Mat *)A_, &P));
   *out = (iife_plan)P;
   return IIFE_OK;
 }
@@ -996,7 +1016,26 @@ int iife_ptap_numeric(iife_plan P_, iife_mat M_, iife_mat A_, iife_mat *C) {
   IIFE_NEED_INIT();
   if (!P_ || !M_ || !A_ || !C) return set_err(IIFE_ERR_ARG, "NULL argument");
   Mat *Cm = (Mat *)*C;
-  IIFE_TRY(ptap_numeric_impl((Plan *)P_, (Mat *)M_, (Mat *)A_, &Cm));
+  IIFE_TRY(ptap_numeric_impl((Plan *)P_, nullptr, (Mat *)M_, (Mat *)A_, &Cm));
+  *C = (iife_mat)Cm;
+  return IIFE_OK;
+}
+
+int iife_rap_symbolic(iife_mat R_, iife_mat A_, iife_mat P_, iife_plan *out) {
+  IIFE_NEED_INIT();
+  if (!R_ || !A_ || !P_ || !out) return set_err(IIFE_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  Plan *P = nullptr;
+  IIFE_TRY(ptap_symbolic_impl((Mat *)R_, (Mat *)P_, (Mat *)A_, &P));
+  *out = (iife_plan)P;
+  return IIFE_OK;
+}
+
+int iife_rap_numeric(iife_plan plan_, iife_mat R_, iife_mat A_, iife_mat P_, iife_mat *C) {
+  IIFE_NEED_INIT();
+  if (!plan_ || !R_ || !A_ || !P_ || !C) return set_err(IIFE_ERR_ARG, "NULL argument");
+  Mat *Cm = (Mat *)*C;
+  IIFE_TRY(ptap_numeric_impl((Plan *)plan_, (Mat *)R_, (Mat *)P_, (Mat *)A_, &Cm));
   *C = (iife_mat)Cm;
   return IIFE_OK;
 }
@@ -1044,7 +1083,7 @@ int iife_ptap(iife_mat M_, iife_mat A_, iife_mat *C, int *plan_was_cached) {
     }
   if (plan_was_cached) *plan_was_cached = P ? 1 : 0;
   if (!P) {
-    IIFE_TRY(ptap_symbolic_impl(M, A, &P));
+    IIFE_TRY(ptap_symbolic_impl(nullptr, M, A, &P));
     g_cache.push_front({fm, fa, P});
     while (g_cache.size() > CACHE_MAX) {
       plan_free(g_cache.back().plan);
@@ -1052,7 +1091,7 @@ int iife_ptap(iife_mat M_, iife_mat A_, iife_mat *C, int *plan_was_cached) {
     }
   }
   Mat *Cm = nullptr;
-  IIFE_TRY(ptap_numeric_impl(P, M, A, &Cm));
+  IIFE_TRY(ptap_numeric_impl(P, nullptr, M, A, &Cm));
   *C = (iife_mat)Cm;
   return IIFE_OK;
 }

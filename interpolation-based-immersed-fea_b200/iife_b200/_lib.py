@@ -32,6 +32,7 @@ PROTOTYPES = {
     "iife_device_bytes": (c_int, [P(c_i64)]),
     "iife_launch_count": (c_int, [P(c_i64), c_int]),
     "iife_mat_create_csr": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_int, P(c_vp)]),
+    "iife_mat_create_csr_ex": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, P(c_vp)]),
     "iife_mat_update_values": (c_int, [c_vp, c_vp, c_int]),
     "iife_mat_get_info": (c_int, [c_vp, P(c_i64), P(c_i64), P(c_i64)]),
     "iife_mat_get_csr": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int]),
@@ -44,6 +45,8 @@ PROTOTYPES = {
     "iife_ptap_symbolic": (c_int, [c_vp, c_vp, P(c_vp)]),
     "iife_plan_matches": (c_int, [c_vp, c_vp, c_vp, P(c_int)]),
     "iife_plan_get_info": (c_int, [c_vp, P(c_i64), P(c_i64), P(c_i64)]),
+    "iife_rap_symbolic": (c_int, [c_vp, c_vp, c_vp, P(c_vp)]),
+    "iife_rap_numeric": (c_int, [c_vp, c_vp, c_vp, c_vp, P(c_vp)]),
     "iife_plan_check": (c_int, [c_vp]),
     "iife_ptap_numeric": (c_int, [c_vp, c_vp, c_vp, P(c_vp)]),
     "iife_plan_destroy": (c_int, [c_vp]),
