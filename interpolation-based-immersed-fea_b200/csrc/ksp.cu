@@ -620,26 +620,42 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     c.launches = before;  // captured, not launched yet
   }
   KSP_DBG("graph capture+inst");
+  // Chunks are enqueued two deep: the flag readback of chunk k is awaited while chunk k+1 already
+  // runs, so host scheduling jitter between chunks never idles the GPU (after convergence the chunk
+  // in flight is a row of no-op kernels).
   int rc = IIFE_OK;
   int64_t enq = 0;
-  while (rc == IIFE_OK) {
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+  auto enqueue_chunk = [&](int slot) -> int {
     if (exec) {
       cudaError_t e = cudaGraphLaunch(exec, c.stream);
-      if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e)); break; }
+      if (e != cudaSuccess) return set_err(IIFE_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
       c.launches += launches_per_chunk;
     } else {
-      for (int k = 0; k < chunk && rc == IIFE_OK; ++k) rc = enqueue_iteration();
-      if (rc != IIFE_OK) break;
-      cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "CG launch: %s", cudaGetErrorString(e)); break; }
+      for (int k = 0; k < chunk; ++k) IIFE_TRY(enqueue_iteration());
+      IIFE_CUDA(cudaGetLastError());
     }
+    IIFE_CUDA(cudaMemcpyAsync(hf[slot].fl, w.fl, sizeof(int) * F_COUNT, cudaMemcpyDeviceToHost, c.stream));
+    IIFE_CUDA(cudaEventRecord(ev[slot], c.stream));
     enq += chunk;
-    KSP_DBG("chunk enqueue");
-    if ((rc = poll_flags(w, hf)) != IIFE_OK) break;
-    KSP_DBG("chunk poll");
-    if (hf->fl[F_REASON] != 0) break;
-    if (enq > max_it + chunk) { rc = set_err(IIFE_ERR_STATE, "CG driver ran past max_it without a reason"); break; }
+    return IIFE_OK;
+  };
+  rc = enqueue_chunk(0);
+  if (rc == IIFE_OK) rc = enqueue_chunk(1);
+  for (int k = 0; rc == IIFE_OK; ++k) {
+    int slot = k & 1;
+    cudaError_t e = cudaEventSynchronize(ev[slot]);
+    if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "CG chunk: %s", cudaGetErrorString(e)); break; }
+    KSP_DBG("chunk done");
+    if (hf[slot].fl[F_REASON] != 0) break;
+    if (enq > max_it + 2 * (int64_t)chunk) { rc = set_err(IIFE_ERR_STATE, "CG driver ran past max_it without a reason"); break; }
+    rc = enqueue_chunk(slot);
   }
+  cudaStreamSynchronize(c.stream);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
   if (exec) cudaGraphExecDestroy(exec);
   if (graph) cudaGraphDestroy(graph);
   return rc;
@@ -820,8 +836,9 @@ static int ksp_solve_common(Mat *A, Halo *H, int ksp_type, int pc_type, double r
     bd = db.p;
     xd = dx.p;
   }
-  HostFlags *hf = nullptr;
-  IIFE_CUDA(cudaMallocHost((void **)&hf, sizeof(HostFlags)));
+  static HostFlags *hf_cached = nullptr;  // pinned, two slots, kept for the life of the process
+  if (!hf_cached) IIFE_CUDA(cudaMallocHost((void **)&hf_cached, 2 * sizeof(HostFlags)));
+  HostFlags *hf = hf_cached;
   int rc;
   if (n == 0 && !H) {
     rc = IIFE_OK;
@@ -850,7 +867,6 @@ static int ksp_solve_common(Mat *A, Halo *H, int ksp_type, int pc_type, double r
       res->rnorm0 = hsc[S_RHO0];
     }
   }
-  cudaFreeHost(hf);
   return rc;
 }
 

@@ -155,7 +155,7 @@ __global__ void k_sell_fill(const int *__restrict__ rowptr, const int *__restric
   }
 }
 
-template <bool DOT>
+template <bool DOT, int U>
 __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, const double *__restrict__ sell_val,
             int64_t n_rows, int64_t n_slices, const double *__restrict__ x, double *__restrict__ y,
@@ -173,20 +173,24 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, 
     const int *cp = sell_col + sb + lane;
     const double *vp = sell_val + sb + lane;
     const int width = (se - sb) >> 5;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    double a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = 0.0;
     int k = 0;
-    for (; k + 4 <= width; k += 4) {
-      int c0 = ld_stream(cp + (k + 0) * 32), c1 = ld_stream(cp + (k + 1) * 32);
-      int c2 = ld_stream(cp + (k + 2) * 32), c3 = ld_stream(cp + (k + 3) * 32);
-      double v0 = ld_stream(vp + (k + 0) * 32), v1 = ld_stream(vp + (k + 1) * 32);
-      double v2 = ld_stream(vp + (k + 2) * 32), v3 = ld_stream(vp + (k + 3) * 32);
-      a0 = fma(v0, __ldg(x + c0), a0);
-      a1 = fma(v1, __ldg(x + c1), a1);
-      a2 = fma(v2, __ldg(x + c2), a2);
-      a3 = fma(v3, __ldg(x + c3), a3);
+    for (; k + U <= width; k += U) {
+      int c[U];
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) c[u] = ld_stream(cp + (k + u) * 32);
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = ld_stream(vp + (k + u) * 32);
+#pragma unroll
+      for (int u = 0; u < U; ++u) a[u] = fma(v[u], __ldg(x + c[u]), a[u]);
     }
-    for (; k < width; ++k) a0 = fma(ld_stream(vp + k * 32), __ldg(x + ld_stream(cp + k * 32)), a0);
-    const double acc = (a0 + a1) + (a2 + a3);
+    for (; k < width; ++k) a[0] = fma(ld_stream(vp + k * 32), __ldg(x + ld_stream(cp + k * 32)), a[0]);
+    double acc = a[0];
+#pragma unroll
+    for (int u = 1; u < U; ++u) acc += a[u];
     const int64_t i = s * 32 + lane;
     if (i < n_rows) {
       y[i] = acc;
@@ -213,6 +217,50 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, 
       }
     }
   }
+}
+
+// grid = SMs x resident CTAs of THIS kernel (occupancy query), so the persistent loop has no tail wave
+template <class K>
+static int resident_grid(K kernel, int64_t need) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 4;
+  }
+  int64_t cap = (int64_t)ctx().sm_count * per_sm;
+  if (need > cap) need = cap;
+  if (need < 1) need = 1;
+  return (int)need;
+}
+
+static int sell_unroll() {
+  static int u = -1;
+  if (u < 0) {
+    const char *e = getenv("IIFE_SELL_UNROLL");
+    u = e ? atoi(e) : 4;
+    if (u != 2 && u != 4 && u != 8) u = 4;
+  }
+  return u;
+}
+
+static int launch_sell(const Mat *A, bool dot, const double *x, double *y, double *dot_out, double *partials,
+                       unsigned int *counter, const int *flag) {
+  int64_t need = (A->sell_slices + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
+#define SELL_GO(D, UU)                                                                                              \
+  {                                                                                                                 \
+    int g = resident_grid(k_spmv_sell<D, UU>, need);                                                                \
+    IIFE_LAUNCH((k_spmv_sell<D, UU>), g, SPMV_THREADS, 0, A->sell_ptr, A->sell_col, A->sell_val, A->n_rows,         \
+                A->sell_slices, x, y, dot_out, partials, counter, flag);                                            \
+  }
+  int u = sell_unroll();
+  if (dot) {
+    if (u == 2) SELL_GO(true, 2) else if (u == 8) SELL_GO(true, 8) else SELL_GO(true, 4)
+  } else {
+    if (u == 2) SELL_GO(false, 2) else if (u == 8) SELL_GO(false, 8) else SELL_GO(false, 4)
+  }
+#undef SELL_GO
+  IIFE_CHECK_LAUNCH();
+  return IIFE_OK;
 }
 
 void mat_free_sell(Mat *A) {
@@ -305,13 +353,8 @@ static int spmv_grid(int64_t n_rows, int lpr) {
 
 int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double *y) {
   if (A->n_rows == 0) return IIFE_OK;
-  if (sell_ready(A) && alpha == 1.0 && beta == 0.0) {
-    IIFE_LAUNCH((k_spmv_sell<false>), sell_grid(A->sell_slices), SPMV_THREADS, 0, A->sell_ptr, A->sell_col, A->sell_val,
-                A->n_rows, A->sell_slices, x, y, (double *)nullptr, (double *)nullptr, (unsigned int *)nullptr,
-                (const int *)nullptr);
-    IIFE_CHECK_LAUNCH();
-    return IIFE_OK;
-  }
+  if (sell_ready(A) && alpha == 1.0 && beta == 0.0)
+    return launch_sell(A, false, x, y, nullptr, nullptr, nullptr, nullptr);
   int lpr = spmv_pick_lpr(A);
   int g = spmv_grid(A->n_rows, lpr);
   bool plain = (alpha == 1.0 && beta == 0.0);
@@ -335,12 +378,7 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
 
 int spmv_dot_launch(const Mat *A, const double *p, double *w, double *dot_out, double *partials,
                     unsigned int *counter, const int *flag) {
-  if (sell_ready(A)) {
-    IIFE_LAUNCH((k_spmv_sell<true>), sell_grid(A->sell_slices), SPMV_THREADS, 0, A->sell_ptr, A->sell_col, A->sell_val,
-                A->n_rows, A->sell_slices, p, w, dot_out, partials, counter, flag);
-    IIFE_CHECK_LAUNCH();
-    return IIFE_OK;
-  }
+  if (sell_ready(A)) return launch_sell(A, true, p, w, dot_out, partials, counter, flag);
   int lpr = spmv_pick_lpr(A);
   int g = spmv_grid(A->n_rows, lpr);
 #define SPMVD_CASE(L)                                                                                            \
