@@ -122,6 +122,7 @@ int mat_max_row_len(Mat *A, int *out);
 // exclusive scan of int32 counts into int32 offsets (n+1 outputs: out[n] = total); total64 returned
 // on the host (synchronises the stream).
 int exclusive_scan_i32(const int *in, int *out, int64_t n, int64_t *total64);
+int exclusive_scan_i32_i64(const int *in, long long *out, int64_t n, int64_t *total64);
 
 // SpMV launchers (spmv.cu)
 int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double *y);

@@ -138,7 +138,8 @@ __global__ void scan_small_i64(long long *__restrict__ a, int nb) {
   if (threadIdx.x == 0) a[nb] = carry;
 }
 
-__global__ void scan_apply(const int *__restrict__ in, int *__restrict__ out, int64_t n,
+template <class OutT>
+__global__ void scan_apply(const int *__restrict__ in, OutT *__restrict__ out, int64_t n,
                            const long long *__restrict__ boff) {
   // thread t owns SCAN_ITEMS consecutive elements of the tile -> serial scan + warp/block scan of sums
   __shared__ long long wsum[SCAN_THREADS / 32];
@@ -167,12 +168,12 @@ __global__ void scan_apply(const int *__restrict__ in, int *__restrict__ out, in
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) {
     int64_t i = base + k;
-    if (i < n) out[i] = (int)run;
+    if (i < n) out[i] = (OutT)run;
     run += v[k];
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) {
     // total goes to out[n]
-    out[n] = (int)run;
+    out[n] = (OutT)run;
   }
 }
 
@@ -193,7 +194,7 @@ int exclusive_scan_i32(const int *in, int *out, int64_t n, int64_t *total64) {
   IIFE_TRY(bsum.alloc((size_t)nb + 1));
   IIFE_LAUNCH(scan_block_sums, nb, SCAN_THREADS, 0, in, n, bsum.p);
   IIFE_LAUNCH(scan_small_i64, 1, 1024, 0, bsum.p, nb);
-  IIFE_LAUNCH(scan_apply, nb, SCAN_THREADS, 0, in, out, n, bsum.p);
+  IIFE_LAUNCH(scan_apply<int>, nb, SCAN_THREADS, 0, in, out, n, bsum.p);
   IIFE_CHECK_LAUNCH();
   long long total = 0;
   IIFE_CUDA(cudaMemcpyAsync(&total, bsum.p + nb, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
@@ -201,6 +202,33 @@ int exclusive_scan_i32(const int *in, int *out, int64_t n, int64_t *total64) {
   if (total64) *total64 = total;
   if (total >= 0x7fffffffLL)
     return set_err(IIFE_ERR_UNSUPPORTED, "scan total %lld does not fit int32 indices", total);
+  return IIFE_OK;
+}
+
+__global__ void scan_empty64(long long *out) { out[0] = 0; }
+
+// same scan with 64-bit offsets (slot-plan offsets exceed 2^31 at the 50 M-DOF size)
+int exclusive_scan_i32_i64(const int *in, long long *out, int64_t n, int64_t *total64) {
+  Ctx &c = ctx();
+  if (n == 0) {
+    IIFE_LAUNCH(scan_empty64, 1, 1, 0, out);
+    IIFE_CHECK_LAUNCH();
+    if (total64) *total64 = 0;
+    return IIFE_OK;
+  }
+  int64_t nb64 = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb64 > 0x7fffffff) return set_err(IIFE_ERR_UNSUPPORTED, "scan of %lld elements too large", (long long)n);
+  int nb = (int)nb64;
+  Tmp<long long> bsum;
+  IIFE_TRY(bsum.alloc((size_t)nb + 1));
+  IIFE_LAUNCH(scan_block_sums, nb, SCAN_THREADS, 0, in, n, bsum.p);
+  IIFE_LAUNCH(scan_small_i64, 1, 1024, 0, bsum.p, nb);
+  IIFE_LAUNCH(scan_apply<long long>, nb, SCAN_THREADS, 0, in, out, n, bsum.p);
+  IIFE_CHECK_LAUNCH();
+  long long total = 0;
+  IIFE_CUDA(cudaMemcpyAsync(&total, bsum.p + nb, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+  IIFE_CUDA(cudaStreamSynchronize(c.stream));
+  if (total64) *total64 = total;
   return IIFE_OK;
 }
 

@@ -39,6 +39,8 @@ static const Level SYM_LEVELS[4] = {{1, 256, 10, 8}, {1, 128, 12, 10}, {0, 256, 
 static const Level NUM_LEVELS[5] = {{1, 256, 8, 6}, {1, 128, 10, 8}, {0, 128, 11, 10}, {0, 256, 13, 12}, {0, 256, 0, 0}};
 constexpr int N_SYM_LEVELS = 4;
 constexpr int N_NUM_LEVELS = 5;
+constexpr int N_BINS = 7;  // numeric bins: 0..4 hashing levels, 5..6 slot-plan rows (ptap_slots.cuh)
+constexpr int SLOT_CAP1[2] = {128, 256}, SLOT_CAP2[2] = {32, 256};
 
 struct Plan {
   uint64_t fpM = 0, fpA = 0, fpR = 0;
@@ -52,7 +54,12 @@ struct Plan {
   int64_t nnz_c = 0, nnz_inter = 0;
   int *n1 = nullptr;          // exact size of the intermediate row (M^T A_f)[i,:]
   int *bin_rows = nullptr;    // rows grouped by numeric level, ascending inside a level
-  int64_t bin_off[N_NUM_LEVELS + 1] = {0};
+  int64_t bin_off[N_BINS + 1] = {0};
+  // slot plan
+  unsigned char *slot1 = nullptr, *slot2 = nullptr;
+  long long *s1_off = nullptr, *s2_off = nullptr;
+  int *inter_rowptr = nullptr, *inter_col = nullptr;
+  int64_t s1_total = 0, s2_total = 0, inter_total = 0;
   int logG1 = 4, logG2 = 2;
   // global-memory tables of the last numeric level
   int g_log_cap1 = 0, g_log_cap2 = 0, g_ctas = 0;
@@ -278,7 +285,68 @@ struct PtapArgs {
   int *g_keys;
   double *g_vals;
   int *err_flag;
+  // slot plan (ptap_slots.cuh): the symbolic phase records, for every product term of a "slot row",
+  // the dense index of its destination (rank of the key in the sorted intermediate / output row)
+  int *e1, *e2;                     // count pass: number of stage-1 / stage-2 product terms of the row
+  const unsigned char *slot_row;    // fill pass: 1 if the row gets a slot plan
+  const long long *s1_off, *s2_off; // per-row offsets into slot1 / slot2
+  unsigned char *slot1, *slot2;
+  const int *inter_rowptr;          // sorted pattern of the intermediate rows (slot rows only)
+  int *inter_col;
 };
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int *total) {
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  *total = __shfl_sync(0xffffffffu, incl, 31);
+  return incl - v;
+}
+
+__device__ __forceinline__ int rank_sorted(const int *a, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// For the items (row ids in `ik`, n_items of them) of operand X, write for every entry the rank of its
+// column in the sorted key list `keys[0..nk)` as one byte at out[running offset].  One warp.
+__device__ __forceinline__ void warp_emit_slots(int n_items, const int *ik, const int *__restrict__ x_rowptr,
+                                                const int *__restrict__ x_col, int logG, const int *keys, int nk,
+                                                unsigned char *out, int lane) {
+  const int G = 1 << logG, NG = 32 >> logG;
+  const int g = lane >> logG, lg = lane & (G - 1);
+  long long base_off = 0;
+  for (int base = 0; base < n_items; base += 32) {
+    int q = base + lane;
+    int beg = 0, len = 0;
+    if (q < n_items) {
+      int r = ik[q];
+      beg = __ldg(x_rowptr + r);
+      len = __ldg(x_rowptr + r + 1) - beg;
+    }
+    int total;
+    int off = warp_excl_scan(len, lane, &total);
+    int cnt = min(32, n_items - base);
+    for (int it0 = 0; it0 < cnt; it0 += NG) {
+      int it = it0 + g;
+      int src = it & 31;
+      int b = __shfl_sync(0xffffffffu, beg, src);
+      int l = __shfl_sync(0xffffffffu, len, src);
+      int o = __shfl_sync(0xffffffffu, off, src);
+      if (it < cnt)
+        for (int e = lg; e < l; e += G) out[base_off + o + e] = (unsigned char)rank_sorted(keys, nk, __ldg(x_col + b + e));
+    }
+    base_off += total;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // symbolic kernels.  MODE 0: count (n1, n2, overflow list);  MODE 1: fill sorted C.col
@@ -323,6 +391,40 @@ __global__ void k_ptap_symbolic(PtapArgs a) {
     else n1 = cta_count(rt.h1k, cap1, rt.scratch);
     bool ovf = (rt.scratch[1] != 0) || (n1 > (cap1 / 4) * 3);
     int n2 = 0;
+    const bool slot_fill = WARP && MODE == 1 && a.slot_row && a.slot_row[i] && !ovf;
+    if (WARP && MODE == 0 && a.e1 && !ovf) {
+      // product-term counts of the two stages (sizes of the slot plan)
+      int s1 = 0, s2 = 0;
+      for (int q = t; q < mt_n; q += 32) {
+        int j = a.mt_col[mt_b + q];
+        s1 += a.a_rowptr[j + 1] - a.a_rowptr[j];
+      }
+      for (int q = t; q < n1; q += 32) {
+        int k = rt.h1k[q];
+        s2 += a.m_rowptr[k + 1] - a.m_rowptr[k];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (t == 0) {
+        a.e1[i] = s1;
+        a.e2[i] = s2;
+      }
+    }
+    if (slot_fill) {
+      // sorted intermediate pattern + destination index of every stage-1 product term
+      int P1 = 32;
+      while (P1 < n1) P1 <<= 1;
+      for (int s = n1 + t; s < P1; s += 32) rt.h1k[s] = EMPTY;
+      __syncwarp();
+      team_bitonic<true>(rt.h1k, P1, 32, t);
+      const int ib = a.inter_rowptr[i];
+      for (int s = t; s < n1; s += 32) a.inter_col[ib + s] = rt.h1k[s];
+      warp_emit_slots(mt_n, a.mt_col + mt_b, a.a_rowptr, a.a_col, a.logG1, rt.h1k, n1, a.slot1 + a.s1_off[i], t);
+      __syncwarp();
+    }
     if (!ovf) {
       // stage 2: keys of ((M^T A) M)[i,:]
       accumulate_items<WARP, false, true>(T, t, WARP ? n1 : cap1, rt.h1k, nullptr, a.m_rowptr, a.m_col, nullptr,
@@ -362,6 +464,10 @@ __global__ void k_ptap_symbolic(PtapArgs a) {
           if (t == 0) atomicExch(a.err_flag, 3);
         } else {
           for (int s = t; s < n2; s += T) a.c_col[cb + s] = rt.h2k[s];
+          if (slot_fill) {
+            team_sync<WARP>();
+            warp_emit_slots(n1, rt.h1k, a.m_rowptr, a.m_col, a.logG2, rt.h2k, n2, a.slot2 + a.s2_off[i], t);
+          }
         }
       }
     }
@@ -423,6 +529,7 @@ __global__ void k_ptap_numeric(PtapArgs a) {
 
 }  // namespace iife
 #include "ptap_warp.cuh"
+#include "ptap_slots.cuh"
 namespace iife {
 
 // ------------------------------------------------------------------------------------------------
@@ -435,15 +542,34 @@ __global__ void k_fill_schar(signed char *p, int64_t n, signed char v) {
 }
 
 // numeric level of each row from the exact counts; -1 for empty output rows
+// rows that get a slot plan: resolved by a warp-team symbolic level, both rows <= 256 entries.
+// Non-slot rows get zero sizes so that the plan arrays only hold slot rows.
+__global__ void k_slot_rows(const int *__restrict__ n1, const int *__restrict__ n2, const signed char *__restrict__ level,
+                            int64_t n, int enable, unsigned char *__restrict__ slot_row, int *__restrict__ e1,
+                            int *__restrict__ e2, int *__restrict__ n1m) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    bool s = enable && level[i] >= 0 && level[i] <= 1 && n2[i] > 0 && n1[i] <= 256 && n2[i] <= 256;
+    slot_row[i] = s ? 1 : 0;
+    if (!s) {
+      e1[i] = 0;
+      e2[i] = 0;
+    }
+    n1m[i] = s ? n1[i] : 0;
+  }
+}
+
 __global__ void k_numeric_level(const int *__restrict__ n1, const int *__restrict__ n2, int64_t n,
                                 signed char *__restrict__ lvl, int c10, int c20, int c11, int c21, int c12, int c22,
-                                int c13, int c23) {
+                                int c13, int c23, const unsigned char *__restrict__ slot_row) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     int a = n1[i], b = n2[i];
     signed char l;
     if (b == 0) l = -1;
+    else if (slot_row && slot_row[i]) l = (a <= 128 && b <= 32) ? 5 : 6;
     else if (2 * a <= c10 && 2 * b <= c20) l = 0;
     else if (2 * a <= c11 && 2 * b <= c21) l = 1;
     else if (2 * a <= c12 && 2 * b <= c22) l = 2;
@@ -565,6 +691,12 @@ static int plan_free(Plan *P) {
   if (P->g_keys) dev_free_t(P->g_keys, P->g_keys_n);
   if (P->g_vals) dev_free_t(P->g_vals, P->g_vals_n);
   if (P->err_flag) dev_free_t(P->err_flag, 1);
+  if (P->slot1) dev_free_t(P->slot1, (size_t)P->s1_total);
+  if (P->slot2) dev_free_t(P->slot2, (size_t)P->s2_total);
+  if (P->s1_off) dev_free_t(P->s1_off, (size_t)P->n_b + 1);
+  if (P->s2_off) dev_free_t(P->s2_off, (size_t)P->n_b + 1);
+  if (P->inter_rowptr) dev_free_t(P->inter_rowptr, (size_t)P->n_b + 1);
+  if (P->inter_col) dev_free_t(P->inter_col, (size_t)P->inter_total);
   delete P;
   return IIFE_OK;
 }
@@ -645,7 +777,8 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
   P->nnzR = R ? R->nnz : M->nnz;
   int rc = IIFE_OK;
   const int64_t n_b = P->n_b;
-  Tmp<int> n2, ovf_a, ovf_b, n_ovf, flag, off;
+  Tmp<int> n2, ovf_a, ovf_b, n_ovf, flag, off, e1, e2, n1m;
+  Tmp<unsigned char> slot_row;
   Tmp<signed char> level, nlevel;
   Tmp<int> sym_keys;  // global tables of the last symbolic level
   Tmp<unsigned long long> u64;
@@ -668,6 +801,12 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
     if ((rc = ovf_b.alloc((size_t)n_b)) != IIFE_OK) break;
     if ((rc = n_ovf.alloc(2)) != IIFE_OK) break;
     if ((rc = u64.alloc(1)) != IIFE_OK) break;
+    if ((rc = e1.alloc((size_t)n_b + 1)) != IIFE_OK) break;
+    if ((rc = e2.alloc((size_t)n_b + 1)) != IIFE_OK) break;
+    if ((rc = n1m.alloc((size_t)n_b + 1)) != IIFE_OK) break;
+    if ((rc = slot_row.alloc((size_t)n_b + 1)) != IIFE_OK) break;
+    cudaMemsetAsync(e1.p, 0, ((size_t)n_b + 1) * sizeof(int), c.stream);
+    cudaMemsetAsync(e2.p, 0, ((size_t)n_b + 1) * sizeof(int), c.stream);
     cudaMemsetAsync(P->err_flag, 0, sizeof(int), c.stream);
     cudaMemsetAsync(n_ovf.p, 0, 2 * sizeof(int), c.stream);
     cudaMemsetAsync(n2.p, 0, ((size_t)n_b + 1) * sizeof(int), c.stream);
@@ -690,6 +829,8 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
     a.logG1 = P->logG1;
     a.logG2 = P->logG2;
     a.err_flag = P->err_flag;
+    a.e1 = e1.p;
+    a.e2 = e2.p;
 
     // ---- count pass down the ladder
     int *lists[2] = {ovf_a.p, ovf_b.p};
@@ -770,6 +911,40 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
       P->nnz_inter = (int64_t)s;
     }
 
+    // ---- slot plan sizes (ptap_slots.cuh): which rows, offsets of their product terms
+    {
+      static const bool slots_on = !(getenv("IIFE_PTAP_SLOTS") && atoi(getenv("IIFE_PTAP_SLOTS")) == 0);
+      if (n_b) IIFE_LAUNCH(k_slot_rows, grid_for(n_b), 256, 0, P->n1, n2.p, level.p, n_b, slots_on ? 1 : 0, slot_row.p, e1.p, e2.p, n1m.p);
+      if ((rc = dev_alloc_t(&P->s1_off, (size_t)n_b + 1)) != IIFE_OK) break;
+      if ((rc = dev_alloc_t(&P->s2_off, (size_t)n_b + 1)) != IIFE_OK) break;
+      if ((rc = dev_alloc_t(&P->inter_rowptr, (size_t)n_b + 1)) != IIFE_OK) break;
+      if ((rc = exclusive_scan_i32_i64(e1.p, P->s1_off, n_b, &P->s1_total)) != IIFE_OK) break;
+      if ((rc = exclusive_scan_i32_i64(e2.p, P->s2_off, n_b, &P->s2_total)) != IIFE_OK) break;
+      int64_t it_total = 0;
+      rc = exclusive_scan_i32(n1m.p, P->inter_rowptr, n_b, &it_total);
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      int64_t need = P->s1_total + P->s2_total + 4 * it_total;
+      if (rc == IIFE_ERR_UNSUPPORTED || (rc == IIFE_OK && need > (int64_t)(free_b / 2))) {
+        // plan would not fit (int32 pattern offsets or memory): fall back to the hashing kernels
+        if (n_b) IIFE_LAUNCH(k_slot_rows, grid_for(n_b), 256, 0, P->n1, n2.p, level.p, n_b, 0, slot_row.p, e1.p, e2.p, n1m.p);
+        if ((rc = exclusive_scan_i32_i64(e1.p, P->s1_off, n_b, &P->s1_total)) != IIFE_OK) break;
+        if ((rc = exclusive_scan_i32_i64(e2.p, P->s2_off, n_b, &P->s2_total)) != IIFE_OK) break;
+        if ((rc = exclusive_scan_i32(n1m.p, P->inter_rowptr, n_b, &it_total)) != IIFE_OK) break;
+      }
+      if (rc != IIFE_OK) break;
+      P->inter_total = it_total;
+      if ((rc = dev_alloc_t(&P->slot1, (size_t)P->s1_total)) != IIFE_OK) break;
+      if ((rc = dev_alloc_t(&P->slot2, (size_t)P->s2_total)) != IIFE_OK) break;
+      if ((rc = dev_alloc_t(&P->inter_col, (size_t)P->inter_total)) != IIFE_OK) break;
+      a.slot_row = slot_row.p;
+      a.s1_off = P->s1_off;
+      a.s2_off = P->s2_off;
+      a.slot1 = P->slot1;
+      a.slot2 = P->slot2;
+      a.inter_rowptr = P->inter_rowptr;
+      a.inter_col = P->inter_col;
+    }
     // ---- fill pass: same traversal, same level per row, sorted columns written
     a.c_rowptr = P->c_rowptr;
     a.c_col = P->c_colind;
@@ -806,9 +981,9 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
       IIFE_LAUNCH(k_numeric_level, grid_for(n_b), 256, 0, P->n1, n2.p, n_b, nlevel.p, 1 << NUM_LEVELS[0].log_cap1,
                   1 << NUM_LEVELS[0].log_cap2, 1 << NUM_LEVELS[1].log_cap1, 1 << NUM_LEVELS[1].log_cap2,
                   1 << NUM_LEVELS[2].log_cap1, 1 << NUM_LEVELS[2].log_cap2, 1 << NUM_LEVELS[3].log_cap1,
-                  1 << NUM_LEVELS[3].log_cap2);
+                  1 << NUM_LEVELS[3].log_cap2, (const unsigned char *)slot_row.p);
     P->bin_off[0] = 0;
-    for (int l = 0; l < N_NUM_LEVELS; ++l) {
+    for (int l = 0; l < N_BINS; ++l) {
       int64_t cnt = 0;
       if (n_b) {
         IIFE_LAUNCH(k_level_flag, grid_for(n_b), 256, 0, nlevel.p, n_b, l, flag.p);
@@ -819,7 +994,7 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
     }
     if (rc != IIFE_OK) break;
     // global tables of the last numeric level
-    int64_t n_last = P->bin_off[N_NUM_LEVELS] - P->bin_off[N_NUM_LEVELS - 1];
+    int64_t n_last = P->bin_off[N_NUM_LEVELS] - P->bin_off[N_NUM_LEVELS - 1];  // bin 4 = global-memory tables
     if (n_last > 0) {
       const int *rows = P->bin_rows + P->bin_off[N_NUM_LEVELS - 1];
       int m1 = 0, m2 = 0;
@@ -893,6 +1068,47 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
     a.logG1 = P->logG1;
     a.logG2 = P->logG2;
     a.err_flag = P->err_flag;
+    a.s1_off = P->s1_off;
+    a.s2_off = P->s2_off;
+    a.slot1 = P->slot1;
+    a.slot2 = P->slot2;
+    a.inter_rowptr = P->inter_rowptr;
+    a.inter_col = P->inter_col;
+    for (int sb = 0; sb < 2; ++sb) {  // slot-plan rows (ptap_slots.cuh)
+      int l = N_NUM_LEVELS + sb;
+      int64_t cnt = P->bin_off[l + 1] - P->bin_off[l];
+      if (cnt == 0) continue;
+      a.rows = P->bin_rows + P->bin_off[l];
+      a.n_rows = cnt;
+      int lg1 = a.logG1 < 3 ? 3 : (a.logG1 > 5 ? 5 : a.logG1);
+      int lg2 = a.logG2 < 2 ? 2 : (a.logG2 > 5 ? 5 : a.logG2);
+      if (const char *e1v = getenv("IIFE_PTAP_LG1")) lg1 = atoi(e1v);
+      if (const char *e2v = getenv("IIFE_PTAP_LG2")) lg2 = atoi(e2v);
+      slot_kernel_t kern = pick_slot_kernel(lg1, lg2);
+      if (!kern) { rc = set_err(IIFE_ERR_ARG, "no slot kernel for group sizes 2^%d / 2^%d", lg1, lg2); break; }
+      int cap1 = SLOT_CAP1[sb], cap2 = SLOT_CAP2[sb];
+      size_t per_warp = ((size_t)(32 >> lg1) * cap1 + (size_t)(32 >> lg2) * cap2) * 8;
+      size_t smem_max = (size_t)(c.max_smem_optin ? c.max_smem_optin : 227 * 1024);
+      int wpc = 8;
+      if (const char *ew = getenv("IIFE_PTAP_WPC")) wpc = atoi(ew);
+      while (wpc > 1 && per_warp * wpc > smem_max / 2) wpc >>= 1;
+      size_t smem = per_warp * wpc;
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e)); break; }
+      }
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+      }
+      int64_t ctas = (cnt + wpc - 1) / wpc;
+      int64_t cap = (int64_t)c.sm_count * per_sm;
+      if (ctas > cap) ctas = cap;
+      kern<<<(int)ctas, wpc * 32, smem, c.stream>>>(a, cap1, cap2);
+      c.launches++;
+    }
+    if (rc != IIFE_OK) break;
     for (int l = 0; l < N_NUM_LEVELS; ++l) {
       int64_t cnt = P->bin_off[l + 1] - P->bin_off[l];
       if (cnt == 0) continue;

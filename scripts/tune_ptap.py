@@ -23,7 +23,7 @@ def t(reps=3):
         e0.record(stream); plan.numeric(M, A, C=C); e1.record(stream); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     return min(ts)
-combos = [("old", None, None, None)] + [("new", lg1, lg2, wpc) for lg1 in (4,) for lg2 in (2, 3) for wpc in (1, 2, 4, 8)] + [("new", 5, 2, 4), ("new", 3, 2, 4)]
+combos = [("new", lg1, lg2, wpc) for lg1 in (4,) for lg2 in (2, 3) for wpc in (2, 4, 8)]
 for kind, lg1, lg2, wpc in combos:
     for k in ("IIFE_PTAP_LG1", "IIFE_PTAP_LG2", "IIFE_PTAP_WPC"): os.environ.pop(k, None)
     if kind == "old":
