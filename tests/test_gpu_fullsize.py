@@ -1,0 +1,111 @@
+"""Full-size (BASELINE config 5, N_b = 184: 50.2 M foreground dofs) checks through size-independent
+properties of the extraction — the oracle cannot run this size in seconds, so parity is asserted through
+invariants the domain offers (SURVEY.md §8c iii, iv; closed-form sizes of §8d)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N = 184
+
+
+@pytest.fixture(scope="module")
+def cube(iife):
+    import torch
+
+    from iife_b200 import synthetic
+
+    # one stream for torch and the library: tensors produced by torch kernels feed library kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    iife.set_stream(stream.cuda_stream)
+    sz = synthetic.cube_sizes(N)
+    b_f = torch.empty(sz["n_f"], dtype=torch.float64, device="cuda:0")
+    A, M = iife.synth_cube(N, 1.0, b_f=b_f)
+    plan = iife.PtapPlan(M, A)
+    C = plan.numeric(M, A, check_errors=True)
+    return dict(A=A, M=M, C=C, plan=plan, b_f=b_f, sz=sz)
+
+
+def test_sizes_match_closed_forms(iife, cube):
+    from iife_b200 import synthetic
+
+    nnzA, nnzM, nnzC = synthetic.cube_nnz(N)
+    assert (nnzA, nnzM, nnzC) == (750387697, 169112377, 169112377)
+    assert cube["A"].nnz == nnzA and cube["M"].nnz == nnzM and cube["C"].nnz == nnzC
+    assert cube["C"].shape == (cube["sz"]["n_b"],) * 2 == (6331625, 6331625)
+    assert cube["plan"].info()["nnz_intermediate"] == 631518729
+
+
+def test_partition_of_unity_and_symmetry(iife, cube):
+    import torch
+
+    A, M, C, sz = cube["A"], cube["M"], cube["C"], cube["sz"]
+    ones_b = torch.ones(sz["n_b"], dtype=torch.float64, device="cuda:0")
+    ones_f = torch.ones(sz["n_f"], dtype=torch.float64, device="cuda:0")
+    # M 1 = 1 (rows of the extraction operator sum to one)
+    m1 = M.spmv(ones_b)
+    assert float((m1 - 1.0).abs().max()) < 1e-14
+    # 1^T A_b 1 = (M 1)^T A_f (M 1) = 1^T A_f 1
+    s_b = float(C.spmv(ones_b).sum())
+    s_f = float(A.spmv(ones_f).sum())
+    assert abs(s_b - s_f) <= 1e-11 * abs(s_f)
+    # A_f symmetric  =>  A_b symmetric: y^T (A_b x) == x^T (A_b y) for two fixed vectors
+    g = torch.Generator(device="cuda:0").manual_seed(0)
+    x = torch.rand(sz["n_b"], dtype=torch.float64, device="cuda:0", generator=g)
+    y = torch.rand(sz["n_b"], dtype=torch.float64, device="cuda:0", generator=g)
+    a, b = float(torch.dot(y, C.spmv(x))), float(torch.dot(x, C.spmv(y)))
+    assert abs(a - b) <= 1e-12 * abs(a)
+    # explicit transpose kernel: (M^T)^T-consistency  x^T (M^T f) == (M x)^T f
+    f = torch.rand(sz["n_f"], dtype=torch.float64, device="cuda:0", generator=g)
+    lhs = float(torch.dot(x, M.spmv(f, trans=True)))
+    rhs = float(torch.dot(M.spmv(x), f))
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+    # load: sum(b_b) = sum(b_f) (partition of unity again)
+    bb = M.spmv(cube["b_f"], trans=True)
+    assert abs(float(bb.sum()) - float(cube["b_f"].sum())) <= 1e-12 * float(cube["b_f"].sum())
+
+
+def test_numeric_is_linear_and_repeatable(iife, cube):
+    import torch
+
+    A, M, C, plan = cube["A"], cube["M"], cube["C"], cube["plan"]
+    _, _, vptr = A.device_ptrs()
+    v0 = C.values()
+    C2 = plan.numeric(M, A, check_errors=True)          # repeatable bit for bit
+    assert np.array_equal(C2.values(), v0)
+    # linearity in A_f: scaling the values by 2 (exact in fp64) scales A_b by exactly 2
+    n = A.nnz
+    tmp = _copy_from_device(vptr, n)
+    A.update_values(tmp * 2.0)
+    C3 = plan.numeric(M, A, check_errors=True)
+    assert np.array_equal(C3.values(), 2.0 * v0)
+    A.update_values(tmp)
+
+
+def _copy_from_device(ptr, n):
+    import torch
+
+    out = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    # device-to-device copy through torch on the library's value array wrapped as a CUDA array
+    class _Wrap:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+    out.copy_(torch.as_tensor(_Wrap(), device="cuda:0"))
+    torch.cuda.synchronize()
+    return out
+
+
+def test_cg_solves_the_full_system(iife, cube):
+    import torch
+
+    M, C, sz = cube["M"], cube["C"], cube["sz"]
+    bb = M.spmv(cube["b_f"], trans=True)
+    x = torch.zeros(sz["n_b"], dtype=torch.float64, device="cuda:0")
+    info = iife.ksp_solve(C, bb, x, iife.KSP_CG, iife.PC_JACOBI, rtol=1e-8, atol=1e-50)
+    assert info.reason == 2 and 100 < info.iterations < 2000
+    r = bb - C.spmv(x)
+    d = torch.as_tensor(C.diagonal(), device="cuda:0")
+    # the solver's criterion, recomputed independently: ||D^-1 (b - A x)|| <= rtol ||D^-1 b|| (small slack:
+    # the recurrence residual of CG drifts from the true residual by rounding)
+    assert float((r / d).norm()) <= 1.05e-8 * float((bb / d).norm())
+    assert abs(info.rnorm0 - float((bb / d).norm())) <= 1e-10 * info.rnorm0
