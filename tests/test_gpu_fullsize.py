@@ -48,7 +48,9 @@ def test_partition_of_unity_and_symmetry(iife, cube):
     # 1^T A_b 1 = (M 1)^T A_f (M 1) = 1^T A_f 1
     s_b = float(C.spmv(ones_b).sum())
     s_f = float(A.spmv(ones_f).sum())
-    assert abs(s_b - s_f) <= 1e-11 * abs(s_f)
+    # analytically 1^T K 1 = 0 and 1^T Mass 1 = volume = 1; the sums cancel entries of size ~1e-3 over
+    # 7.5e8 terms, so the attainable accuracy is ~1e-10
+    assert abs(s_b - 1.0) < 2e-9 and abs(s_f - 1.0) < 2e-9 and abs(s_b - s_f) < 2e-9
     # A_f symmetric  =>  A_b symmetric: y^T (A_b x) == x^T (A_b y) for two fixed vectors
     g = torch.Generator(device="cuda:0").manual_seed(0)
     x = torch.rand(sz["n_b"], dtype=torch.float64, device="cuda:0", generator=g)
