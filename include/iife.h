@@ -180,6 +180,15 @@ int iife_halo_create(int64_t n_owned, int64_t n_ghost, const int64_t *send_count
 /* fill x[n_owned .. n_owned+n_ghost) from the peers' owned entries (device pointer) */
 int iife_halo_exchange(iife_halo H, double *x_dev);
 int iife_halo_destroy(iife_halo H);
+/* NVLink peer-memory path of the row-partitioned solver (p2p.cu): export allocates the halo's peer-visible
+ * vector + mailbox and returns two 64-byte cudaIpc handles; the host framework all-gathers the handles of
+ * all ranks (rank order, 128 bytes each) and tells every rank where its send block starts inside each
+ * peer's vector (dst_start[q] = n_owned_q + offset of this rank's block in q's ghost section).  After
+ * attach, iife_ksp_solve_dist exchanges ghosts and reduces dot products with library kernels that store
+ * into peer memory, without NCCL calls inside the iteration. */
+int iife_halo_p2p_export(iife_halo H, void *handles128);
+int iife_halo_p2p_attach(iife_halo H, const void *all_handles, const int64_t *dst_start);
+int iife_halo_p2p_error(iife_halo H, int *err);
 /* row-partitioned y_local = A_local * [x_owned; x_ghost] (halo exchange + SpMV), device pointers */
 int iife_spmv_dist(iife_mat A_local, iife_halo H, double *x_dev, double *y_dev);
 /* row-partitioned KSP: A_local is n_owned x (n_owned + n_ghost), b and x are device vectors of the

@@ -129,7 +129,7 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
 // w = A p and *dot_out = sum_i p_i w_i over the rows of A (partials + deterministic last-block
 // reduce); if flag != nullptr and *flag != 0 the kernel is a no-op.
 int spmv_dot_launch(const Mat *A, const double *p, double *w, double *dot_out, double *partials,
-                    unsigned int *counter, const int *flag);
+                    unsigned int *counter, const int *flag, const struct P2PRed *red = nullptr);
 int spmv_pick_lpr(const Mat *A);
 // SELL-32 operator copy: builds it on first use (returns IIFE_OK with A->sell_state == -1 if the
 // padding would exceed 1.25x nnz, in which case callers stay on CSR) and refreshes values.
@@ -144,7 +144,37 @@ struct Halo {
   int *send_idx = nullptr;     // device [total_send]
   double *send_buf = nullptr;  // device [total_send]
   int64_t total_send = 0;
+  // ---- peer-memory path (p2p.cu): ghost entries are stored directly into the neighbours' vectors
+  // and the dot products are reduced through per-rank mailboxes, all over NVLink peer mappings
+  bool p2p = false;
+  int me = 0;
+  double *xbuf = nullptr;            // [n_owned + n_ghost], IPC-exported: the multiplied vector of the solver
+  struct Mailbox *mbox = nullptr;    // IPC-exported
+  double *peer_xbuf[16] = {nullptr};
+  struct Mailbox *peer_mbox[16] = {nullptr};
+  long long dst_start[16] = {0};     // where my block starts inside peer q's xbuf
+  unsigned char *send_peer = nullptr;  // device [total_send]: destination rank of every send entry
+  int *send_off_dev = nullptr;         // device [nranks+1]
+  unsigned long long *dev_seq = nullptr;  // device [3]: halo / allreduce sequence numbers, CG iteration counter
+  unsigned int *p2p_counter = nullptr;    // device [1]
+  int *p2p_err = nullptr;                 // device [1]
+  unsigned int send_mask = 0, recv_mask = 0;
 };
+
+constexpr int P2P_MAX_RANKS = 16;
+struct Mailbox {
+  double ar_vals[2][P2P_MAX_RANKS][4];
+  unsigned long long ar_flag[2][P2P_MAX_RANKS];
+  unsigned long long halo_flag[P2P_MAX_RANKS];
+  // reductions fused into the CG kernels (two per iteration, slot = sequence parity)
+  double it_vals[2][P2P_MAX_RANKS][4];
+  unsigned long long it_flag[2][P2P_MAX_RANKS];
+};
+// enqueue on the library stream: push ghost entries of H->xbuf to the peers and wait for mine
+int p2p_halo_exchange(Halo *H, const int *reason_flag);
+// in-place sum over ranks of vals[0..n) (n <= 4) through the mailboxes; mode 0: plain, 1: then the CG
+// update scalar step (ksp.cu supplies the kernel through p2p_set_cg_scalars)
+int p2p_allreduce(Halo *H, double *vals, int n, const int *reason_flag);
 int halo_exchange(Halo *H, double *x_dev);     // fills x[n_owned .. n_owned+n_ghost)
 int allreduce_sum(double *buf_dev, int64_t n);  // in place, on the library stream
 

@@ -14,6 +14,7 @@
 // per chunk; after convergence the remaining kernels of the chunk are no-ops.  There is no host
 // round trip per iteration.
 #include "common.cuh"
+#include "p2p_dev.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <chrono>
@@ -175,16 +176,32 @@ k_cg_p(const double *__restrict__ r, const double *__restrict__ dinv, double *__
 }
 
 // alpha = beta/delta; x += alpha p; r -= alpha w; z = D^-1 r; (z,r), (z,z) -> beta, dp, test(i+1)
-template <bool DIST>
+// MODE 0: single GPU (scalar step by the last CTA).  MODE 1: row-partitioned with NCCL (raw sums out).
+// MODE 2: row-partitioned over peer memory: delta is summed from the ranks' partials waiting in the
+// mailbox (prologue), the two new partial sums are pushed to every rank by the last CTA (epilogue).
+template <int MODE>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
             const double *__restrict__ w, const double *__restrict__ dinv, int64_t n, double *sc, int *fl,
-            double *partials, unsigned int *counter, double *hist, long long hist_len) {
+            double *partials, unsigned int *counter, double *hist, long long hist_len, P2PRed pr) {
   if (fl[F_REASON] != 0) return;
   __shared__ double red[32];
   __shared__ double out[2];
   __shared__ bool last;
-  double delta = sc[S_DELTA];
+  double delta;
+  if (MODE == 2) {
+    __shared__ double s_delta;
+    if (threadIdx.x == 0) {
+      double d;
+      p2p_wait_sum(pr, 2ull * (*pr.iter) + 1ull, &d, 1);
+      s_delta = d;
+      if (blockIdx.x == 0) sc[S_DELTA] = d;
+    }
+    __syncthreads();
+    delta = s_delta;
+  } else {
+    delta = sc[S_DELTA];
+  }
   if (!(delta > 0.0)) {
     // (p, A p) <= 0 or NaN: DIVERGED_INDEFINITE_MAT, no update (PETSc: its = i+1 at that point)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -207,14 +224,30 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
     acc[0] = fma(z, ri, acc[0]);
     acc[1] = fma(z, z, acc[1]);
   }
-  if (grid_reduce<2>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
-    if (DIST) {
-      sc[S_RAW + 0] = out[0];
-      sc[S_RAW + 1] = out[1];
-    } else {
-      cg_update_scalars(sc, fl, out[0], out[1], hist, hist_len);
+  if (grid_reduce<2>(acc, partials, counter, out, red, &last)) {
+    if (MODE == 2) {
+      p2p_push(pr, 2ull * (*pr.iter) + 2ull, out, 2, threadIdx.x);
+    } else if (threadIdx.x == 0) {
+      if (MODE == 1) {
+        sc[S_RAW + 0] = out[0];
+        sc[S_RAW + 1] = out[1];
+      } else {
+        cg_update_scalars(sc, fl, out[0], out[1], hist, hist_len);
+      }
     }
   }
+}
+
+// peer-memory path: wait for every rank's (z.r, z.z) partials, scalar step, advance the iteration counter
+__global__ void k_cg_scalars_p2p(double *sc, int *fl, double *hist, long long hist_len, P2PRed pr,
+                                 unsigned long long *iter) {
+  if (threadIdx.x != 0) return;
+  if (fl[F_REASON] != 0) return;
+  if (!(sc[S_DELTA] > 0.0)) return;  // reason was set by k_cg_update
+  double v[2];
+  p2p_wait_sum(pr, 2ull * (*iter) + 2ull, v, 2);
+  cg_update_scalars(sc, fl, v[0], v[1], hist, hist_len);
+  *iter = *iter + 1ull;
 }
 
 // row-partitioned solver: scalar step after the allreduce of the two raw sums
@@ -547,16 +580,36 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   const bool dist = (H != nullptr) && c.nranks > 1;
   const int64_t n_ext = H ? H->n_owned + H->n_ghost : n;  // owned + ghost entries of a multiplied vector
   double dbg_t0 = now_ms();
-  Tmp<double> r, p, wv;
+  // peer-memory path (p2p.cu): p lives in the halo's IPC-exported vector so that neighbours can store
+  // their boundary entries straight into its ghost section; exchanges are library kernels, not NCCL
+  const bool p2p = dist && H->p2p;
+  struct PBuf { double *p = nullptr; } p;
+  Tmp<double> r, p_own, wv;
   IIFE_TRY(r.alloc((size_t)n));
-  IIFE_TRY(p.alloc((size_t)n_ext));
+  if (p2p) p.p = H->xbuf;
+  else {
+    IIFE_TRY(p_own.alloc((size_t)n_ext));
+    p.p = p_own.p;
+  }
   IIFE_TRY(wv.alloc((size_t)n));
   const int g = vec_grid(n);
+  auto xchg = [&](const int *flag) -> int { return p2p ? p2p_halo_exchange(H, flag) : halo_exchange(H, p.p); };
+  auto ar = [&](double *v, int cnt, const int *flag) -> int { return p2p ? p2p_allreduce(H, v, cnt, flag) : allreduce_sum(v, cnt); };
+  P2PRed pr{};
+  if (p2p) {
+    pr.enabled = 1;
+    pr.me = H->me;
+    pr.nranks = H->nranks;
+    pr.mbox = H->mbox;
+    for (int q = 0; q < P2P_MAX_RANKS; ++q) pr.peer[q] = H->peer_mbox[q];
+    pr.iter = H->dev_seq + 2;
+    pr.err = H->p2p_err;
+  }
   // r = b - A x0   (row-partitioned: x0 is staged in p to receive its ghost entries)
   IIFE_LAUNCH(k_copy_gated, g, VEC_THREADS, 0, b, r.p, n, (const int *)nullptr);
   if (H) {
     IIFE_LAUNCH(k_copy_gated, g, VEC_THREADS, 0, (const double *)x, p.p, n, (const int *)nullptr);
-    if (dist) IIFE_TRY(halo_exchange(H, p.p));
+    if (dist) IIFE_TRY(xchg(nullptr));
     IIFE_TRY(spmv_launch(A, -1.0, p.p, 1.0, r.p));
   } else {
     IIFE_TRY(spmv_launch(A, -1.0, x, 1.0, r.p));
@@ -564,7 +617,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   if (dist) {
     IIFE_LAUNCH(k_cg_init<true>, g, VEC_THREADS, 0, r.p, b, dinv, n, w.sc, w.fl, w.partials, w.counters, w.hist,
                 (long long)w.hist_len);
-    IIFE_TRY(allreduce_sum(w.sc + S_RAW, 3));
+    IIFE_TRY(ar(w.sc + S_RAW, 3, nullptr));
     IIFE_LAUNCH(k_cg_init_scalars, 1, 1, 0, w.sc, w.fl, w.hist, (long long)w.hist_len);
   } else {
     IIFE_LAUNCH(k_cg_init<false>, g, VEC_THREADS, 0, r.p, b, dinv, n, w.sc, w.fl, w.partials, w.counters, w.hist,
@@ -579,20 +632,27 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   int chunk = env_int("IIFE_KSP_CHUNK", 32);
   if (chunk < 1) chunk = 1;
   // NCCL calls inside the loop: keep to plain stream launches (no graph capture) in that case
-  const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && !dist;
+  const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && (!dist || p2p);
   auto enqueue_iteration = [&]() -> int {
     IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl);
-    if (dist) IIFE_TRY(halo_exchange(H, p.p));
-    IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl));
-    if (dist) {
-      IIFE_TRY(allreduce_sum(w.sc + S_DELTA, 1));
-      IIFE_LAUNCH(k_cg_update<true>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
-                  w.hist, (long long)w.hist_len);
-      IIFE_TRY(allreduce_sum(w.sc + S_RAW, 2));
+    if (dist) IIFE_TRY(xchg(w.fl));
+    IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl,
+                             p2p ? &pr : nullptr));
+    if (p2p) {
+      // reductions ride inside the compute kernels: partials pushed by the producer's last CTA, summed
+      // in rank order by the consumer
+      IIFE_LAUNCH(k_cg_update<2>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
+                  w.hist, (long long)w.hist_len, pr);
+      IIFE_LAUNCH(k_cg_scalars_p2p, 1, 32, 0, w.sc, w.fl, w.hist, (long long)w.hist_len, pr, H->dev_seq + 2);
+    } else if (dist) {
+      IIFE_TRY(ar(w.sc + S_DELTA, 1, w.fl));
+      IIFE_LAUNCH(k_cg_update<1>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
+                  w.hist, (long long)w.hist_len, pr);
+      IIFE_TRY(ar(w.sc + S_RAW, 2, w.fl));
       IIFE_LAUNCH(k_cg_update_scalars, 1, 1, 0, w.sc, w.fl, w.hist, (long long)w.hist_len);
     } else {
-      IIFE_LAUNCH(k_cg_update<false>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
-                  w.hist, (long long)w.hist_len);
+      IIFE_LAUNCH(k_cg_update<0>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
+                  w.hist, (long long)w.hist_len, pr);
     }
     return IIFE_OK;
   };

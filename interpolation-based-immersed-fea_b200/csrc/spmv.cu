@@ -10,6 +10,7 @@
 // variant need a bounded scratch array and are reduced in a fixed order by the last CTA to finish
 // (bit-reproducible for a given launch geometry).
 #include "common.cuh"
+#include "p2p_dev.cuh"
 #include <stdlib.h>
 
 namespace iife {
@@ -64,7 +65,7 @@ template <int LPR>
 __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv_dot(const int *__restrict__ rowptr, const int *__restrict__ colind, const double *__restrict__ val,
            int64_t n_rows, const double *__restrict__ p, double *__restrict__ w, double *__restrict__ dot_out,
-           double *__restrict__ partials, unsigned int *__restrict__ counter, const int *__restrict__ flag) {
+           double *__restrict__ partials, unsigned int *__restrict__ counter, const int *__restrict__ flag, P2PRed pr) {
   if (flag && *flag != 0) return;
   constexpr int RPB = SPMV_THREADS / LPR;
   __shared__ double red[32];
@@ -100,9 +101,15 @@ k_spmv_dot(const int *__restrict__ rowptr, const int *__restrict__ colind, const
     double s = 0.0;
     for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += __ldcg(partials + k);
     s = block_sum(s, red);
+    __shared__ double s_sum;
     if (threadIdx.x == 0) {
       *dot_out = s;
       *counter = 0u;
+      s_sum = s;
+    }
+    if (pr.enabled) {  // row-partitioned solver: hand the partial to every rank (no wait here)
+      __syncthreads();
+      p2p_push(pr, 2ull * (*pr.iter) + 1ull, &s_sum, 1, threadIdx.x);
     }
   }
 }
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, const double *__restrict__ sell_val,
             int64_t n_rows, int64_t n_slices, const double *__restrict__ x, double *__restrict__ y,
             double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *__restrict__ counter,
-            const int *__restrict__ flag) {
+            const int *__restrict__ flag, P2PRed pr) {
   if (DOT && flag && *flag != 0) return;
   __shared__ double red[32];
   __shared__ bool is_last;
@@ -211,9 +218,15 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, 
       double sacc = 0.0;
       for (int kk = threadIdx.x; kk < (int)gridDim.x; kk += blockDim.x) sacc += __ldcg(partials + kk);
       sacc = block_sum(sacc, red);
+      __shared__ double s_sum;
       if (threadIdx.x == 0) {
         *dot_out = sacc;
         *counter = 0u;
+        s_sum = sacc;
+      }
+      if (pr.enabled) {  // row-partitioned solver: hand the partial to every rank (no wait here)
+        __syncthreads();
+        p2p_push(pr, 2ull * (*pr.iter) + 1ull, &s_sum, 1, threadIdx.x);
       }
     }
   }
@@ -244,13 +257,15 @@ static int sell_unroll() {
 }
 
 static int launch_sell(const Mat *A, bool dot, const double *x, double *y, double *dot_out, double *partials,
-                       unsigned int *counter, const int *flag) {
+                       unsigned int *counter, const int *flag, const P2PRed *red_in = nullptr) {
+  P2PRed pr{};
+  if (red_in) pr = *red_in;
   int64_t need = (A->sell_slices + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
 #define SELL_GO(D, UU)                                                                                              \
   {                                                                                                                 \
     int g = resident_grid(k_spmv_sell<D, UU>, need);                                                                \
     IIFE_LAUNCH((k_spmv_sell<D, UU>), g, SPMV_THREADS, 0, A->sell_ptr, A->sell_col, A->sell_val, A->n_rows,         \
-                A->sell_slices, x, y, dot_out, partials, counter, flag);                                            \
+                A->sell_slices, x, y, dot_out, partials, counter, flag, pr);                                        \
   }
   int u = sell_unroll();
   if (dot) {
@@ -377,13 +392,15 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
 }
 
 int spmv_dot_launch(const Mat *A, const double *p, double *w, double *dot_out, double *partials,
-                    unsigned int *counter, const int *flag) {
-  if (sell_ready(A)) return launch_sell(A, true, p, w, dot_out, partials, counter, flag);
+                    unsigned int *counter, const int *flag, const P2PRed *red) {
+  if (sell_ready(A)) return launch_sell(A, true, p, w, dot_out, partials, counter, flag, red);
+  P2PRed pr{};
+  if (red) pr = *red;
   int lpr = spmv_pick_lpr(A);
   int g = spmv_grid(A->n_rows, lpr);
 #define SPMVD_CASE(L)                                                                                            \
   case L:                                                                                                        \
-    IIFE_LAUNCH(k_spmv_dot<L>, g, SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, p, w, dot_out, partials, counter, flag); \
+    IIFE_LAUNCH(k_spmv_dot<L>, g, SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, p, w, dot_out, partials, counter, flag, pr); \
     break;
   switch (lpr) {
     SPMVD_CASE(2)

@@ -61,6 +61,9 @@ PROTOTYPES = {
     "iife_halo_create": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, P(c_vp)]),
     "iife_halo_exchange": (c_int, [c_vp, c_vp]),
     "iife_halo_destroy": (c_int, [c_vp]),
+    "iife_halo_p2p_export": (c_int, [c_vp, c_vp]),
+    "iife_halo_p2p_attach": (c_int, [c_vp, c_vp, c_vp]),
+    "iife_halo_p2p_error": (c_int, [c_vp, P(c_int)]),
     "iife_spmv_dist": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "iife_allreduce_sum": (c_int, [c_vp, c_i64]),
     "iife_alltoallv_bytes": (c_int, [c_vp, c_vp, c_vp, c_vp]),

@@ -142,8 +142,15 @@ def fetch_rows(rowptr, colind, val, row_start, part_t, wanted):
 
 
 def refresh_values(plan: RowFetchPlan, val):
-    """values of the fetched rows for new local values ``val`` (same pattern)."""
-    return torch.cat(alltoallv([val[p] for p in plan.gather_pos]))
+    """values of the fetched rows for new local values ``val`` (same pattern).  The block a rank "sends
+    to itself" is usually ALL of its rows in order: then it is passed through without a gather."""
+    rank, _ = _world()
+    if getattr(plan, "self_identity", None) is None:
+        p = plan.gather_pos[rank]
+        plan.self_identity = bool(p.numel() == val.numel() and (p.numel() == 0 or (int(p[0]) == 0 and int(p[-1]) == p.numel() - 1
+                                                                                   and bool((p[1:] > p[:-1]).all()))))
+    send = [val if (q == rank and plan.self_identity) else val[p] for q, p in enumerate(plan.gather_pos)]
+    return torch.cat(alltoallv(send))
 
 
 def fetch_entries(plan: RowFetchPlan, vec_local):
@@ -327,6 +334,30 @@ class DistExtraction:
         check(lib.iife_halo_create(int(halo["n_owned"]), int(halo["n_ghost"]), sc.ctypes.data_as(ctypes.c_void_p),
                                    si.ctypes.data_as(ctypes.c_void_p), rc.ctypes.data_as(ctypes.c_void_p), ctypes.byref(h)))
         self.halo = h
+        self.p2p = False
+        if self.world > 1 and self.world <= 16 and os.environ.get("IIFE_P2P", "1") != "0":
+            self._attach_p2p(halo)
+
+    def _attach_p2p(self, halo):
+        """NVLink peer-memory path: all-gather the IPC handles of every rank's solver vector + mailbox and
+        the offsets at which each rank's send block lands in its neighbours' ghost sections."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        raw = (ctypes.c_ubyte * 128)()
+        check(lib.iife_halo_p2p_export(self.halo, raw))
+        mine = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine)
+        # start of the block received from each source inside MY vector: n_owned + recv offset
+        rc = torch.tensor(halo["recv_counts"], dtype=torch.int64, device=dev)
+        starts = int(halo["n_owned"]) + torch.cumsum(rc, 0) - rc
+        all_starts = [torch.empty_like(starts) for _ in range(self.world)]
+        dist.all_gather(all_starts, starts)
+        dst = np.array([int(all_starts[q][self.rank].item()) for q in range(self.world)], dtype=np.int64)
+        blob = torch.cat(allh).cpu().numpy().tobytes()
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(lib.iife_halo_p2p_attach(self.halo, buf, dst.ctypes.data_as(ctypes.c_void_p)))
+        dist.barrier()
+        self.p2p = True
 
     def rhs(self, b_f_local):
         """b_b (owned block) = M^T b_f: the M^T block times the gathered entries of b_f."""
@@ -339,6 +370,11 @@ class DistExtraction:
         check(lib.iife_ksp_solve_dist(self.C_op.handle, self.halo, core.KSP_CG, core.PC_JACOBI, rtol, atol, 1e4,
                                       int(max_it), 300, ctypes.c_void_p(b_owned.data_ptr()),
                                       ctypes.c_void_p(x_owned.data_ptr()), ctypes.byref(res), None, 0))
+        if self.p2p:
+            err = ctypes.c_int(0)
+            check(lib.iife_halo_p2p_error(self.halo, ctypes.byref(err)))
+            if err.value:
+                raise RuntimeError("peer-memory exchange timed out (a rank did not arrive)")
         return core.KSPInfo(int(res.iterations), int(res.reason), float(res.rnorm), float(res.rnorm0), np.zeros(0))
 
 
@@ -382,11 +418,26 @@ def bench_distributed(args, I, stream, peak, peak_src, metric, unit):
     x = torch.zeros(ex.n_owned, dtype=torch.float64, device=dev)
     state = {}
 
+    debug = bool(os.environ.get("IIFE_BENCH_DEBUG"))
+
     def step():
+        if debug:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record(stream)
         ex.numeric(A_t[2])
+        if debug:
+            ev[1].record(stream)
         bb = ex.rhs(b_f)
         x.zero_()
+        if debug:
+            ev[2].record(stream)
         state["info"] = ex.solve(bb, x)
+        if debug:
+            ev[3].record(stream)
+            torch.cuda.synchronize()
+            if rank == 0:
+                print(f"[step r0] numeric {ev[0].elapsed_time(ev[1]):.2f} ms, rhs {ev[1].elapsed_time(ev[2]):.2f} ms, "
+                      f"cg {ev[2].elapsed_time(ev[3]):.2f} ms ({state['info'].iterations} its)", file=sys.stderr)
 
     def barrier():
         torch.cuda.synchronize()
