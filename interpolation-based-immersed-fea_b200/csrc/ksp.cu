@@ -191,11 +191,13 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
   double delta;
   if (MODE == 2) {
     __shared__ double s_delta;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
       double d;
       p2p_wait_sum(pr, 2ull * (*pr.iter) + 1ull, &d, 1);
-      s_delta = d;
-      if (blockIdx.x == 0) sc[S_DELTA] = d;
+      if (threadIdx.x == 0) {
+        s_delta = d;
+        if (blockIdx.x == 0) sc[S_DELTA] = d;
+      }
     }
     __syncthreads();
     delta = s_delta;
@@ -241,11 +243,11 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
 // peer-memory path: wait for every rank's (z.r, z.z) partials, scalar step, advance the iteration counter
 __global__ void k_cg_scalars_p2p(double *sc, int *fl, double *hist, long long hist_len, P2PRed pr,
                                  unsigned long long *iter) {
-  if (threadIdx.x != 0) return;
   if (fl[F_REASON] != 0) return;
   if (!(sc[S_DELTA] > 0.0)) return;  // reason was set by k_cg_update
   double v[2];
-  p2p_wait_sum(pr, 2ull * (*iter) + 2ull, v, 2);
+  p2p_wait_sum(pr, 2ull * (*iter) + 2ull, v, 2);  // one warp
+  if (threadIdx.x != 0) return;
   cg_update_scalars(sc, fl, v[0], v[1], hist, hist_len);
   *iter = *iter + 1ull;
 }
@@ -583,6 +585,8 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   // peer-memory path (p2p.cu): p lives in the halo's IPC-exported vector so that neighbours can store
   // their boundary entries straight into its ghost section; exchanges are library kernels, not NCCL
   const bool p2p = dist && H->p2p;
+  // timing experiments only (results are wrong with these set): drop the halo / the reductions
+  static const bool dbg_nohalo = getenv("IIFE_DBG_NOHALO") != nullptr, dbg_nored = getenv("IIFE_DBG_NORED") != nullptr;
   struct PBuf { double *p = nullptr; } p;
   Tmp<double> r, p_own, wv;
   IIFE_TRY(r.alloc((size_t)n));
@@ -635,10 +639,13 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && (!dist || p2p);
   auto enqueue_iteration = [&]() -> int {
     IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl);
-    if (dist) IIFE_TRY(xchg(w.fl));
+    if (dist && !dbg_nohalo) IIFE_TRY(xchg(w.fl));
     IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl,
-                             p2p ? &pr : nullptr));
-    if (p2p) {
+                             (p2p && !dbg_nored) ? &pr : nullptr));
+    if (dbg_nored) {
+      IIFE_LAUNCH(k_cg_update<0>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
+                  w.hist, (long long)w.hist_len, pr);
+    } else if (p2p) {
       // reductions ride inside the compute kernels: partials pushed by the producer's last CTA, summed
       // in rank order by the consumer
       IIFE_LAUNCH(k_cg_update<2>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,

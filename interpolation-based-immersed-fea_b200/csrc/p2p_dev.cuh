@@ -51,14 +51,20 @@ __device__ __forceinline__ void p2p_push(const P2PRed &r, unsigned long long seq
   }
 }
 
-// called by ONE thread: wait for all ranks' partials of reduction `seq`, add them in rank order
+// called by ONE WARP (all 32 lanes): lane q waits for rank q's partials of reduction `seq` and reads them
+// (the waits and the remote-written loads proceed in parallel instead of one after the other); lane 0
+// returns the sums added in rank order, so every rank gets bit-identical results.
 __device__ __forceinline__ void p2p_wait_sum(const P2PRed &r, unsigned long long seq, double *out, int n) {
+  const int lane = threadIdx.x & 31;
   const int par = (int)(seq & 1ull);
-  for (int q = 0; q < r.nranks; ++q) spin_until(&r.mbox->it_flag[par][q], seq, r.err);
-  __threadfence_system();
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  if (lane < r.nranks) {
+    spin_until(&r.mbox->it_flag[par][lane], seq, r.err);
+    for (int i = 0; i < n; ++i) v[i] = ((volatile double *)r.mbox->it_vals[par][lane])[i];
+  }
   for (int i = 0; i < n; ++i) {
     double s = 0.0;
-    for (int q = 0; q < r.nranks; ++q) s += ((volatile double *)r.mbox->it_vals[par][q])[i];
+    for (int q = 0; q < r.nranks; ++q) s += __shfl_sync(0xffffffffu, v[i], q);
     out[i] = s;
   }
 }

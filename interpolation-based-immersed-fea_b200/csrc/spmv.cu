@@ -241,7 +241,12 @@ static int resident_grid(K kernel, int64_t need) {
     per_sm = 4;
   }
   int64_t cap = (int64_t)ctx().sm_count * per_sm;
-  if (need > cap) need = cap;
+  if (need > cap) {
+    // even work per CTA: with a few items per warp (a rank's block of a partitioned operator) a grid of
+    // exactly `cap` CTAs leaves some warps one item more than others — a 15-25 % tail
+    int64_t per_cta = (need + cap - 1) / cap;
+    need = (need + per_cta - 1) / per_cta;
+  }
   if (need < 1) need = 1;
   return (int)need;
 }

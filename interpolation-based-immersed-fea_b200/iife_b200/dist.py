@@ -367,6 +367,8 @@ class DistExtraction:
     def solve(self, b_owned, x_owned, rtol=1e-8, atol=1e-9, max_it=1000000):
         core = self.core
         res = _lib.KspResult()
+        if os.environ.get("IIFE_DBG_FIXED_ITS"):  # timing experiments: exactly this many iterations
+            rtol, atol, max_it = 1e-300, 1e-300, int(os.environ["IIFE_DBG_FIXED_ITS"])
         check(lib.iife_ksp_solve_dist(self.C_op.handle, self.halo, core.KSP_CG, core.PC_JACOBI, rtol, atol, 1e4,
                                       int(max_it), 300, ctypes.c_void_p(b_owned.data_ptr()),
                                       ctypes.c_void_p(x_owned.data_ptr()), ctypes.byref(res), None, 0))
