@@ -60,6 +60,9 @@ struct Plan {
   long long *s1_off = nullptr, *s2_off = nullptr;
   int *inter_rowptr = nullptr, *inter_col = nullptr;
   int64_t s1_total = 0, s2_total = 0, inter_total = 0;
+  int *mt_abeg = nullptr, *inter_mbeg = nullptr;
+  unsigned char *mt_alen = nullptr, *inter_mlen = nullptr;
+  bool packed_meta = false;
   int logG1 = 4, logG2 = 2;
   // global-memory tables of the last numeric level
   int g_log_cap1 = 0, g_log_cap2 = 0, g_ctas = 0;
@@ -293,6 +296,10 @@ struct PtapArgs {
   unsigned char *slot1, *slot2;
   const int *inter_rowptr;          // sorted pattern of the intermediate rows (slot rows only)
   int *inter_col;
+  // packed operand-row metadata (start, length) per Mt entry / per intermediate entry: replaces the
+  // dependent rowptr gathers of the numeric kernel by coalesced loads (nullptr: gather from rowptr)
+  const int *mt_abeg, *inter_mbeg;
+  const unsigned char *mt_alen, *inter_mlen;
 };
 
 __device__ __forceinline__ int warp_excl_scan(int v, int lane, int *total) {
@@ -579,6 +586,21 @@ __global__ void k_numeric_level(const int *__restrict__ n1, const int *__restric
   }
 }
 
+// (start, length) of the operand row behind every entry of `ids` (Mt columns -> A rows; intermediate
+// columns -> M rows); lengths above 255 raise `bad` (the numeric kernel then gathers from rowptr)
+__global__ void k_row_meta(const int *__restrict__ ids, int64_t n, const int *__restrict__ x_rowptr,
+                           int *__restrict__ beg, unsigned char *__restrict__ len, int *__restrict__ bad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int r = ids[i];
+    int b = x_rowptr[r], l = x_rowptr[r + 1] - b;
+    beg[i] = b;
+    len[i] = (unsigned char)(l > 255 ? 255 : l);
+    if (l > 255) atomicOr(bad, 1);
+  }
+}
+
 __global__ void k_level_flag(const signed char *__restrict__ lvl, int64_t n, int which, int *__restrict__ flag) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -697,6 +719,10 @@ static int plan_free(Plan *P) {
   if (P->s2_off) dev_free_t(P->s2_off, (size_t)P->n_b + 1);
   if (P->inter_rowptr) dev_free_t(P->inter_rowptr, (size_t)P->n_b + 1);
   if (P->inter_col) dev_free_t(P->inter_col, (size_t)P->inter_total);
+  if (P->mt_abeg) dev_free_t(P->mt_abeg, (size_t)P->nnzR);
+  if (P->mt_alen) dev_free_t(P->mt_alen, (size_t)P->nnzR);
+  if (P->inter_mbeg) dev_free_t(P->inter_mbeg, (size_t)P->inter_total);
+  if (P->inter_mlen) dev_free_t(P->inter_mlen, (size_t)P->inter_total);
   delete P;
   return IIFE_OK;
 }
@@ -972,6 +998,21 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
     if ((rc = read_int(P->err_flag, &h_err)) != IIFE_OK) break;
     if (h_err) { rc = set_err(IIFE_ERR_STATE, "PtAP symbolic fill pass inconsistent with count pass (code %d)", h_err); break; }
 
+    // ---- packed operand-row metadata for the slot kernel
+    if (P->inter_total > 0 && !getenv("IIFE_PTAP_NOMETA")) {
+      Mat *Rm2 = R ? R : P->MT;
+      if ((rc = dev_alloc_t(&P->mt_abeg, (size_t)P->nnzR)) != IIFE_OK) break;
+      if ((rc = dev_alloc_t(&P->mt_alen, (size_t)P->nnzR)) != IIFE_OK) break;
+      if ((rc = dev_alloc_t(&P->inter_mbeg, (size_t)P->inter_total)) != IIFE_OK) break;
+      if ((rc = dev_alloc_t(&P->inter_mlen, (size_t)P->inter_total)) != IIFE_OK) break;
+      cudaMemsetAsync(n_ovf.p, 0, sizeof(int), c.stream);
+      IIFE_LAUNCH(k_row_meta, grid_for(P->nnzR), 256, 0, Rm2->colind, P->nnzR, A->rowptr, P->mt_abeg, P->mt_alen, n_ovf.p);
+      IIFE_LAUNCH(k_row_meta, grid_for(P->inter_total), 256, 0, P->inter_col, P->inter_total, M->rowptr, P->inter_mbeg,
+                  P->inter_mlen, n_ovf.p);
+      int bad = 0;
+      if ((rc = read_int(n_ovf.p, &bad)) != IIFE_OK) break;
+      P->packed_meta = (bad == 0);
+    }
     // ---- numeric row bins from the exact counts
     if ((rc = nlevel.alloc((size_t)n_b)) != IIFE_OK) break;
     if ((rc = flag.alloc((size_t)n_b + 1)) != IIFE_OK) break;
@@ -1074,6 +1115,10 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
     a.slot2 = P->slot2;
     a.inter_rowptr = P->inter_rowptr;
     a.inter_col = P->inter_col;
+    a.mt_abeg = P->packed_meta ? P->mt_abeg : nullptr;
+    a.mt_alen = P->packed_meta ? P->mt_alen : nullptr;
+    a.inter_mbeg = P->packed_meta ? P->inter_mbeg : nullptr;
+    a.inter_mlen = P->packed_meta ? P->inter_mlen : nullptr;
     for (int sb = 0; sb < 2; ++sb) {  // slot-plan rows (ptap_slots.cuh)
       int l = N_NUM_LEVELS + sb;
       int64_t cnt = P->bin_off[l + 1] - P->bin_off[l];

@@ -119,10 +119,15 @@ __global__ void __launch_bounds__(256) k_ptap_numeric_slots(PtapArgs a, int cap1
         int my_beg = 0, my_len = 0;
         double my_w = 0.0;
         if (q < mt_n) {
-          int j = __ldg(a.mt_col + mt_b + q);
           my_w = __ldg(a.mt_val + mt_b + q);
-          my_beg = __ldg(a.a_rowptr + j);
-          my_len = __ldg(a.a_rowptr + j + 1) - my_beg;
+          if (a.mt_abeg) {  // packed metadata: coalesced, no dependent gather
+            my_beg = __ldg(a.mt_abeg + mt_b + q);
+            my_len = (int)__ldg(a.mt_alen + mt_b + q);
+          } else {
+            int j = __ldg(a.mt_col + mt_b + q);
+            my_beg = __ldg(a.a_rowptr + j);
+            my_len = __ldg(a.a_rowptr + j + 1) - my_beg;
+          }
         }
         int total;
         int my_off = warp_excl_scan(my_len, lane, &total);
@@ -146,10 +151,15 @@ __global__ void __launch_bounds__(256) k_ptap_numeric_slots(PtapArgs a, int cap1
         int my_beg = 0, my_len = 0;
         double my_w = 0.0;
         if (q < n1) {
-          int k = __ldg(a.inter_col + ib + q);
           my_w = h1v[q];
-          my_beg = __ldg(a.m_rowptr + k);
-          my_len = __ldg(a.m_rowptr + k + 1) - my_beg;
+          if (a.inter_mbeg) {
+            my_beg = __ldg(a.inter_mbeg + ib + q);
+            my_len = (int)__ldg(a.inter_mlen + ib + q);
+          } else {
+            int k = __ldg(a.inter_col + ib + q);
+            my_beg = __ldg(a.m_rowptr + k);
+            my_len = __ldg(a.m_rowptr + k + 1) - my_beg;
+          }
         }
         int total;
         int my_off = warp_excl_scan(my_len, lane, &total);
