@@ -110,6 +110,9 @@ struct Mat {
   int *sell_col = nullptr;
   double *sell_val = nullptr;
   bool sell_vals_valid = false;
+  // row-partitioned solver: slice order "interior first" for the halo-fused SpMV
+  int *sell_order = nullptr;
+  int64_t sell_n_interior = 0, sell_order_owned = -1;
 };
 
 int mat_alloc(Mat **out, int64_t n_rows, int64_t n_cols, int64_t nnz);
@@ -134,6 +137,9 @@ int spmv_pick_lpr(const Mat *A);
 // SELL-32 operator copy: builds it on first use (returns IIFE_OK with A->sell_state == -1 if the
 // padding would exceed 1.25x nnz, in which case callers stay on CSR) and refreshes values.
 int mat_ensure_sell(Mat *A);
+int mat_ensure_sell_order(Mat *A, int64_t n_owned);
+int spmv_dot_halo_launch(const Mat *A, struct Halo *H, double *p, double *w, double *dot_out, double *partials,
+                         unsigned int *counter, const int *flag, const struct P2PRed *red);
 void mat_free_sell(Mat *A);
 
 // ghost-entry exchange plan of a row-partitioned operator (comm.cu)

@@ -633,15 +633,28 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   KSP_DBG("init poll");
   if (hf->fl[F_REASON] != 0) return IIFE_OK;
 
+  // peer-memory path with a SELL operator: optionally the ghost exchange rides inside the SpMV kernel
+  // (IIFE_P2P_FUSED_HALO=1).  Measured at 2 GPUs / 0.8 M rows per GPU it is ~8 % SLOWER than the separate
+  // exchange kernel (three-phase tails outweigh the hidden latency), so it is off by default.
+  bool fused_halo = false;
+  if (p2p && A->sell_state == 1 && env_int("IIFE_P2P_FUSED_HALO", 0) != 0 && !dbg_nohalo) {
+    IIFE_TRY(mat_ensure_sell_order(A, H->n_owned));
+    fused_halo = (A->sell_order != nullptr);
+  }
   int chunk = env_int("IIFE_KSP_CHUNK", 32);
   if (chunk < 1) chunk = 1;
   // NCCL calls inside the loop: keep to plain stream launches (no graph capture) in that case
   const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && (!dist || p2p);
   auto enqueue_iteration = [&]() -> int {
     IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl);
-    if (dist && !dbg_nohalo) IIFE_TRY(xchg(w.fl));
-    IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl,
-                             (p2p && !dbg_nored) ? &pr : nullptr));
+    if (fused_halo) {
+      IIFE_TRY(spmv_dot_halo_launch(A, H, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl,
+                                    dbg_nored ? nullptr : &pr));
+    } else {
+      if (dist && !dbg_nohalo) IIFE_TRY(xchg(w.fl));
+      IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl,
+                               (p2p && !dbg_nored) ? &pr : nullptr));
+    }
     if (dbg_nored) {
       IIFE_LAUNCH(k_cg_update<0>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
                   w.hist, (long long)w.hist_len, pr);

@@ -162,6 +162,40 @@ __global__ void k_sell_fill(const int *__restrict__ rowptr, const int *__restric
   }
 }
 
+// one SELL slice (32 rows, one per lane): returns this lane's row sum.  CG: gather x with ld.global.cg
+// (L2 only) — used for rows whose ghost entries were written by a peer GPU during this kernel.
+template <int U, bool CG = false>
+__device__ __forceinline__ double sell_slice(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col,
+                                             const double *__restrict__ sell_val, const double *__restrict__ x, int64_t s,
+                                             int lane) {
+  const int sb = __ldg(sell_ptr + s), se = __ldg(sell_ptr + s + 1);
+  const int *cp = sell_col + sb + lane;
+  const double *vp = sell_val + sb + lane;
+  const int width = (se - sb) >> 5;
+  double a[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) a[u] = 0.0;
+  int k = 0;
+  for (; k + U <= width; k += U) {
+    int c[U];
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = ld_stream(cp + (k + u) * 32);
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ld_stream(vp + (k + u) * 32);
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = fma(v[u], CG ? __ldcg(x + c[u]) : __ldg(x + c[u]), a[u]);
+  }
+  for (; k < width; ++k) {
+    const int c1 = ld_stream(cp + k * 32);
+    a[0] = fma(ld_stream(vp + k * 32), CG ? __ldcg(x + c1) : __ldg(x + c1), a[0]);
+  }
+  double acc = a[0];
+#pragma unroll
+  for (int u = 1; u < U; ++u) acc += a[u];
+  return acc;
+}
+
 template <bool DOT, int U>
 __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, const double *__restrict__ sell_val,
@@ -176,28 +210,7 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, 
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   double dsum = 0.0;
   for (int64_t s = w0; s < n_slices; s += nw) {
-    const int sb = __ldg(sell_ptr + s), se = __ldg(sell_ptr + s + 1);
-    const int *cp = sell_col + sb + lane;
-    const double *vp = sell_val + sb + lane;
-    const int width = (se - sb) >> 5;
-    double a[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) a[u] = 0.0;
-    int k = 0;
-    for (; k + U <= width; k += U) {
-      int c[U];
-      double v[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) c[u] = ld_stream(cp + (k + u) * 32);
-#pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = ld_stream(vp + (k + u) * 32);
-#pragma unroll
-      for (int u = 0; u < U; ++u) a[u] = fma(v[u], __ldg(x + c[u]), a[u]);
-    }
-    for (; k < width; ++k) a[0] = fma(ld_stream(vp + k * 32), __ldg(x + ld_stream(cp + k * 32)), a[0]);
-    double acc = a[0];
-#pragma unroll
-    for (int u = 1; u < U; ++u) acc += a[u];
+    const double acc = sell_slice<U>(sell_ptr, sell_col, sell_val, x, s, lane);
     const int64_t i = s * 32 + lane;
     if (i < n_rows) {
       y[i] = acc;
@@ -230,6 +243,147 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, 
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-partitioned solver, peer-memory path: SpMV + (p, Ap) with the ghost exchange INSIDE the kernel.
+//   phase 0  all CTAs store this rank's boundary entries of x into the neighbours' vectors; the last
+//            CTA to finish raises the sequence flags in their mailboxes
+//   phase 1  slices whose rows touch no ghost column (the bulk) are multiplied
+//   phase 2  every CTA waits for the flags of the ranks it receives from
+//   phase 3  the remaining (boundary) slices
+// so the NVLink latency of the exchange hides behind the interior rows.  `order` lists the interior
+// slices first (n_interior of them), then the boundary slices.
+// ------------------------------------------------------------------------------------------------
+struct HaloFused {
+  const int *send_idx;
+  const unsigned char *send_peer;
+  const int *send_off;
+  long long total_send;
+  PeerTable pt;
+  Mailbox *mbox;
+  int me, nranks;
+  unsigned int send_mask, recv_mask;
+  unsigned long long *seq_ptr;
+  unsigned int *push_counter;
+  int *err;
+};
+
+template <int U>
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_sell_halo(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, const double *__restrict__ sell_val,
+                 int64_t n_rows, int64_t n_slices, const int *__restrict__ order, int64_t n_interior, double *x,
+                 double *__restrict__ y, double *__restrict__ dot_out, double *__restrict__ partials,
+                 unsigned int *__restrict__ counter, const int *__restrict__ flag, P2PRed pr, HaloFused hf) {
+  if (flag && *flag != 0) return;
+  __shared__ double red[32];
+  __shared__ bool is_last;
+  __shared__ bool last_pusher;
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned long long seq = *hf.seq_ptr + 1ull;
+  // ---- phase 0: push
+  {
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    bool stored = false;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < hf.total_send; k += nthreads) {
+      int q = hf.send_peer[k];
+      hf.pt.xbuf[q][hf.pt.dst_start[q] + (k - hf.send_off[q])] = x[hf.send_idx[k]];
+      stored = true;
+    }
+    // only threads that stored need the system-scope fence (a fence invalidates the SM's L1, which the
+    // x gathers of the co-resident CTAs live on)
+    if (stored) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int t = atomicAdd(hf.push_counter, 1u);
+      last_pusher = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last_pusher) {
+      int q = threadIdx.x;
+      if (q < hf.nranks && ((hf.send_mask >> q) & 1u)) st_flag(&hf.pt.mbox[q]->halo_flag[hf.me], seq);
+    }
+  }
+  double dsum = 0.0;
+  // ---- phase 1: interior slices
+  for (int64_t idx = w0; idx < n_interior; idx += nw) {
+    const int64_t s = order[idx];
+    const double acc = sell_slice<U>(sell_ptr, sell_col, sell_val, x, s, lane);
+    const int64_t i = s * 32 + lane;
+    if (i < n_rows) {
+      y[i] = acc;
+      dsum = fma(acc, x[i], dsum);
+    }
+  }
+  // ---- phase 2: ghosts must have arrived
+  {
+    int q = threadIdx.x;
+    if (q < hf.nranks && ((hf.recv_mask >> q) & 1u)) spin_until(&hf.mbox->halo_flag[q], seq, hf.err);  // ld.acquire.sys
+    __syncthreads();  // ghost entries are then read with volatile (L1-bypassing) loads: no fence needed
+  }
+  // ---- phase 3: boundary slices (ghost entries are read with plain loads: written by peers during this kernel)
+  for (int64_t idx = n_interior + w0; idx < n_slices; idx += nw) {
+    const int64_t s = order[idx];
+    const double acc = sell_slice<U, true>(sell_ptr, sell_col, sell_val, x, s, lane);
+    const int64_t i = s * 32 + lane;
+    if (i < n_rows) {
+      y[i] = acc;
+      dsum = fma(acc, x[i], dsum);
+    }
+  }
+  double bs = block_sum(dsum, red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = bs;
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double sacc = 0.0;
+    for (int kk = threadIdx.x; kk < (int)gridDim.x; kk += blockDim.x) sacc += __ldcg(partials + kk);
+    sacc = block_sum(sacc, red);
+    __shared__ double s_sum;
+    if (threadIdx.x == 0) {
+      *dot_out = sacc;
+      *counter = 0u;
+      *hf.push_counter = 0u;
+      *hf.seq_ptr = seq;
+      s_sum = sacc;
+    }
+    if (pr.enabled) {
+      __syncthreads();
+      p2p_push(pr, 2ull * (*pr.iter) + 1ull, &s_sum, 1, threadIdx.x);
+    }
+  }
+}
+
+// slices whose rows reference a ghost column (col >= n_owned)
+__global__ void k_sell_ghost_flag(const int *__restrict__ sell_ptr, const int *__restrict__ sell_col, int64_t n_slices,
+                                  int n_owned, int *__restrict__ is_interior, int *__restrict__ is_boundary) {
+  int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = w; s < n_slices; s += nw) {
+    int sb = sell_ptr[s], se = sell_ptr[s + 1];
+    bool ghost = false;
+    for (int p = sb + lane; p < se; p += 32) ghost |= (sell_col[p] >= n_owned);
+    ghost = __any_sync(0xffffffffu, ghost);
+    if (lane == 0) {
+      is_interior[s] = ghost ? 0 : 1;
+      is_boundary[s] = ghost ? 1 : 0;
+    }
+  }
+}
+
+__global__ void k_sell_order(const int *__restrict__ is_interior, const int *__restrict__ off_int,
+                             const int *__restrict__ off_bnd, int64_t n_slices, int n_interior, int *__restrict__ order) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; s < n_slices; s += stride) order[is_interior[s] ? off_int[s] : n_interior + off_bnd[s]] = (int)s;
 }
 
 // grid = SMs x resident CTAs of THIS kernel (occupancy query), so the persistent loop has no tail wave
@@ -283,7 +437,71 @@ static int launch_sell(const Mat *A, bool dot, const double *x, double *y, doubl
   return IIFE_OK;
 }
 
+static int sell_grid(int64_t n_slices);
+static bool sell_ready(const Mat *A);
+
+int mat_ensure_sell_order(Mat *A, int64_t n_owned) {
+  if (A->sell_state != 1) return IIFE_OK;
+  if (A->sell_order && A->sell_order_owned == n_owned) return IIFE_OK;
+  if (A->sell_order) {
+    dev_free_t(A->sell_order, (size_t)A->sell_slices);
+    A->sell_order = nullptr;
+  }
+  const int64_t ns = A->sell_slices;
+  Tmp<int> fi, fb, oi, ob;
+  IIFE_TRY(fi.alloc((size_t)ns + 1));
+  IIFE_TRY(fb.alloc((size_t)ns + 1));
+  IIFE_TRY(oi.alloc((size_t)ns + 1));
+  IIFE_TRY(ob.alloc((size_t)ns + 1));
+  IIFE_LAUNCH(k_sell_ghost_flag, sell_grid(ns), SPMV_THREADS, 0, A->sell_ptr, A->sell_col, ns, (int)n_owned, fi.p, fb.p);
+  IIFE_CHECK_LAUNCH();
+  int64_t n_int = 0, n_bnd = 0;
+  IIFE_TRY(exclusive_scan_i32(fi.p, oi.p, ns, &n_int));
+  IIFE_TRY(exclusive_scan_i32(fb.p, ob.p, ns, &n_bnd));
+  IIFE_TRY(dev_alloc_t(&A->sell_order, (size_t)ns));
+  IIFE_LAUNCH(k_sell_order, sell_grid(ns), SPMV_THREADS, 0, fi.p, oi.p, ob.p, ns, (int)n_int, A->sell_order);
+  IIFE_CHECK_LAUNCH();
+  IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
+  A->sell_n_interior = n_int;
+  A->sell_order_owned = n_owned;
+  return IIFE_OK;
+}
+
+// SpMV + dot with the ghost exchange fused (peer-memory path of the row-partitioned CG)
+int spmv_dot_halo_launch(const Mat *A, Halo *H, double *p, double *w, double *dot_out, double *partials,
+                         unsigned int *counter, const int *flag, const P2PRed *red) {
+  if (!sell_ready(A) || !A->sell_order || !H->p2p) return set_err(IIFE_ERR_STATE, "fused halo SpMV needs SELL + order + p2p");
+  HaloFused hf;
+  hf.send_idx = H->send_idx;
+  hf.send_peer = H->send_peer;
+  hf.send_off = H->send_off_dev;
+  hf.total_send = H->total_send;
+  for (int q = 0; q < P2P_MAX_RANKS; ++q) {
+    hf.pt.xbuf[q] = H->peer_xbuf[q];
+    hf.pt.mbox[q] = H->peer_mbox[q];
+    hf.pt.dst_start[q] = H->dst_start[q];
+  }
+  hf.mbox = H->mbox;
+  hf.me = H->me;
+  hf.nranks = H->nranks;
+  hf.send_mask = H->send_mask;
+  hf.recv_mask = H->recv_mask;
+  hf.seq_ptr = H->dev_seq;
+  hf.push_counter = H->p2p_counter;
+  hf.err = H->p2p_err;
+  P2PRed pr{};
+  if (red) pr = *red;
+  int64_t need = (A->sell_slices + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
+  int g = resident_grid(k_spmv_sell_halo<4>, need);
+  IIFE_LAUNCH(k_spmv_sell_halo<4>, g, SPMV_THREADS, 0, A->sell_ptr, A->sell_col, A->sell_val, A->n_rows, A->sell_slices,
+              A->sell_order, A->sell_n_interior, p, w, dot_out, partials, counter, flag, pr, hf);
+  IIFE_CHECK_LAUNCH();
+  return IIFE_OK;
+}
+
 void mat_free_sell(Mat *A) {
+  if (A->sell_order) dev_free_t(A->sell_order, (size_t)A->sell_slices);
+  A->sell_order = nullptr;
   if (A->sell_ptr) dev_free_t(A->sell_ptr, (size_t)A->sell_slices + 1);
   if (A->sell_col) dev_free_t(A->sell_col, (size_t)A->sell_padded);
   if (A->sell_val) dev_free_t(A->sell_val, (size_t)A->sell_padded);
