@@ -232,7 +232,8 @@ int iife_spmv_dist(iife_mat A_, iife_halo H_, double *x_dev, double *y_dev) {
   Mat *A = (Mat *)A_;
   Halo *H = (Halo *)H_;
   if (!A || !H || !x_dev || !y_dev) return set_err(IIFE_ERR_ARG, "NULL argument");
-  if (A->n_rows != H->n_owned || A->n_cols != H->n_owned + H->n_ghost)
+  // rows may differ from the owned column block (M is n_f_local x n_b): only the column space must match
+  if (A->n_cols != H->n_owned + H->n_ghost)
     return set_err(IIFE_ERR_ARG, "operator %lld x %lld does not match the halo (%lld owned + %lld ghost)", (long long)A->n_rows,
                    (long long)A->n_cols, (long long)H->n_owned, (long long)H->n_ghost);
   IIFE_TRY(halo_exchange(H, x_dev));

@@ -267,7 +267,27 @@ struct GmresSmall {
   int m;  // restart
 };
 
+__device__ __forceinline__ void gm_cycle_scalars(double *sc, int *fl, GmresSmall gs, double vv, double bb2, int first_cycle,
+                                                 double *hist, long long hist_len) {
+  double res = sqrt(vv);
+  if (first_cycle) {
+    double rho0 = sqrt(bb2);
+    sc[S_RHO0] = rho0;
+    sc[S_TTOL] = fmax(sc[S_RTOL] * rho0, sc[S_ATOL]);
+    fl[F_ITS] = 0;
+    log_hist(hist, hist_len, 0, res);
+  }
+  sc[S_RES] = res;
+  gs.rs[0] = res;
+  sc[S_SCALE] = res != 0.0 ? 1.0 / res : 0.0;
+  fl[F_LOC_IT] = 0;
+  fl[F_HAPEND] = 0;
+  converged_default(sc, fl, fl[F_ITS], res);
+  if (fl[F_REASON] == 0 && fl[F_ITS] >= fl[F_MAXIT]) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
+}
+
 // ||v||^2 of the fresh residual in V0 -> rs[0], scale, test at cycle start (true residual)
+template <bool DIST>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_gm_cycle_start(const double *__restrict__ v0, const double *__restrict__ b, int64_t n, double *sc, int *fl,
                  GmresSmall gs, double *partials, unsigned int *counter, double *hist, long long hist_len,
@@ -287,22 +307,18 @@ k_gm_cycle_start(const double *__restrict__ v0, const double *__restrict__ b, in
     }
   }
   if (grid_reduce<2>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
-    double res = sqrt(out[0]);
-    if (first_cycle) {
-      double rho0 = sqrt(out[1]);
-      sc[S_RHO0] = rho0;
-      sc[S_TTOL] = fmax(sc[S_RTOL] * rho0, sc[S_ATOL]);
-      fl[F_ITS] = 0;
-      log_hist(hist, hist_len, 0, res);
+    if (DIST) {
+      sc[S_RAW + 0] = out[0];
+      sc[S_RAW + 1] = out[1];
+    } else {
+      gm_cycle_scalars(sc, fl, gs, out[0], out[1], first_cycle, hist, hist_len);
     }
-    sc[S_RES] = res;
-    gs.rs[0] = res;
-    sc[S_SCALE] = res != 0.0 ? 1.0 / res : 0.0;
-    fl[F_LOC_IT] = 0;
-    fl[F_HAPEND] = 0;
-    converged_default(sc, fl, fl[F_ITS], res);
-    if (fl[F_REASON] == 0 && fl[F_ITS] >= fl[F_MAXIT]) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
   }
+}
+
+__global__ void k_gm_cycle_scalars(double *sc, int *fl, GmresSmall gs, int first_cycle, double *hist, long long hist_len) {
+  if (fl[F_REASON] != 0) return;
+  gm_cycle_scalars(sc, fl, gs, sc[S_RAW + 0], sc[S_RAW + 1], first_cycle, hist, hist_len);
 }
 
 // v_j *= scale (normalise in place), z_j = D^-1 v_j
@@ -367,48 +383,12 @@ k_gm_dots(const double *__restrict__ w, double *const *__restrict__ V, int64_t n
   if (threadIdx.x == 0) *counter = 0u;
 }
 
-// classical Gram-Schmidt, part 2: w -= sum_k h_k v_k; ||w||^2; then (last CTA, one thread) the
-// Hessenberg/Givens update, residual estimate and convergence test of PETSc's KSPFGMRESCycle.
-constexpr int ROWS_PT = 2;
-__global__ void __launch_bounds__(VEC_THREADS)
-k_gm_update(double *__restrict__ w, double *const *__restrict__ V, int64_t n, int j, GmresSmall gs, double *sc,
-            int *fl, double *partials, unsigned int *counter, double *hist, long long hist_len) {
-  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != j) return;
-  extern __shared__ double hsh[];  // j+1 coefficients
-  __shared__ double red[32];
-  __shared__ double out[1];
-  __shared__ bool last;
-  const double *Hj = gs.H + (size_t)j * (gs.m + 1);
-  for (int k = threadIdx.x; k <= j; k += blockDim.x) hsh[k] = Hj[k];
-  __syncthreads();
-  double acc[1] = {0.0};
-  int64_t stride = (int64_t)gridDim.x * blockDim.x * ROWS_PT;
-  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x) * ROWS_PT + threadIdx.x; base < n; base += stride) {
-    double a[ROWS_PT];
-    int64_t idx[ROWS_PT];
-#pragma unroll
-    for (int r = 0; r < ROWS_PT; ++r) {
-      idx[r] = base + (int64_t)r * blockDim.x;
-      a[r] = idx[r] < n ? w[idx[r]] : 0.0;
-    }
-    for (int k = 0; k <= j; ++k) {
-      const double *vk = V[k];
-      double h = hsh[k];
-#pragma unroll
-      for (int r = 0; r < ROWS_PT; ++r)
-        if (idx[r] < n) a[r] = fma(-h, vk[idx[r]], a[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < ROWS_PT; ++r)
-      if (idx[r] < n) {
-        w[idx[r]] = a[r];
-        acc[0] = fma(a[r], a[r], acc[0]);
-      }
-  }
-  if (grid_reduce<1>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
+// Hessenberg / Givens update, residual estimate and convergence test of one FGMRES step (one thread)
+__device__ __forceinline__ void gm_update_scalars(GmresSmall gs, double *sc, int *fl, int j, double norm2, double *hist,
+                                                  long long hist_len) {
     const int m1 = gs.m + 1;
     double *hh = gs.H + (size_t)j * m1;
-    double tt = sqrt(out[0]);
+    double tt = sqrt(norm2);
     // happy breakdown test (fgmres.c): hapbnd = min(|tt / rs[j]|, haptol = 1e-30)
     double hapbnd = fabs(tt / gs.rs[j]);
     if (hapbnd > 1e-30) hapbnd = 1e-30;
@@ -455,7 +435,56 @@ k_gm_update(double *__restrict__ w, double *const *__restrict__ V, int64_t n, in
       if (hapend) fl[F_REASON] = IIFE_KSP_DIVERGED_BREAKDOWN;
       else if (its >= fl[F_MAXIT]) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
     }
+}
+
+// classical Gram-Schmidt, part 2: w -= sum_k h_k v_k; ||w||^2; then (last CTA, one thread) the
+// Hessenberg/Givens update, residual estimate and convergence test of PETSc's KSPFGMRESCycle.
+constexpr int ROWS_PT = 2;
+template <bool DIST>
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gm_update(double *__restrict__ w, double *const *__restrict__ V, int64_t n, int j, GmresSmall gs, double *sc,
+            int *fl, double *partials, unsigned int *counter, double *hist, long long hist_len) {
+  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != j) return;
+  extern __shared__ double hsh[];  // j+1 coefficients
+  __shared__ double red[32];
+  __shared__ double out[1];
+  __shared__ bool last;
+  const double *Hj = gs.H + (size_t)j * (gs.m + 1);
+  for (int k = threadIdx.x; k <= j; k += blockDim.x) hsh[k] = Hj[k];
+  __syncthreads();
+  double acc[1] = {0.0};
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * ROWS_PT;
+  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x) * ROWS_PT + threadIdx.x; base < n; base += stride) {
+    double a[ROWS_PT];
+    int64_t idx[ROWS_PT];
+#pragma unroll
+    for (int r = 0; r < ROWS_PT; ++r) {
+      idx[r] = base + (int64_t)r * blockDim.x;
+      a[r] = idx[r] < n ? w[idx[r]] : 0.0;
+    }
+    for (int k = 0; k <= j; ++k) {
+      const double *vk = V[k];
+      double h = hsh[k];
+#pragma unroll
+      for (int r = 0; r < ROWS_PT; ++r)
+        if (idx[r] < n) a[r] = fma(-h, vk[idx[r]], a[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS_PT; ++r)
+      if (idx[r] < n) {
+        w[idx[r]] = a[r];
+        acc[0] = fma(a[r], a[r], acc[0]);
+      }
   }
+  if (grid_reduce<1>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
+    if (DIST) sc[S_RAW + 0] = out[0];
+    else gm_update_scalars(gs, sc, fl, j, out[0], hist, hist_len);
+  }
+}
+
+__global__ void k_gm_update_scalars(GmresSmall gs, double *sc, int *fl, int j, double *hist, long long hist_len) {
+  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != j) return;
+  gm_update_scalars(gs, sc, fl, j, sc[S_RAW + 0], hist, hist_len);
 }
 
 // back substitution H(0:k,0:k) y = rs(0:k), k = loc_it, one warp
@@ -744,10 +773,16 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
 // ------------------------------------------------------------------------------------------------
 // FGMRES driver (device pointers)
 // ------------------------------------------------------------------------------------------------
-static int fgmres_solve(Mat *A, const double *dinv, const double *b, double *x, int64_t max_it, int restart,
+static int fgmres_solve(Mat *A, Halo *H, const double *dinv, const double *b, double *x, int64_t max_it, int restart,
                         KspWork &w, HostFlags *hf) {
   Ctx &c = ctx();
   const int64_t n = A->n_rows;
+  // row-partitioned (NCCL layer): z_j and x carry ghost entries for the SpMV, every reduction is followed by
+  // an allreduce and its scalar step runs in a one-thread kernel afterwards
+  const bool dist = (H != nullptr) && c.nranks > 1;
+  const int64_t n_ext = H ? H->n_owned + H->n_ghost : n;
+  Tmp<double> xe;
+  if (H) IIFE_TRY(xe.alloc((size_t)n_ext));
   int m = restart;
   if (m < 1) m = 30;
   if ((int64_t)m > max_it && max_it > 0) m = (int)max_it;
@@ -782,7 +817,7 @@ static int fgmres_solve(Mat *A, const double *dinv, const double *b, double *x, 
     if (need_v < 0) need_v = 0;
     if (need_z < 0) need_z = 0;
     if (need_v + need_z == 0) return IIFE_OK;
-    size_t n_pad = ((size_t)n + 31) & ~(size_t)31;  // keep every vector 256-byte aligned
+    size_t n_pad = ((size_t)n_ext + 31) & ~(size_t)31;  // keep every vector 256-byte aligned
     size_t count = (size_t)(need_v + need_z) * n_pad;
     double *slab = nullptr;
     IIFE_TRY(dev_alloc_t(&slab, count));
@@ -808,20 +843,40 @@ static int fgmres_solve(Mat *A, const double *dinv, const double *b, double *x, 
     // cycle start: V0 = b - A x
     if ((rc = ensure_vecs(chunk < m ? chunk : m, (chunk < m ? chunk : m) - 1)) != IIFE_OK) break;
     IIFE_LAUNCH(k_copy_gated, g, VEC_THREADS, 0, b, V[0], n, (const int *)w.fl);
-    if ((rc = spmv_launch(A, -1.0, x, 1.0, V[0])) != IIFE_OK) break;
-    IIFE_LAUNCH(k_gm_cycle_start, g, VEC_THREADS, 0, V[0], b, n, w.sc, w.fl, gs, w.partials, w.counters, w.hist,
-                (long long)w.hist_len, first_cycle ? 1 : 0);
+    if (H) {
+      IIFE_LAUNCH(k_copy_gated, g, VEC_THREADS, 0, (const double *)x, xe.p, n, (const int *)nullptr);
+      if (dist && (rc = halo_exchange(H, xe.p)) != IIFE_OK) break;
+      if ((rc = spmv_launch(A, -1.0, xe.p, 1.0, V[0])) != IIFE_OK) break;
+    } else if ((rc = spmv_launch(A, -1.0, x, 1.0, V[0])) != IIFE_OK) break;
+    if (dist) {
+      IIFE_LAUNCH(k_gm_cycle_start<true>, g, VEC_THREADS, 0, V[0], b, n, w.sc, w.fl, gs, w.partials, w.counters, w.hist,
+                  (long long)w.hist_len, first_cycle ? 1 : 0);
+      if ((rc = allreduce_sum(w.sc + S_RAW, 2)) != IIFE_OK) break;
+      IIFE_LAUNCH(k_gm_cycle_scalars, 1, 1, 0, w.sc, w.fl, gs, first_cycle ? 1 : 0, w.hist, (long long)w.hist_len);
+    } else {
+      IIFE_LAUNCH(k_gm_cycle_start<false>, g, VEC_THREADS, 0, V[0], b, n, w.sc, w.fl, gs, w.partials, w.counters, w.hist,
+                  (long long)w.hist_len, first_cycle ? 1 : 0);
+    }
     first_cycle = false;
     if ((rc = poll_flags(w, hf)) != IIFE_OK) break;
     if (hf->fl[F_REASON] != 0) { done = true; break; }
     for (int j = 0; j < m && rc == IIFE_OK; ++j) {
       IIFE_LAUNCH(k_gm_scale_pc, g, VEC_THREADS, 0, V[j], Z[j], dinv, n, w.sc, w.fl, j);
       // w = A z_j into V[j+1]  (harmless after convergence: V[j+1] is not read any more)
+      if (dist && (rc = halo_exchange(H, Z[j])) != IIFE_OK) break;
       if ((rc = spmv_launch(A, 1.0, Z[j], 0.0, V[j + 1])) != IIFE_OK) break;
       IIFE_LAUNCH(k_gm_dots, g, VEC_THREADS, 0, V[j + 1], (double *const *)vtab.p, n, j, gs, w.fl, mpart.p,
                   w.counters + 1);
-      IIFE_LAUNCH(k_gm_update, g, VEC_THREADS, (size_t)(j + 1) * sizeof(double), V[j + 1], (double *const *)vtab.p, n,
-                  j, gs, w.sc, w.fl, w.partials, w.counters, w.hist, (long long)w.hist_len);
+      if (dist) {
+        if ((rc = allreduce_sum(gs.H + (size_t)j * (gs.m + 1), j + 1)) != IIFE_OK) break;
+        IIFE_LAUNCH(k_gm_update<true>, g, VEC_THREADS, (size_t)(j + 1) * sizeof(double), V[j + 1], (double *const *)vtab.p,
+                    n, j, gs, w.sc, w.fl, w.partials, w.counters, w.hist, (long long)w.hist_len);
+        if ((rc = allreduce_sum(w.sc + S_RAW, 1)) != IIFE_OK) break;
+        IIFE_LAUNCH(k_gm_update_scalars, 1, 1, 0, gs, w.sc, w.fl, j, w.hist, (long long)w.hist_len);
+      } else {
+        IIFE_LAUNCH(k_gm_update<false>, g, VEC_THREADS, (size_t)(j + 1) * sizeof(double), V[j + 1], (double *const *)vtab.p,
+                    n, j, gs, w.sc, w.fl, w.partials, w.counters, w.hist, (long long)w.hist_len);
+      }
       ++enq_total;
       if ((j + 1) % chunk == 0 || j + 1 == m) {
         cudaError_t e = cudaGetLastError();
@@ -871,7 +926,6 @@ static int ksp_solve_common(Mat *A, Halo *H, int ksp_type, int pc_type, double r
   if (H && (A->n_rows != H->n_owned || A->n_cols != H->n_owned + H->n_ghost))
     return set_err(IIFE_ERR_ARG, "local operator %lld x %lld does not match the halo (%lld owned + %lld ghost)", (long long)A->n_rows,
                    (long long)A->n_cols, (long long)H->n_owned, (long long)H->n_ghost);
-  if (H && ksp_type != IIFE_KSP_CG) return set_err(IIFE_ERR_UNSUPPORTED, "the row-partitioned solver implements CG; FGMRES is single-GPU in this round");
   if (H && mem != IIFE_MEM_DEVICE) return set_err(IIFE_ERR_ARG, "the row-partitioned solver takes device vectors");
   if (ksp_type != IIFE_KSP_CG && ksp_type != IIFE_KSP_FGMRES) return set_err(IIFE_ERR_ARG, "unknown ksp_type %d", ksp_type);
   if (pc_type != IIFE_PC_NONE && pc_type != IIFE_PC_JACOBI) return set_err(IIFE_ERR_ARG, "unknown pc_type %d", pc_type);
@@ -927,7 +981,7 @@ static int ksp_solve_common(Mat *A, Halo *H, int ksp_type, int pc_type, double r
   } else if (ksp_type == IIFE_KSP_CG) {
     rc = cg_solve(A, H, dinv, bd, xd, max_it, w, hf);
   } else {
-    rc = fgmres_solve(A, dinv, bd, xd, max_it, restart, w, hf);
+    rc = fgmres_solve(A, H, dinv, bd, xd, max_it, restart, w, hf);
   }
   if (rc == IIFE_OK) {
     double hsc[S_COUNT] = {0};

@@ -364,13 +364,43 @@ class DistExtraction:
         bJ = fetch_entries(self.T.planA, b_f_local)
         return self.R.spmv(bJ)
 
-    def solve(self, b_owned, x_owned, rtol=1e-8, atol=1e-9, max_it=1000000):
+    def _halo_from(self, halo):
+        sc = np.asarray(halo["send_counts"], dtype=np.int64)
+        rc = np.asarray(halo["recv_counts"], dtype=np.int64)
+        si = halo["send_idx"].cpu().numpy().astype(np.int32)
+        h = ctypes.c_void_p(0)
+        check(lib.iife_halo_create(int(halo["n_owned"]), int(halo["n_ghost"]), sc.ctypes.data_as(ctypes.c_void_p),
+                                   si.ctypes.data_as(ctypes.c_void_p), rc.ctypes.data_as(ctypes.c_void_p), ctypes.byref(h)))
+        return h
+
+    def transfer_to_foreground(self, u_b_owned, M_loc):
+        """u_f (owned foreground rows) = M u_b with ghost entries of u_b fetched from their owners
+        (reference common.py:123-140 under MPI: Mat.mult + ghost update).  ``M_loc`` = this rank's rows of M
+        (rowptr, colind, val) with GLOBAL background column ids."""
+        core = self.core
+        dev = u_b_owned.device
+        if getattr(self, "_M_op", None) is None:
+            rp, ci, v = M_loc
+            # M's columns live in the BACKGROUND partition, its rows in the foreground one: the "owned" column
+            # block of this rank is its background block
+            local, G, halo = localize_operator(self.n_b, rp.to(torch.int64), ci.to(torch.int64), self.T.bg_part, self.rank)
+            self._M_op = _mat_from_tensors(core, (rp.numel() - 1, self.n_owned + int(G.numel())), rp, local, v, unsorted_ok=True)
+            self._M_halo = self._halo_from(halo)
+            self._M_xext = torch.zeros(self.n_owned + int(G.numel()), dtype=torch.float64, device=dev)
+        self._M_xext[: self.n_owned].copy_(u_b_owned)
+        u_f = torch.empty(self._M_op.shape[0], dtype=torch.float64, device=dev)
+        check(lib.iife_spmv_dist(self._M_op.handle, self._M_halo, ctypes.c_void_p(self._M_xext.data_ptr()),
+                                 ctypes.c_void_p(u_f.data_ptr())))
+        return u_f
+
+    def solve(self, b_owned, x_owned, rtol=1e-8, atol=1e-9, max_it=1000000, method="cg", restart=300):
         core = self.core
         res = _lib.KspResult()
+        ksp_type = core.KSP_CG if method == "cg" else core.KSP_FGMRES
         if os.environ.get("IIFE_DBG_FIXED_ITS"):  # timing experiments: exactly this many iterations
             rtol, atol, max_it = 1e-300, 1e-300, int(os.environ["IIFE_DBG_FIXED_ITS"])
-        check(lib.iife_ksp_solve_dist(self.C_op.handle, self.halo, core.KSP_CG, core.PC_JACOBI, rtol, atol, 1e4,
-                                      int(max_it), 300, ctypes.c_void_p(b_owned.data_ptr()),
+        check(lib.iife_ksp_solve_dist(self.C_op.handle, self.halo, ksp_type, core.PC_JACOBI, rtol, atol, 1e4,
+                                      int(max_it), int(restart), ctypes.c_void_p(b_owned.data_ptr()),
                                       ctypes.c_void_p(x_owned.data_ptr()), ctypes.byref(res), None, 0))
         if self.p2p:
             err = ctypes.c_int(0)

@@ -62,11 +62,25 @@ err = np.linalg.norm(x.cpu().numpy() - xg[b0:b1]) / np.linalg.norm(xg)
 assert info.reason == ig.reason == 2, (info.reason, ig.reason)
 assert abs(info.iterations - ig.iterations) <= 1, (info.iterations, ig.iterations)
 assert err <= 1e-8, err
+# FGMRES (restart shorter than the iteration count) over the NCCL layer
+xf = torch.zeros(b1 - b0, dtype=torch.float64, device=dev)
+infof = ex.solve(bb, xf, rtol=1e-10, atol=1e-50, method="gmres", restart=20)
+xgf = np.zeros(n_b)
+igf = I.ksp_solve(Cg, bbg, xgf, I.KSP_FGMRES, I.PC_JACOBI, rtol=1e-10, atol=1e-50, restart=20)
+errf = np.linalg.norm(xf.cpu().numpy() - xgf[b0:b1]) / np.linalg.norm(xgf)
+assert infof.reason == igf.reason == 2, (infof.reason, igf.reason)
+assert abs(infof.iterations - igf.iterations) <= 2, (infof.iterations, igf.iterations)
+assert errf <= 1e-8, errf
+# transferToForeground: u_f = M u_b with ghost entries of u_b
+u_f = ex.transfer_to_foreground(x, block(g["M"], f0, f1))
+u_f_ref = dM.spmv(xg)[f0:f1]
+assert np.allclose(u_f.cpu().numpy(), u_f_ref, rtol=1e-7, atol=1e-12 * np.abs(u_f_ref).max())
 # second numeric call with new values reuses the plan
 C2 = ex.numeric(A_loc_vals * 2.0)
 v2 = C2.values()
 assert np.allclose(v2, 2.0 * gv[sl], rtol=1e-14, atol=0)
 dist.barrier()
 if rank == 0:
-    print(f"dist_check ok: world={world} N_b={N} its={info.iterations} (single {ig.iterations}) sol_err={err:.2e}")
+    print(f"dist_check ok: world={world} N_b={N} cg its={info.iterations} (single {ig.iterations}) sol_err={err:.2e}; "
+          f"fgmres its={infof.iterations} (single {igf.iterations}) sol_err={errf:.2e}")
 dist.destroy_process_group()
