@@ -1165,8 +1165,7 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
       a.log_cap2 = global_tables ? P->g_log_cap2 : L.log_cap2;
       a.g_keys = global_tables ? P->g_keys : nullptr;
       a.g_vals = global_tables ? P->g_vals : nullptr;
-      static const bool use_old = getenv("IIFE_PTAP_OLD") != nullptr;
-      if (L.warp_team && !use_old) {
+      if (L.warp_team) {
         // privatised-table warp kernel (ptap_warp.cuh)
         int lg1 = a.logG1 < 3 ? 3 : (a.logG1 > 5 ? 5 : a.logG1);
         int lg2 = a.logG2 < 2 ? 2 : (a.logG2 > 5 ? 5 : a.logG2);
@@ -1206,13 +1205,8 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
       int64_t cap = (int64_t)c.sm_count * max_ctas_sm;
       if (ctas > cap) ctas = cap;
       if (global_tables && ctas > P->g_ctas) ctas = P->g_ctas;
-      if (L.warp_team) {
-        if ((rc = set_smem(k_ptap_numeric<true>, smem)) != IIFE_OK) break;
-        IIFE_LAUNCH(k_ptap_numeric<true>, (int)ctas, L.threads, smem, a);
-      } else {
-        if ((rc = set_smem(k_ptap_numeric<false>, smem)) != IIFE_OK) break;
-        IIFE_LAUNCH(k_ptap_numeric<false>, (int)ctas, L.threads, smem, a);
-      }
+      if ((rc = set_smem(k_ptap_numeric<false>, smem)) != IIFE_OK) break;
+      IIFE_LAUNCH(k_ptap_numeric<false>, (int)ctas, L.threads, smem, a);
     }
     if (rc != IIFE_OK) break;
     cudaError_t e = cudaGetLastError();
