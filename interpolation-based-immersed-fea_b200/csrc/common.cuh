@@ -107,7 +107,9 @@ struct Mat {
   int sell_state = 0;  // 0 not tried, 1 built, -1 rejected (padding too large)
   int64_t sell_slices = 0, sell_padded = 0;
   int *sell_ptr = nullptr;  // [sell_slices+1] entry offsets
-  int *sell_col = nullptr;
+  int *sell_cptr = nullptr;  // [sell_slices+1] offsets into sell_col (compact column words)
+  int64_t sell_cwords = 0;
+  int *sell_col = nullptr;   // per slice: `width` shared offsets (uniform slice) or width*32 explicit columns
   double *sell_val = nullptr;
   bool sell_vals_valid = false;
   // row-partitioned solver: slice order "interior first" for the halo-fused SpMV
