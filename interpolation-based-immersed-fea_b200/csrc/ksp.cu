@@ -705,6 +705,37 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     }
     return IIFE_OK;
   };
+  if (getenv("IIFE_KSP_TIMELINE") && !dist) {
+    // development aid: device timeline of the first iterations (events between the kernels)
+    const int NIT = 12;
+    const int tmask = atoi(getenv("IIFE_KSP_TIMELINE"));  // bit 0: p update, bit 1: SpMV+dot, bit 2: x/r update
+    cudaEvent_t ev[NIT * 3 + 1];
+    for (auto &e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], c.stream);
+    for (int k = 0; k < NIT; ++k) {
+      if (tmask & 1) IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl);
+      cudaEventRecord(ev[3 * k + 1], c.stream);
+      if (tmask & 2) {
+        P2PRed dbg{};
+        dbg.enabled = getenv("IIFE_DBG_DOTVAR") ? atoi(getenv("IIFE_DBG_DOTVAR")) : 0;
+        IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl, &dbg));
+      }
+      if (tmask & 8) IIFE_TRY(spmv_launch(A, 1.0, p.p, 0.0, wv.p));
+      cudaEventRecord(ev[3 * k + 2], c.stream);
+      if (tmask & 4) IIFE_LAUNCH(k_cg_update<0>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
+                  w.hist, (long long)w.hist_len, pr);
+      cudaEventRecord(ev[3 * k + 3], c.stream);
+    }
+    cudaStreamSynchronize(c.stream);
+    for (int k = NIT - 4; k < NIT; ++k) {
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, ev[3 * k], ev[3 * k + 1]);
+      cudaEventElapsedTime(&b, ev[3 * k + 1], ev[3 * k + 2]);
+      cudaEventElapsedTime(&d, ev[3 * k + 2], ev[3 * k + 3]);
+      fprintf(stderr, "[timeline] it %d: k_cg_p %.1f us, spmv_dot %.1f us, k_cg_update %.1f us\n", k, a * 1e3, b * 1e3, d * 1e3);
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+  }
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   int64_t launches_per_chunk = 0;

@@ -274,7 +274,7 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr,
             const double *__restrict__ sell_val, int64_t n_rows, int64_t n_slices, const double *__restrict__ x, double *__restrict__ y,
             double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *__restrict__ counter,
             const int *__restrict__ flag, P2PRed pr) {
-  if (DOT && flag && *flag != 0) return;
+  if (flag && *flag != 0) return;  // converged: the rest of the enqueued chunk is a row of no-ops
   __shared__ double red[32];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31;
@@ -463,6 +463,53 @@ __global__ void k_sell_order(const int *__restrict__ is_interior, const int *__r
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; s < n_slices; s += stride) order[is_interior[s] ? off_int[s] : n_interior + off_bnd[s]] = (int)s;
+}
+
+// (x, y) with the usual last-CTA fixed-order reduction (and the push to the peers' mailboxes in the
+// row-partitioned solver).  Used after the plain SELL SpMV: fusing the dot into the SpMV kernel made the
+// compiler serialise the slice's loads (392 us fused against 294 us plain + ~20 us for this kernel).
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_vec_dot(const double *__restrict__ x, const double *__restrict__ y, int64_t n, double *__restrict__ dot_out,
+          double *__restrict__ partials, unsigned int *__restrict__ counter, const int *__restrict__ flag, P2PRed pr) {
+  if (flag && *flag != 0) return;
+  __shared__ double red[32];
+  __shared__ bool is_last;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const double x0 = __ldg(x + i), x1 = __ldg(x + i + stride), x2 = __ldg(x + i + 2 * stride), x3 = __ldg(x + i + 3 * stride);
+    const double y0 = __ldcs(y + i), y1 = __ldcs(y + i + stride), y2 = __ldcs(y + i + 2 * stride), y3 = __ldcs(y + i + 3 * stride);
+    d0 = fma(x0, y0, d0);
+    d1 = fma(x1, y1, d1);
+    d2 = fma(x2, y2, d2);
+    d3 = fma(x3, y3, d3);
+  }
+  for (; i < n; i += stride) d0 = fma(__ldg(x + i), y[i], d0);
+  double bs = block_sum((d0 + d1) + (d2 + d3), red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = bs;
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double sacc = 0.0;
+    for (int kk = threadIdx.x; kk < (int)gridDim.x; kk += blockDim.x) sacc += __ldcg(partials + kk);
+    sacc = block_sum(sacc, red);
+    __shared__ double s_sum;
+    if (threadIdx.x == 0) {
+      *dot_out = sacc;
+      *counter = 0u;
+      s_sum = sacc;
+    }
+    if (pr.enabled) {
+      __syncthreads();
+      p2p_push(pr, 2ull * (*pr.iter) + 1ull, &s_sum, 1, threadIdx.x);
+    }
+  }
 }
 
 // grid = SMs x resident CTAs of THIS kernel (occupancy query), so the persistent loop has no tail wave
@@ -726,7 +773,19 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
 
 int spmv_dot_launch(const Mat *A, const double *p, double *w, double *dot_out, double *partials,
                     unsigned int *counter, const int *flag, const P2PRed *red) {
-  if (sell_ready(A)) return launch_sell(A, true, p, w, dot_out, partials, counter, flag, red);
+  if (sell_ready(A)) {
+    static const bool fused = getenv("IIFE_SELL_FUSED_DOT") != nullptr;
+    if (fused) return launch_sell(A, true, p, w, dot_out, partials, counter, flag, red);
+    // plain SpMV followed by the dot kernel, both gated by the reason flag
+    IIFE_TRY(launch_sell(A, false, p, w, nullptr, nullptr, nullptr, flag));
+    P2PRed pr2{};
+    if (red) pr2 = *red;
+    int64_t need = (A->n_rows + SPMV_THREADS * 4 - 1) / (SPMV_THREADS * 4);
+    int g = resident_grid(k_vec_dot, need);
+    IIFE_LAUNCH(k_vec_dot, g, SPMV_THREADS, 0, p, (const double *)w, A->n_rows, dot_out, partials, counter, flag, pr2);
+    IIFE_CHECK_LAUNCH();
+    return IIFE_OK;
+  }
   P2PRed pr{};
   if (red) pr = *red;
   int lpr = spmv_pick_lpr(A);
