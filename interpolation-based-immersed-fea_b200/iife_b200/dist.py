@@ -53,17 +53,20 @@ def _world():
     return (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
 
 
-def alltoallv(send, group=None):
+def alltoallv(send, group=None, recv_counts=None):
     """send[q] = 1-D tensor for rank q (all same dtype/device).  Returns the list received from each rank.
-    Counts travel with all_gather, payloads with batched isend/irecv (works with NCCL and gloo)."""
+    Counts travel with all_gather (skipped when the caller knows ``recv_counts`` from a stored plan: no host
+    synchronisation then), payloads with batched isend/irecv (works with NCCL and gloo)."""
     rank, world = _world()
     if world == 1:
         return [send[0]]
     dev, dtype = send[0].device, send[0].dtype
-    counts = torch.tensor([int(t.numel()) for t in send], dtype=torch.int64, device=dev)
-    gathered = [torch.empty_like(counts) for _ in range(world)]
-    dist.all_gather(gathered, counts, group=group)
-    recv = [torch.empty(int(gathered[q][rank].item()), dtype=dtype, device=dev) for q in range(world)]
+    if recv_counts is None:
+        counts = torch.tensor([int(t.numel()) for t in send], dtype=torch.int64, device=dev)
+        gathered = [torch.empty_like(counts) for _ in range(world)]
+        dist.all_gather(gathered, counts, group=group)
+        recv_counts = [int(gathered[q][rank].item()) for q in range(world)]
+    recv = [torch.empty(int(recv_counts[q]), dtype=dtype, device=dev) for q in range(world)]
     recv[rank] = send[rank]
     ops = []
     for q in range(world):
@@ -132,9 +135,13 @@ def fetch_rows(rowptr, colind, val, row_start, part_t, wanted):
         send_len.append(lens)
         send_col.append(colind[pos])
         send_val.append(val[pos])
-    lens_w = torch.cat(alltoallv(send_len))
-    col_w = torch.cat(alltoallv(send_col))
-    val_w = torch.cat(alltoallv(send_val))
+    lens_parts = alltoallv(send_len)
+    lens_w = torch.cat(lens_parts)
+    # element counts of the blocks this rank receives: static for the plan (value refreshes skip the count exchange)
+    plan.recv_entry_counts = [int(t.sum().item()) for t in lens_parts]
+    plan.recv_row_counts = [int(t.numel()) for t in lens_parts]
+    col_w = torch.cat(alltoallv(send_col, recv_counts=plan.recv_entry_counts))
+    val_w = torch.cat(alltoallv(send_val, recv_counts=plan.recv_entry_counts))
     rowptr_w = torch.zeros(wanted.numel() + 1, dtype=torch.int64, device=wanted.device)
     torch.cumsum(lens_w, 0, out=rowptr_w[1:])
     plan.rowptr, plan.colind = rowptr_w, col_w
@@ -150,12 +157,12 @@ def refresh_values(plan: RowFetchPlan, val):
         plan.self_identity = bool(p.numel() == val.numel() and (p.numel() == 0 or (int(p[0]) == 0 and int(p[-1]) == p.numel() - 1
                                                                                    and bool((p[1:] > p[:-1]).all()))))
     send = [val if (q == rank and plan.self_identity) else val[p] for q, p in enumerate(plan.gather_pos)]
-    return torch.cat(alltoallv(send))
+    return torch.cat(alltoallv(send, recv_counts=plan.recv_entry_counts))
 
 
 def fetch_entries(plan: RowFetchPlan, vec_local):
     """entries of a row-partitioned VECTOR at the rows of ``plan`` (b_f at J)."""
-    return torch.cat(alltoallv([vec_local[idx] for idx in plan.req_local]))
+    return torch.cat(alltoallv([vec_local[idx] for idx in plan.req_local], recv_counts=plan.recv_row_counts))
 
 
 # --------------------------------------------------------------------------------------------------
