@@ -132,6 +132,10 @@ int iife_ptap_symbolic(iife_mat M, iife_mat A, iife_plan *out);
 /* pattern-compatibility check of (M, A) against a plan (fingerprints) */
 int iife_plan_matches(iife_plan P, iife_mat M, iife_mat A, int *matches);
 int iife_plan_get_info(iife_plan P, int64_t *n_b, int64_t *nnz_c, int64_t *nnz_inter);
+/* rows per numeric kernel: [0] warp hashing 256/64, [1] warp hashing 1K/256, [2] CTA hashing 2K/1K, [3] CTA hashing
+ * 8K/4K, [4] CTA hashing with global-memory tables, [5] slot plan 128/32, [6] slot plan 256/256 (tests use it to
+ * prove that every kernel of the ladder is exercised) */
+int iife_plan_bin_counts(iife_plan P, int64_t *counts7);
 /* numeric phase; *C == NULL creates the result matrix, otherwise refills its values (reuse) */
 int iife_ptap_numeric(iife_plan P, iife_mat M, iife_mat A, iife_mat *C);
 /* general triple product C = R A P with an explicit restriction R (n_out x nJ), A (nJ x nK), P (nK x n_cols):

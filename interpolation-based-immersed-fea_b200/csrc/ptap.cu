@@ -1295,6 +1295,13 @@ int iife_rap_numeric(iife_plan plan_, iife_mat R_, iife_mat A_, iife_mat P_, iif
   return IIFE_OK;
 }
 
+int iife_plan_bin_counts(iife_plan P_, int64_t *counts7) {
+  Plan *P = (Plan *)P_;
+  if (!P || !counts7) return set_err(IIFE_ERR_ARG, "NULL argument");
+  for (int l = 0; l < N_BINS; ++l) counts7[l] = P->bin_off[l + 1] - P->bin_off[l];
+  return IIFE_OK;
+}
+
 int iife_plan_check(iife_plan P_) {
   IIFE_NEED_INIT();
   Plan *P = (Plan *)P_;

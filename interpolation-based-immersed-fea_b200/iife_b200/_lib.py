@@ -47,6 +47,7 @@ PROTOTYPES = {
     "iife_plan_get_info": (c_int, [c_vp, P(c_i64), P(c_i64), P(c_i64)]),
     "iife_rap_symbolic": (c_int, [c_vp, c_vp, c_vp, P(c_vp)]),
     "iife_rap_numeric": (c_int, [c_vp, c_vp, c_vp, c_vp, P(c_vp)]),
+    "iife_plan_bin_counts": (c_int, [c_vp, P(c_i64)]),
     "iife_plan_check": (c_int, [c_vp]),
     "iife_ptap_numeric": (c_int, [c_vp, c_vp, c_vp, P(c_vp)]),
     "iife_plan_destroy": (c_int, [c_vp]),

@@ -252,6 +252,12 @@ class PtapPlan:
         check(lib.iife_plan_get_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return {"n_b": int(a.value), "nnz_c": int(b.value), "nnz_intermediate": int(c.value)}
 
+    def bin_counts(self):
+        """rows handled by each numeric kernel (see include/iife.h: iife_plan_bin_counts)"""
+        c = (ctypes.c_int64 * 7)()
+        check(lib.iife_plan_bin_counts(self._h, c))
+        return list(c)
+
     def matches(self, M: DeviceMat, A: DeviceMat) -> bool:
         m = ctypes.c_int(0)
         check(lib.iife_plan_matches(self._h, M.handle, A.handle, ctypes.byref(m)))

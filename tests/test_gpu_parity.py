@@ -197,6 +197,34 @@ def test_ptap_random(iife, oracle, case):
     check_ptap(iife, oracle, M, A)
 
 
+def test_ptap_every_numeric_kernel_is_exercised(iife, oracle):
+    """Cases built to land rows in each bin of the numeric ladder (slot plans 128/32 and 256/256, warp and
+    CTA hashing levels, global-memory tables) — all against the oracle, and the plan reports the bins."""
+    rng = np.random.default_rng(11)
+    seen = np.zeros(7, dtype=np.int64)
+
+    def one_entry_M(n_f, n_b):
+        # every foreground row maps to exactly one background function: Mt rows have ~n_f/n_b entries
+        cols = rng.integers(0, n_b, n_f)
+        return oracle.CSR(n_f, n_b, np.arange(n_f + 1), cols, rng.random(n_f) + 0.5)
+
+    cases = [
+        (ocsr(oracle, 1200, 400, rand_csr(rng, 1200, 400, 3, empty_frac=0.3)), ocsr(oracle, 1200, 1200, rand_csr(rng, 1200, 1200, 6))),   # slots 128/32-ish
+        (ocsr(oracle, 800, 200, rand_csr(rng, 800, 200, 4)), ocsr(oracle, 800, 800, rand_csr(rng, 800, 800, 12))),                          # slots 256/256
+        (one_entry_M(3000, 100), ocsr(oracle, 3000, 3000, rand_csr(rng, 3000, 3000, 15))),                                                  # n1 ~ 450: warp hashing
+        (ocsr(oracle, 4000, 600, rand_csr(rng, 4000, 600, 2)), ocsr(oracle, 4000, 4000, rand_csr(rng, 4000, 4000, 50))),                     # CTA hashing
+        (ocsr(oracle, 3000, 40, rand_csr(rng, 3000, 40, 8)), ocsr(oracle, 3000, 3000, rand_csr(rng, 3000, 3000, 20))),                       # fat rows
+        (ocsr(oracle, 6000, 6, rand_csr(rng, 6000, 6, 2)), ocsr(oracle, 6000, 6000, rand_csr(rng, 6000, 6000, 30))),                         # global tables
+    ]
+    for M, A in cases:
+        _, _, _, _, plan = check_ptap(iife, oracle, M, A)
+        seen += np.array(plan.bin_counts())
+    assert seen[5] > 0 and seen[6] > 0, seen           # both slot-plan kernels
+    assert seen[1] + seen[2] + seen[3] > 0, seen        # shared-memory hashing levels
+    assert seen[4] > 0, seen                            # global-memory tables
+    print("rows per numeric kernel:", seen.tolist())
+
+
 def test_ptap_numeric_reuse_and_cache(iife, oracle):
     """config 4 pattern: same M, same A_f pattern, new values many times on one symbolic plan."""
     from oracle.synthetic_cube import assemble_cube
