@@ -62,6 +62,7 @@ const char *get_err();
 // device allocation with accounting
 int dev_alloc(void **p, size_t bytes);
 int dev_free(void *p, size_t bytes);
+void dev_release_cached();  // hand the allocator's free blocks back to the driver
 template <class T>
 inline int dev_alloc_t(T **p, size_t n) {
   return dev_alloc((void **)p, (n ? n : 1) * sizeof(T));

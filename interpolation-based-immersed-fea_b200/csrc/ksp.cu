@@ -715,11 +715,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     for (int k = 0; k < NIT; ++k) {
       if (tmask & 1) IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl);
       cudaEventRecord(ev[3 * k + 1], c.stream);
-      if (tmask & 2) {
-        P2PRed dbg{};
-        dbg.enabled = getenv("IIFE_DBG_DOTVAR") ? atoi(getenv("IIFE_DBG_DOTVAR")) : 0;
-        IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl, &dbg));
-      }
+      if (tmask & 2) IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl, nullptr));
       if (tmask & 8) IIFE_TRY(spmv_launch(A, 1.0, p.p, 0.0, wv.p));
       cudaEventRecord(ev[3 * k + 2], c.stream);
       if (tmask & 4) IIFE_LAUNCH(k_cg_update<0>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,

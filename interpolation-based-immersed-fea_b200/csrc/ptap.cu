@@ -1231,6 +1231,18 @@ struct CacheEntry {
 static std::list<CacheEntry> g_cache;
 constexpr size_t CACHE_MAX = 8;
 
+// a plan of the 50 M-DOF case holds ~12 GB (transpose, patterns, slot plan): before building another one,
+// drop least-recently-used plans while less than a quarter of the device memory is free
+static void cache_make_room() {
+  size_t free_b = 0, total_b = 0;
+  while (!g_cache.empty() && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b < total_b / 4) {
+    cudaStreamSynchronize(ctx().stream);
+    plan_free(g_cache.back().plan);
+    g_cache.pop_back();
+    dev_release_cached();
+  }
+}
+
 }  // namespace iife
 
 using namespace iife;
@@ -1345,6 +1357,7 @@ int iife_ptap(iife_mat M_, iife_mat A_, iife_mat *C, int *plan_was_cached) {
     }
   if (plan_was_cached) *plan_was_cached = P ? 1 : 0;
   if (!P) {
+    cache_make_room();
     IIFE_TRY(ptap_symbolic_impl(nullptr, M, A, &P));
     g_cache.push_front({fm, fa, P});
     while (g_cache.size() > CACHE_MAX) {
