@@ -151,3 +151,83 @@ def test_jacobi_zero_diagonal_becomes_one(oracle):
     A = oracle.CSR(3, 3, [0, 1, 1, 3], [0, 1, 2], [2.0, 5.0, 4.0])  # row 1 empty, row 2 has a 0-diag? no: (2,1),(2,2)
     d = oracle.jacobi_inverse(A)
     assert d[0] == 0.5 and d[1] == 1.0 and d[2] == 0.25
+
+
+# ---- independent cross-checks against scipy (Gustavson/SMMP structural SpGEMM, its own CG/GMRES).  scipy is
+# not PETSc, so this does not pin the oracle to the reference's binary — it pins it to a second, unrelated
+# implementation of the same published algorithms, including on the reference's own shipped operators.
+def _scipy_triple(M, A):
+    """(structural pattern, values) of M^T A M by scipy.  scipy's numeric pass drops sums that are exactly 0,
+    so the STRUCTURAL pattern comes from the product of the all-ones patterns (positive sums never cancel)."""
+    import scipy.sparse as sp
+
+    Ms, As = M.to_scipy(), A.to_scipy()
+    Mp = sp.csr_matrix((np.ones(Ms.nnz), M.colind, M.rowptr), shape=Ms.shape)
+    Ap = sp.csr_matrix((np.ones(As.nnz), A.colind, A.rowptr), shape=As.shape)
+    P = (Mp.T.tocsr() @ Ap) @ Mp
+    P.sort_indices()
+    V = (Ms.T.tocsr() @ As) @ Ms
+    scale = ((abs(Ms).T.tocsr() @ abs(As)) @ abs(Ms)).max()  # forward-error scale: terms may cancel (1e13 -> 1e4)
+    return P, V, float(scale)
+
+
+def _assert_matches_scipy(C, P, V, tol):
+    import scipy.sparse as sp
+
+    assert np.array_equal(C.rowptr, P.indptr) and np.array_equal(C.colind, P.indices)
+    D = sp.csr_matrix((C.val, C.colind, C.rowptr), shape=V.shape) - V
+    assert D.nnz == 0 or np.abs(D.data).max() <= tol
+
+
+def _golden_names():
+    import pathlib
+
+    return sorted(p.stem for p in (pathlib.Path(__file__).parent / "golden").glob("*.npz"))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_ptap_pattern_and_values_against_scipy_random(oracle, seed):
+    rng = np.random.default_rng(100 + seed)
+    n_f, n_b = 400 + 50 * seed, 90 + 10 * seed
+    M = _csr(oracle, n_f, n_b, rand_csr(rng, n_f, n_b, 3, empty_frac=0.2))
+    A = _csr(oracle, n_f, n_f, rand_csr(rng, n_f, n_f, 7, empty_frac=0.05))
+    C = oracle.AT_R_A(M, A)
+    P, V, scale = _scipy_triple(M, A)
+    _assert_matches_scipy(C, P, V, 1e-13 * scale)
+
+
+@pytest.mark.parametrize("name", _golden_names())
+def test_ptap_against_scipy_on_shipped_operators(oracle, name):
+    import pathlib
+
+    z = np.load(pathlib.Path(__file__).parent / "golden" / f"{name}.npz")
+    n_f, n_b = int(z["n_f"]), int(z["n_b"])
+    M = oracle.CSR(n_f, n_b, z["M_rowptr"], z["M_colind"], z["M_val"])
+    A = oracle.CSR(n_f, n_f, z["A_rowptr"], z["A_colind"], z["A_val"])
+    C = oracle.AT_R_A(M, A)
+    P, V, scale = _scipy_triple(M, A)
+    _assert_matches_scipy(C, P, V, 1e-13 * scale)
+    x = np.linspace(-1.0, 1.0, n_f)
+    assert np.allclose(oracle.AT_x(M, x), M.to_scipy().T @ x, rtol=0, atol=1e-12 * np.abs(x).max() * 8)
+
+
+def test_cg_solution_against_scipy(oracle):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    rng = np.random.default_rng(7)
+    n = 300
+    B = sp.random(n, n, density=0.02, random_state=7, format="csr")
+    S = (B @ B.T + sp.diags(np.full(n, 2.0))).tocsr()
+    S.sort_indices()
+    A = oracle.CSR.from_scipy(S)
+    b = rng.standard_normal(n)
+    res = oracle.solve_ksp(A, b, method="cg", PC="jacobi", rtol=1e-12, atol=1e-30, max_it=2000)
+    x = res.x
+    assert res.reason > 0
+    d = S.diagonal()
+    xs, info = spla.cg(S, b, rtol=1e-13, atol=0.0, maxiter=5000, M=sp.diags(1.0 / d))
+    assert info == 0
+    assert np.linalg.norm(x - xs) <= 1e-9 * np.linalg.norm(xs)
+    resg = oracle.solve_ksp(A, b, method="gmres", PC="jacobi", rtol=1e-12, atol=1e-30, max_it=2000, restart=40)
+    assert resg.reason > 0 and np.linalg.norm(resg.x - xs) <= 1e-8 * np.linalg.norm(xs)
