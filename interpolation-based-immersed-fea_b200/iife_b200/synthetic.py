@@ -49,11 +49,12 @@ def p1_element(verts: np.ndarray):
     return K, Mm, load
 
 
-def element_tables(n_bg_cells: int, sigma: float = 1.0):
+def element_tables(n_bg_cells: int, sigma: float = 1.0, h: float | None = None):
     """coef[c, d] (8 x 27) and load8[c] (8): contribution of ONE foreground cell to the pair
     (vertex at local corner c, vertex at c + d) and to the load at corner c.  c = cx + 2 cy + 4 cz,
-    d = (dx+1) + 3 (dy+1) + 9 (dz+1)."""
-    h = 1.0 / (2.0 * n_bg_cells)
+    d = (dx+1) + 3 (dy+1) + 9 (dz+1).  ``h`` = foreground cell size (default: the S1 cube's 1/(2N))."""
+    if h is None:
+        h = 1.0 / (2.0 * n_bg_cells)
     coef = np.zeros((8, 27))
     load8 = np.zeros(8)
     for tet in kuhn_tets():
@@ -75,14 +76,9 @@ def cube_sizes(n_bg_cells: int):
     return {"n_f": nv ** 3, "n_b": nb ** 3, "nv": nv, "nb": nb}
 
 
-def cube_operators(n_bg_cells: int, sigma: float = 1.0, row_begin: int = 0, row_end: int | None = None):
-    """Host generator.  Returns dict with A=(rowptr,colind,val), M=(rowptr,colind,val), b_f, n_f, n_b for
-    foreground rows [row_begin, row_end) (global column ids)."""
-    sz = cube_sizes(n_bg_cells)
-    nv, nb, n_f, n_b = sz["nv"], sz["nb"], sz["n_f"], sz["n_b"]
-    if row_end is None:
-        row_end = n_f
-    coef, load8 = element_tables(n_bg_cells, sigma)
+def _kuhn_grid_rows(nv: int, coef, load8, row_begin: int, row_end: int):
+    """Rows [row_begin, row_end) of the P1 operator on an (nv-1)^3-cell Kuhn grid from the per-cell tables:
+    (x, y, z, a_rowptr, a_col, a_val, b_f)."""
     j = np.arange(row_begin, row_end, dtype=np.int64)
     x, y, z = j % nv, (j // nv) % nv, j // (nv * nv)
     ncell = nv - 1
@@ -118,6 +114,19 @@ def cube_operators(n_bg_cells: int, sigma: float = 1.0, row_begin: int = 0, row_
     b_f = np.zeros(n)
     for c in range(8):
         b_f = np.where(cell_ok[c], b_f + load8[c], b_f)
+    return x, y, z, a_rowptr, a_col, a_val, b_f
+
+
+def cube_operators(n_bg_cells: int, sigma: float = 1.0, row_begin: int = 0, row_end: int | None = None):
+    """Host generator.  Returns dict with A=(rowptr,colind,val), M=(rowptr,colind,val), b_f, n_f, n_b for
+    foreground rows [row_begin, row_end) (global column ids)."""
+    sz = cube_sizes(n_bg_cells)
+    nv, nb, n_f, n_b = sz["nv"], sz["nb"], sz["n_f"], sz["n_b"]
+    if row_end is None:
+        row_end = n_f
+    coef, load8 = element_tables(n_bg_cells, sigma)
+    x, y, z, a_rowptr, a_col, a_val, b_f = _kuhn_grid_rows(nv, coef, load8, row_begin, row_end)
+    n = x.size
     # M: tensor product of 1D hats
     bx0, by0, bz0 = x >> 1, y >> 1, z >> 1
     nx, ny, nz = (x & 1) + 1, (y & 1) + 1, (z & 1) + 1
@@ -159,3 +168,76 @@ def cube_nnz(n_bg_cells: int):
     nnz_m = (3 * n_bg_cells + 1) ** 3
     nnz_ab = (3 * n_bg_cells + 1) ** 3
     return nnz_a, nnz_m, nnz_ab
+
+
+# --------------------------------------------------------------------------------------------------
+# S2 "unfitted" stress case: the foreground cube of generateUnfittedMesh(dim=3)
+# (reference common.py:80-90, demos/poisson_unfitted.py:115-134) inside a rotated background grid
+# --------------------------------------------------------------------------------------------------
+def unfitted_sizes(n_fg_cells: int, degree: int = 1):
+    """n_f, n_b of the S2 case: foreground L_f = 2 with N_f^3 cells, background L_b = 4 with h_b = 2 h_f
+    (=> N_b = N_f cells per edge), uniform B-splines of the given degree (N_b + degree functions per edge)."""
+    nv = n_fg_cells + 1
+    nbx = n_fg_cells + degree
+    return {"n_f": nv ** 3, "n_b": nbx ** 3, "nv": nv, "nb": nbx}
+
+
+def unfitted_operators(n_fg_cells: int, degree: int = 1, sigma: float = 1.0, angle: float = np.pi / 6.0):
+    """Host generator of the S2 operands.
+
+      foreground : cube [-1, 1]^3, N_f^3 cells of 6 Kuhn tetrahedra, P1, A_f = K + sigma * Mass (15-pt stencil)
+      background : cube [-2, 2]^3 rotated by ``angle`` about z and then about y (``mesh_b.rotate(angle, 2)``,
+                   ``mesh_b.rotate(angle, 1)``: reference common.py:88-90), N_b = N_f cells per edge (h_b = 2 h_f),
+                   uniform tensor-product B-splines of degree 1 or 2
+      M[j, k]    : background function k evaluated at foreground vertex j  ((degree+1)^3 entries per row, rows
+                   sum to 1; exact zeros are not stored).  Background functions whose support holds no
+                   foreground vertex are empty columns => empty rows of A_b, as with the reference's XTK data.
+    """
+    if degree not in (1, 2):
+        raise ValueError("degree must be 1 or 2")
+    sz = unfitted_sizes(n_fg_cells, degree)
+    nv, nbx, n_f, n_b = sz["nv"], sz["nb"], sz["n_f"], sz["n_b"]
+    L_f, L_b = 2.0, 4.0
+    h_f = L_f / n_fg_cells
+    h_b = 2.0 * h_f
+    coef, load8 = element_tables(n_fg_cells, sigma, h=h_f)
+    x, y, z, a_rowptr, a_col, a_val, b_f = _kuhn_grid_rows(nv, coef, load8, 0, n_f)
+    # foreground vertex coordinates in the background frame: xi = R^T X, R = R_y(angle) R_z(angle)
+    X = np.stack([-L_f / 2 + h_f * x, -L_f / 2 + h_f * y, -L_f / 2 + h_f * z], axis=1)
+    c, s = np.cos(angle), np.sin(angle)
+    Rz = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+    Ry = np.array([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]])
+    R = Ry @ Rz
+    t = ((X @ R) + L_b / 2) / h_b  # rows of X @ R = (R^T X_j)^T ; in units of background cells
+    cell = np.floor(t).astype(np.int64)
+    u = t - cell
+    n_cells_b = n_fg_cells
+    if cell.min() < 0 or cell.max() >= n_cells_b:
+        raise ValueError("foreground leaves the background grid")
+    if degree == 1:
+        w1d = np.stack([1.0 - u, u], axis=2)  # (n, 3, 2): functions cell, cell+1
+    else:
+        w1d = np.stack([0.5 * (1.0 - u) ** 2, 0.5 * (-2.0 * u * u + 2.0 * u + 1.0), 0.5 * u * u], axis=2)
+    q = degree + 1
+    n = n_f
+    mcols = np.zeros((n, q ** 3), dtype=np.int64)
+    mvals = np.zeros((n, q ** 3))
+    sidx = 0
+    for kz in range(q):  # ascending background id within a row: x fastest
+        for ky in range(q):
+            for kx in range(q):
+                mcols[:, sidx] = (cell[:, 0] + kx) + nbx * ((cell[:, 1] + ky) + nbx * (cell[:, 2] + kz))
+                mvals[:, sidx] = w1d[:, 0, kx] * w1d[:, 1, ky] * w1d[:, 2, kz]
+                sidx += 1
+    keep = mvals != 0.0
+    m_len = keep.sum(axis=1)
+    m_rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(m_len, out=m_rowptr[1:])
+    return {
+        "A": (a_rowptr, a_col, a_val),
+        "M": (m_rowptr, mcols[keep].astype(np.int32), mvals[keep]),
+        "b_f": b_f,
+        "n_f": n_f,
+        "n_b": n_b,
+        "n_rows": n,
+    }

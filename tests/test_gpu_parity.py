@@ -393,3 +393,36 @@ def test_end_to_end_cube_pipeline(iife, oracle):
     assert np.linalg.norm(x - ro.x) <= SOL_TOL * np.linalg.norm(ro.x)
     uf = dM.spmv(x)  # transferToForeground (reference common.py:123-140)
     assert np.allclose(uf, oracle.spmv(M, ro.x), rtol=1e-7, atol=1e-12)
+
+
+@pytest.mark.parametrize("degree,n_cells", [(1, 20), (2, 14)])
+def test_unfitted_stress_case(iife, oracle, degree, n_cells):
+    """S2: foreground cube inside a rotated background grid (reference common.py:80-90).
+    Wide rows — A_b up to 119 (p=1) / 331 (p=2) entries, intermediate rows beyond the 256-entry slot plan —
+    so the hashing kernels run on a realistic pattern, with thousands of unsupported (empty) rows."""
+    from iife_b200 import synthetic
+
+    g = synthetic.unfitted_operators(n_cells, degree)
+    A = oracle.CSR(g["n_f"], g["n_f"], *g["A"])
+    M = oracle.CSR(g["n_f"], g["n_b"], *g["M"])
+    dM, dA, dC, C, plan = check_ptap(iife, oracle, M, A)
+    lens = np.diff(C.rowptr)
+    assert (lens == 0).sum() > 1000 and lens.max() > (100 if degree == 1 else 256)
+    bb = dM.spmv(g["b_f"], trans=True)
+    bbo = oracle.AT_x(M, g["b_f"])
+    assert np.allclose(bb, bbo, rtol=0, atol=1e-13 * np.abs(bbo).max())
+    bnorm = np.linalg.norm(bbo)
+    for method, kt in (("cg", iife.KSP_CG), ("gmres", iife.KSP_FGMRES)):
+        ro = oracle.solve_ksp(C, bbo, method=method, max_it=5000, hist_len=64)
+        x = np.zeros(C.n_rows)
+        info = iife.ksp_solve(dC, bb, x, kt, iife.PC_JACOBI, max_it=5000, hist_len=64)
+        assert info.reason == ro.reason == 2, (method, info.reason_name)
+        # cut-cell conditioning (p=2: 800 CG iterations at 2 700 dofs): the count moves with rounding
+        assert abs(info.iterations - ro.iterations) <= max(2, ro.iterations // 10), (method, info.iterations)
+        k = min(info.iterations, ro.iterations, 10) + 1
+        assert np.allclose(info.history[:k], ro.history[:k], rtol=1e-3, atol=1e-9 * ro.history[0])
+        r_gpu = np.linalg.norm(bbo - oracle.spmv(C, x))
+        r_orc = np.linalg.norm(bbo - oracle.spmv(C, ro.x))
+        assert r_gpu <= 10.0 * max(r_orc, 1e-8 * bnorm), (method, r_gpu, r_orc)
+        if degree == 1:  # well enough conditioned for forward-error parity
+            assert np.linalg.norm(x - ro.x) <= 1e-6 * np.linalg.norm(ro.x)

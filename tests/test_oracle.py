@@ -231,3 +231,28 @@ def test_cg_solution_against_scipy(oracle):
     assert np.linalg.norm(x - xs) <= 1e-9 * np.linalg.norm(xs)
     resg = oracle.solve_ksp(A, b, method="gmres", PC="jacobi", rtol=1e-12, atol=1e-30, max_it=2000, restart=40)
     assert resg.reason > 0 and np.linalg.norm(resg.x - xs) <= 1e-8 * np.linalg.norm(xs)
+
+
+@pytest.mark.parametrize("degree,n_cells", [(1, 12), (2, 10)])
+def test_unfitted_stress_case_generator(oracle, degree, n_cells):
+    """S2 generator: partition of unity, (p+1)^3 entries per row of M, unsupported background
+    functions give empty rows of A_b, total mass/stiffness conserved; oracle == scipy on it."""
+    import sys, pathlib
+
+    sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1] / "interpolation-based-immersed-fea_b200"))
+    from iife_b200 import synthetic
+
+    g = synthetic.unfitted_operators(n_cells, degree)
+    M = oracle.CSR(g["n_f"], g["n_b"], *g["M"])
+    A = oracle.CSR(g["n_f"], g["n_f"], *g["A"])
+    ml = np.diff(M.rowptr)
+    assert ml.max() == (degree + 1) ** 3 and ml.min() >= 1
+    assert np.abs(np.add.reduceat(M.val, M.rowptr[:-1]) - 1.0).max() < 1e-14 and M.val.min() > 0.0
+    C = oracle.AT_R_A(M, A)
+    supported = np.zeros(g["n_b"], dtype=bool)
+    supported[M.colind] = True
+    assert np.array_equal(np.diff(C.rowptr) > 0, supported)
+    assert abs(C.val.sum() - A.val.sum()) < 1e-11 * np.abs(A.val).sum()  # 1^T A_b 1 = 1^T A_f 1 (M 1 = 1)
+    assert abs(A.val.sum() - 8.0) < 1e-11  # sigma * volume of [-1,1]^3 (stiffness rows sum to 0)
+    P, V, scale = _scipy_triple(M, A)
+    _assert_matches_scipy(C, P, V, 1e-13 * scale)
