@@ -14,6 +14,8 @@
  *   common.py:364        Mat.multAdd()              (MatMultAdd)    iife_spmv(alpha=1, beta=1 on a copy)
  *   common.py:554-574, 628-636  KSP create/setUp/solve (KSPCG, KSPFGMRES, PCJACOBI)  iife_ksp_solve
  *   common.py:222,305    Mat.getDiagonal()                          iife_mat_get_diagonal
+ *   common.py:284,327    Mat.zeroRows()  (trimNodes)  (MatZeroRows)  iife_mat_zero_rows
+ *   common.py:243-249    A0.setDiagonal(vd); A += A0  (removeZeroDiagonal, getIdentity)  iife_mat_add_diagonal
  *
  * Conventions
  *   - every function returns 0 on success, a positive IIFE_ERR_* code otherwise;
@@ -118,6 +120,14 @@ int iife_mat_fingerprint(iife_mat A, uint64_t *fp);
 int iife_mat_transpose(iife_mat A, iife_mat *out);
 /* diag[i] = A[i,i], 0 where the diagonal entry is not stored (MatGetDiagonal) */
 int iife_mat_get_diagonal(iife_mat A, double *diag, int mem);
+/* MatZeroRows as trimNodes uses it (common.py:284,327; no KEEP_NONZERO_PATTERN): *out = copy of A in which
+ * every listed row (idx_bytes-wide 0-based indices, duplicates allowed) holds exactly one entry (i,i) = diag
+ * when diag != 0 and i < n_cols, and nothing otherwise.  A is unchanged; the caller swaps handles. */
+int iife_mat_zero_rows(iife_mat A, const void *rows, int64_t n_listed, int idx_bytes, double diag, int mem,
+                       iife_mat *out);
+/* *out = A + diag(d) with pattern union(A, full diagonal), rows column-sorted: the `A += A0` of
+ * removeZeroDiagonal (common.py:243-249; A0 = MatDiagonalSet(vd) on an empty matrix). d has n_rows entries. */
+int iife_mat_add_diagonal(iife_mat A, const double *d, int mem, iife_mat *out);
 int iife_mat_destroy(iife_mat A);
 
 /* ---------------------------------------------------------------- SpMV */

@@ -1,7 +1,9 @@
 """Drop-in mirror of the hot-path functions of the reference's ``InterpolationBasedImmersedFEA.common``
 (reference InterpolationBasedImmersedFEA/common.py): ``assembleLinearSystemBackground`` (:142-163),
-``transferToForeground`` (:123-140), ``zeroDofBackground`` (:120-121), ``solveKSP`` (:509-641) and the
-extraction-operator import ``readExOp`` (:645-712, host side).  FEniCS assembly stays on the host
+``transferToForeground`` (:123-140), ``zeroDofBackground`` (:120-121), ``solveKSP`` (:509-641), the
+extraction-operator import ``readExOp`` (:645-712, host side) and — SURVEY.md §8f rows N1/N3 — the
+basis-function-removal helpers ``createNonzeroDiagonal`` / ``removeZeroDiagonal`` / ``getIdentity`` /
+``trimNodes`` (:207-332) and the Newton driver for linear systems ``solveNewtonsLinear`` (:335-402).  FEniCS assembly stays on the host
 exactly as in the reference; everything PETSc did on this path runs in libiife.so on the GPU.
 """
 from __future__ import annotations
@@ -79,7 +81,7 @@ def solveKSP(A, b, u, method='gmres', PC='jacobi',
     if PC != 'jacobi':
         raise NotImplementedError(f"unknown PC {PC!r}")
     if remove_zero_diagonal and bfr_tol is not None:
-        raise NotImplementedError("trimNodes (basis function removal) is outside the hot path (SURVEY.md §2 C10)")
+        A, b = trimNodes(A, b=b, bfr_tol=bfr_tol)  # reference common.py:565-566
     dA = _as_device(arg2m(A))
     bv, uv = arg2v(b), arg2v(u)
     x = np.ascontiguousarray(_vec_array(uv), dtype=np.float64).copy()
@@ -92,6 +94,130 @@ def solveKSP(A, b, u, method='gmres', PC='jacobi',
         print('Converged in', info.iterations, 'iterations.')
         print('Convergence history:', [])
     return None
+
+
+# --------------------------------------------------------------------------------------------------
+# basis function removal (reference common.py:207-332) — SURVEY.md §8f row N3
+# --------------------------------------------------------------------------------------------------
+def createNonzeroDiagonal(A, bfr_tol=1E-9):
+    """Vector with 1 where ``|A_ii| <= bfr_tol`` and 0 elsewhere (reference common.py:207-233).  The diagonal
+    is extracted on the device; the comparison is one vectorised pass instead of the reference's
+    ``getValue``/``setValue`` loop."""
+    d = arg2m(A).getDiagonal().array
+    return Vec(np.where(np.abs(d) <= bfr_tol, 1.0, 0.0))
+
+
+def removeZeroDiagonal(A, bfr_tol=1E-9):
+    """Ones onto the (near-)zero diagonal entries of A, in place (reference common.py:236-251): ``A += A0``
+    with ``A0 = diag(createNonzeroDiagonal(A))`` — the pattern gains the full diagonal."""
+    A = arg2m(A)
+    vd = createNonzeroDiagonal(A, bfr_tol=bfr_tol)
+    A.addDiagonal(vd)
+    return A
+
+
+def getIdentity(size):
+    """Identity of the given ``(local, global)`` size (reference common.py:254-258)."""
+    (size_l, size_g) = size
+    A = zero_petsc_mat(size_g, size_g, row_loc=size_l, col_loc=size_l)  # noqa: F405
+    return removeZeroDiagonal(A)
+
+
+def trimNodes(A, b=None, bfr_tol=1E-9, target=None, zero_vec=None, monitor=False):
+    """Rows whose diagonal is ``<= bfr_tol`` (signed, reference common.py:312) — or the rows listed in
+    ``zero_vec`` — become unit rows, ``b`` there becomes ``target`` (or 0) (reference common.py:262-332).
+    ``A`` and ``b`` are modified in place and returned.  Diagonal scan and row rewrite run on the device."""
+    A = arg2m(A)
+    bv = None if b is None else _vec_array(arg2v(b))
+    tv = None if target is None else _vec_array(arg2v(target))
+    if zero_vec is not None:
+        ids = np.asarray(zero_vec, dtype=np.int64)
+    else:
+        ids = np.flatnonzero(A.getDiagonal().array <= bfr_tol)
+    nz_val = 0
+    if bv is not None:
+        vals = np.zeros(ids.size) if tv is None else tv[ids]
+        bv[ids] = vals
+        nz_val = int(np.count_nonzero(vals > 1e-15))
+    if zero_vec is None or monitor:  # the reference prints unconditionally on the scan branch (:322-323)
+        print("number of nodes trimmed: ", int(ids.size))
+        print("number of nonzero residuals set: ", nz_val)
+    A.zeroRows(ids)
+    return A, b
+
+
+# --------------------------------------------------------------------------------------------------
+# Newton iteration on an assembled linear system (reference common.py:335-402) — SURVEY.md §8f row N1
+# --------------------------------------------------------------------------------------------------
+def solveNewtonsLinear(A, L, u_f, M, u_p,
+                       maxIters=20,
+                       relativeTolerance=1e-7,
+                       monitorNewtonConvergence=True,
+                       moniterLinearConvergence=False,
+                       linear_method=None,
+                       linear_preconditioner=None,
+                       relax_param=1,
+                       zero_vec=None):
+    """Newton / iterative-refinement loop on the background system (reference common.py:335-402; the keyword
+    spelling ``moniterLinearConvergence`` is the reference's).  A_b, L_b, the iterate, the residual and the
+    correction stay on the device for the whole loop; per iteration only two norms come back to the host, and
+    ``u_f = M u_p`` is downloaded for the caller as the reference's ``transferToForeground`` does.  Returns
+    ``u_p`` (a ``Vec``) on convergence; like the reference it stops the run if the loop does not converge."""
+    import torch
+
+    A_b, L_b = assembleLinearSystemBackground(A, L, M)
+    u_p = zeroDofBackground(M)
+    if zero_vec is not None:
+        A_b, L_b = trimNodes(A_b, b=L_b, target=u_p, zero_vec=zero_vec, monitor=False)
+    method = linear_method or 'gmres'
+    pc = linear_preconditioner or 'jacobi'
+    if method in _DELEGATED_METHODS or pc in _DELEGATED_PCS or method not in _KRYLOV or pc != 'jacobi':
+        raise NotImplementedError(f"solveNewtonsLinear(linear_method={method!r}, linear_preconditioner={pc!r})")
+    dA, dM = _as_device(arg2m(A_b)), _as_device(arg2m(M))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_b = dA.shape[0]
+    Lb_d = torch.from_numpy(np.ascontiguousarray(_vec_array(arg2v(L_b)), dtype=np.float64)).to(dev)
+    up_d = torch.zeros(n_b, dtype=torch.float64, device=dev)
+    res_d = torch.empty_like(up_d)
+    du_d = torch.empty_like(up_d)
+    uf_d = torch.empty(dM.shape[0], dtype=torch.float64, device=dev)
+    initialNorm = initialNormRes = None
+    def tsync():  # torch's stream and the library's stream are different streams: order them by hand
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(0, maxIters):
+        res_d.copy_(Lb_d)
+        tsync()
+        dA.spmv(up_d, y=res_d, alpha=1.0, beta=1.0)  # A_b.multAdd(u_p, L_b, res_b)  (:364)
+        _iife.sync()
+        currentNormRes = float(torch.linalg.vector_norm(res_d))
+        du_d.zero_()
+        tsync()
+        info = _iife.ksp_solve(dA, res_d, du_d, _KRYLOV[method], _iife.PC_JACOBI, rtol=1e-8, atol=1e-9,
+                               max_it=1000000, restart=300)
+        currentNorm = float(torch.linalg.vector_norm(du_d))
+        if i == 0:
+            initialNorm, initialNormRes = currentNorm, currentNormRes
+        relativeNorm = currentNorm / initialNorm
+        relativeNormRes = currentNormRes / initialNormRes
+        if monitorNewtonConvergence:
+            print("Newton solver iteration: " + str(i) + ", Relative norm of du: " + str(relativeNorm)
+                  + ", Relative norm of res: " + str(relativeNormRes), flush=True)
+        if moniterLinearConvergence:
+            print('Converged in', info.iterations, 'iterations.')
+        if (relativeNorm < relativeTolerance) or (relativeNormRes < relativeTolerance):
+            print('converged')
+            u_p.array[:] = up_d.cpu().numpy()
+            return u_p
+        up_d.add_(du_d, alpha=-float(relax_param))  # u_p += -du_p*relax_param  (:395)
+        tsync()
+        dM.spmv(up_d, y=uf_d)  # transferToForeground(u_f, u_p, M)  (:399)
+        _iife.sync()
+        target = u_f.vector() if (HAVE_DOLFIN and hasattr(u_f, "vector")) else u_f
+        _vec_array(arg2v(target))[:] = uf_d.cpu().numpy()
+        updateU(u_f)
+    print("ERROR: Nonlinear solver failed to converge.")
+    raise SystemExit(1)  # the reference calls exit() here (:401-402)
 
 
 def read_exop_triplets(fileNames):

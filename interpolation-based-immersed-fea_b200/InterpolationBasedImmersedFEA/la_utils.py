@@ -237,12 +237,24 @@ class CSRMat:
     def matMult(self, other):
         raise NotImplementedError("use AT_R_A: the two MatMatMult calls of the reference are fused into one PtAP")
 
+    def _replace_device(self, dev: DeviceMat):
+        self._dev = dev
+        self._shape = dev.shape
+        self._rowptr = self._colind = self._val = None
+
     def zeroRows(self, rows, diag=1.0):
-        rp, ci, v = self.rowptr, self.colind, self.val.copy()
-        for r in np.atleast_1d(rows):
-            seg = slice(rp[r], rp[r + 1])
-            v[seg] = np.where(ci[seg] == r, diag, 0.0)
-        self.set_values(v)
+        """``Mat.zeroRows`` as trimNodes uses it (reference common.py:284,327): in place; a listed row keeps only
+        (i, i) = diag (the entry is created if it was not stored, like PETSc without KEEP_NONZERO_PATTERN)."""
+        self._replace_device(self.device().zero_rows(np.atleast_1d(np.asarray(rows, dtype=np.int64)), diag))
+
+    def addDiagonal(self, d):
+        """``A += A0`` with ``A0.setDiagonal(d)`` (reference common.py:243-249): in place, pattern = union with
+        the full diagonal."""
+        self._replace_device(self.device().add_diagonal(_vec_array(arg2v(d))))
+        return self
+
+    def norm(self):
+        return float(np.linalg.norm(self.val))
 
 
 # --------------------------------------------------------------------------------------------------

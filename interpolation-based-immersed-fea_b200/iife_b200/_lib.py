@@ -40,6 +40,8 @@ PROTOTYPES = {
     "iife_mat_fingerprint": (c_int, [c_vp, P(ctypes.c_uint64)]),
     "iife_mat_transpose": (c_int, [c_vp, P(c_vp)]),
     "iife_mat_get_diagonal": (c_int, [c_vp, c_vp, c_int]),
+    "iife_mat_zero_rows": (c_int, [c_vp, c_vp, ctypes.c_int64, c_int, c_dbl, c_int, P(c_vp)]),
+    "iife_mat_add_diagonal": (c_int, [c_vp, c_vp, c_int, P(c_vp)]),
     "iife_mat_destroy": (c_int, [c_vp]),
     "iife_spmv": (c_int, [c_vp, c_int, c_dbl, c_vp, c_dbl, c_vp, c_int]),
     "iife_ptap_symbolic": (c_int, [c_vp, c_vp, P(c_vp)]),

@@ -206,6 +206,24 @@ class DeviceMat:
         check(lib.iife_mat_get_diagonal(self._h, _ptr(d)[0], MEM_HOST))
         return d
 
+    def zero_rows(self, rows, diag=1.0) -> "DeviceMat":
+        """New matrix with the listed rows reduced to the single entry (i, i) = diag (MatZeroRows as used by
+        trimNodes, reference common.py:284,327); see include/iife.h."""
+        r = np.ascontiguousarray(np.atleast_1d(rows))
+        if r.dtype not in (np.int32, np.int64):
+            r = r.astype(np.int64)
+        h = ctypes.c_void_p(0)
+        check(lib.iife_mat_zero_rows(self._h, _ptr(r)[0], int(r.size), r.dtype.itemsize, float(diag), MEM_HOST,
+                                     ctypes.byref(h)))
+        return DeviceMat(h.value)
+
+    def add_diagonal(self, d) -> "DeviceMat":
+        """New matrix A + diag(d) on the pattern union(A, full diagonal) (removeZeroDiagonal, common.py:243-249)."""
+        dv = _host_f64(d, self.shape[0])
+        h = ctypes.c_void_p(0)
+        check(lib.iife_mat_add_diagonal(self._h, _ptr(dv)[0], MEM_HOST, ctypes.byref(h)))
+        return DeviceMat(h.value)
+
     def spmv(self, x, y=None, trans=False, alpha=1.0, beta=0.0):
         """y = alpha*op(A) x + beta*y.  Host numpy in -> numpy out; device tensors in -> written in place."""
         n_rows, n_cols, _ = self.info()

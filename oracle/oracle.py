@@ -197,6 +197,80 @@ def jacobi_inverse(A: CSR) -> np.ndarray:
     return d
 
 
+def diagonal(A: CSR) -> np.ndarray:
+    """MatGetDiagonal (reference common.py:222,305): stored (i, i) or 0."""
+    d = np.zeros(A.n_rows)
+    for i in range(min(A.n_rows, A.n_cols)):
+        seg = A.colind[A.rowptr[i]:A.rowptr[i + 1]]
+        k = np.searchsorted(seg, i)
+        if k < seg.size and seg[k] == i:
+            d[i] = A.val[A.rowptr[i] + k]
+    return d
+
+
+def zero_rows(A: CSR, rows, diag: float = 1.0) -> CSR:
+    """MatZeroRows as trimNodes calls it (reference common.py:284,327; AIJ, no KEEP_NONZERO_PATTERN): a listed
+    row keeps the single entry (i, i) = diag when diag != 0 (and the position exists), nothing otherwise."""
+    flag = np.zeros(A.n_rows, dtype=bool)
+    flag[np.asarray(rows, dtype=np.int64)] = True
+    rp = [0]
+    ci, v = [], []
+    for i in range(A.n_rows):
+        if flag[i]:
+            if diag != 0.0 and i < A.n_cols:
+                ci.append(np.array([i], dtype=np.int32))
+                v.append(np.array([diag]))
+                rp.append(rp[-1] + 1)
+            else:
+                rp.append(rp[-1])
+        else:
+            b, e = A.rowptr[i], A.rowptr[i + 1]
+            ci.append(A.colind[b:e])
+            v.append(A.val[b:e])
+            rp.append(rp[-1] + int(e - b))
+    cat = (lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dtype=dt))
+    return CSR(A.n_rows, A.n_cols, np.array(rp, dtype=np.int64), cat(ci, np.int32), cat(v, np.float64))
+
+
+def add_diagonal(A: CSR, d: np.ndarray) -> CSR:
+    """``A += A0`` with ``A0.setDiagonal(vd)`` on an empty matrix (removeZeroDiagonal, reference common.py:243-249):
+    MatAXPY over different patterns => pattern union(A, full diagonal), sorted rows, (i, i) = A_ii + d_i."""
+    rp = [0]
+    ci, v = [], []
+    for i in range(A.n_rows):
+        b, e = A.rowptr[i], A.rowptr[i + 1]
+        cols, vals = A.colind[b:e], A.val[b:e].copy()
+        if i < A.n_cols:
+            k = int(np.searchsorted(cols, i))
+            if k < cols.size and cols[k] == i:
+                vals[k] = vals[k] + d[i]
+            else:
+                cols = np.insert(cols, k, i)
+                vals = np.insert(vals, k, 0.0 + d[i])
+        ci.append(cols)
+        v.append(vals)
+        rp.append(rp[-1] + cols.size)
+    cat = (lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dtype=dt))
+    return CSR(A.n_rows, A.n_cols, np.array(rp, dtype=np.int64), cat(ci, np.int32), cat(v, np.float64))
+
+
+def create_nonzero_diagonal(A: CSR, bfr_tol: float = 1e-9) -> np.ndarray:
+    """createNonzeroDiagonal (reference common.py:207-233): 1 where |A_ii| <= bfr_tol, else 0."""
+    return np.where(np.abs(diagonal(A)) <= bfr_tol, 1.0, 0.0)
+
+
+def trim_nodes(A: CSR, b=None, bfr_tol: float = 1e-9, target=None, zero_vec=None):
+    """trimNodes (reference common.py:262-332): rows with A_ii <= bfr_tol (SIGNED test, :312) — or the rows of
+    ``zero_vec`` — become unit rows; b there becomes target or 0.  Returns (A', b', ids)."""
+    ids = np.asarray(zero_vec, dtype=np.int64) if zero_vec is not None else np.flatnonzero(diagonal(A) <= bfr_tol)
+    A2 = zero_rows(A, ids, 1.0)
+    b2 = None
+    if b is not None:
+        b2 = np.array(b, dtype=np.float64, copy=True)
+        b2[ids] = 0.0 if target is None else np.asarray(target)[ids]
+    return A2, b2, ids
+
+
 @dataclass
 class KSPResult:
     x: np.ndarray

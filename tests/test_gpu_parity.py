@@ -424,5 +424,108 @@ def test_unfitted_stress_case(iife, oracle, degree, n_cells):
         r_gpu = np.linalg.norm(bbo - oracle.spmv(C, x))
         r_orc = np.linalg.norm(bbo - oracle.spmv(C, ro.x))
         assert r_gpu <= 10.0 * max(r_orc, 1e-8 * bnorm), (method, r_gpu, r_orc)
-        if degree == 1:  # well enough conditioned for forward-error parity
+        # forward-error parity where it is meaningful: one more or less iteration moves the p=1 CG solution by
+        # 4e-8 but the FGMRES one by 1e-6..1e-4 (true-residual test on a cut-cell operator)
+        if degree == 1 and (method == "cg" or info.iterations == ro.iterations):
             assert np.linalg.norm(x - ro.x) <= 1e-6 * np.linalg.norm(ro.x)
+
+
+def test_row_edits_match_oracle(iife, oracle):
+    """iife_mat_zero_rows / iife_mat_add_diagonal against the oracle's restatement of MatZeroRows and
+    `A += diag` (trimNodes / removeZeroDiagonal, reference common.py:236-332): bit-exact pattern and values."""
+    rng = np.random.default_rng(21)
+    for n, mean, empty in ((1, 1, 0.0), (37, 3, 0.3), (5000, 9, 0.1), (300, 60, 0.0)):
+        A = ocsr(oracle, n, n, rand_csr(rng, n, n, mean, empty_frac=empty))
+        dA = dmat(iife, A)
+        rows = rng.choice(n, size=max(1, n // 7), replace=True)  # duplicates allowed
+        for diag in (1.0, 0.0, -2.5):
+            Z = oracle.zero_rows(A, rows, diag)
+            rp, ci, v = dA.zero_rows(rows, diag).to_csr(np.int64)
+            assert np.array_equal(rp, Z.rowptr) and np.array_equal(ci, Z.colind) and np.array_equal(v, Z.val)
+        for dt in (np.int32, np.int64):
+            rp, ci, v = dA.zero_rows(rows.astype(dt)).to_csr(np.int64)
+            Z = oracle.zero_rows(A, rows, 1.0)
+            assert np.array_equal(rp, Z.rowptr) and np.array_equal(ci, Z.colind) and np.array_equal(v, Z.val)
+        d = rng.standard_normal(n)
+        D = oracle.add_diagonal(A, d)
+        rp, ci, v = dA.add_diagonal(d).to_csr(np.int64)
+        assert np.array_equal(rp, D.rowptr) and np.array_equal(ci, D.colind) and np.array_equal(v, D.val)
+        # the source matrix is untouched
+        rp, ci, v = dA.to_csr(np.int64)
+        assert np.array_equal(rp, A.rowptr) and np.array_equal(ci, A.colind) and np.array_equal(v, A.val)
+    # rectangular: diagonal positions exist only for i < n_cols
+    R = ocsr(oracle, 30, 12, rand_csr(rng, 30, 12, 3))
+    dR = dmat(iife, R)
+    rows = np.array([2, 11, 12, 29])
+    Z = oracle.zero_rows(R, rows, 1.0)
+    rp, ci, v = dR.zero_rows(rows).to_csr(np.int64)
+    assert np.array_equal(rp, Z.rowptr) and np.array_equal(ci, Z.colind) and np.array_equal(v, Z.val)
+    d = rng.standard_normal(30)
+    D = oracle.add_diagonal(R, d)
+    rp, ci, v = dR.add_diagonal(d).to_csr(np.int64)
+    assert np.array_equal(rp, D.rowptr) and np.array_equal(ci, D.colind) and np.array_equal(v, D.val)
+    # empty list, empty matrix, out-of-range index
+    rp, ci, v = dA.zero_rows(np.zeros(0, dtype=np.int64)).to_csr(np.int64)
+    assert np.array_equal(rp, A.rowptr) and np.array_equal(v, A.val)
+    E = iife.DeviceMat.from_csr(4, 4, np.zeros(5, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0))
+    rp, ci, v = E.add_diagonal(np.ones(4)).to_csr(np.int64)
+    assert np.array_equal(rp, np.arange(5)) and np.array_equal(ci, np.arange(4)) and np.array_equal(v, np.ones(4))
+    with pytest.raises(iife.IifeError):
+        dA.zero_rows(np.array([A.n_rows]))
+
+
+def test_trim_nodes_and_newton_through_the_mirror(iife, oracle, capsys):
+    """trimNodes / removeZeroDiagonal / getIdentity / solveKSP(remove_zero_diagonal=True) / solveNewtonsLinear
+    through the reference's own names (reference common.py:207-402), against the oracle."""
+    from InterpolationBasedImmersedFEA import common as api
+    from iife_b200 import synthetic
+
+    g = synthetic.unfitted_operators(12, 1)  # thousands of unsupported background functions => empty rows of A_b
+    n_f, n_b = g["n_f"], g["n_b"]
+    Ao, Mo = oracle.CSR(n_f, n_f, *g["A"]), oracle.CSR(n_f, n_b, *g["M"])
+    A, M = api.CSRMat((n_f, n_f), *g["A"]), api.CSRMat((n_f, n_b), *g["M"])
+    A_b, b_b = api.assembleLinearSystemBackground(A, api.Vec(g["b_f"]), M)
+    Co, bbo = oracle.AT_R_A(Mo, Ao), oracle.AT_x(Mo, g["b_f"])
+    # createNonzeroDiagonal / removeZeroDiagonal on a copy
+    vd = api.createNonzeroDiagonal(A_b)
+    assert np.array_equal(vd.array, oracle.create_nonzero_diagonal(Co)) and vd.array.sum() > 1000
+    Cc = api.CSRMat((n_b, n_b), A_b.rowptr.copy(), A_b.colind.copy(), A_b.val.copy())
+    R = api.removeZeroDiagonal(Cc)
+    Ro = oracle.add_diagonal(Co, oracle.create_nonzero_diagonal(Co))
+    assert R is Cc and np.array_equal(R.rowptr, Ro.rowptr) and np.array_equal(R.colind, Ro.colind)
+    assert np.allclose(R.val, Ro.val, rtol=0, atol=1e-12 * np.abs(Ro.val).max())
+    I7 = api.getIdentity((7, 7))
+    assert np.array_equal(I7.to_scipy().toarray(), np.eye(7))
+    # trimNodes, scan branch (prints like the reference) and list branch
+    T_o, bt_o, ids = oracle.trim_nodes(Co, bbo)
+    b_t = api.Vec(b_b.array.copy())
+    T, b_ret = api.trimNodes(A_b, b=b_t)
+    out = capsys.readouterr().out
+    assert f"number of nodes trimmed:  {ids.size}" in out and "number of nonzero residuals set:  0" in out
+    assert T is A_b and b_ret is b_t
+    assert np.array_equal(T.rowptr, T_o.rowptr) and np.array_equal(T.colind, T_o.colind)
+    assert np.allclose(T.val, T_o.val, rtol=0, atol=1e-12 * np.abs(T_o.val).max())
+    assert np.all(b_t.array[ids] == 0.0)
+    tgt = api.Vec(np.linspace(1.0, 2.0, n_b))
+    b_l = api.Vec(b_b.array.copy())
+    A_l, _ = api.assembleLinearSystemBackground(A, api.Vec(g["b_f"]), M)
+    api.trimNodes(A_l, b=b_l, target=tgt, zero_vec=list(ids[:5]))
+    assert np.array_equal(b_l.array[ids[:5]], tgt.array[ids[:5]])
+    assert np.all(np.diff(A_l.rowptr)[ids[:5]] == 1)
+    # the trimmed system is nonsingular: the Krylov solve agrees with the oracle's
+    u = api.Vec(np.zeros(n_b))
+    api.solveKSP(T, b_t, u, method="cg", PC="jacobi", monitor=False)
+    ro = oracle.solve_ksp(T_o, bt_o, method="cg")
+    assert api.last_ksp_info.reason == ro.reason == 2 and abs(api.last_ksp_info.iterations - ro.iterations) <= 2
+    assert np.linalg.norm(u.array - ro.x) <= 1e-6 * np.linalg.norm(ro.x)
+    # solveKSP(remove_zero_diagonal=True) trims first (reference common.py:565-566)
+    A2, b2 = api.assembleLinearSystemBackground(A, api.Vec(g["b_f"]), M)
+    u2 = api.Vec(np.zeros(n_b))
+    api.solveKSP(A2, b2, u2, method="cg", PC="jacobi", remove_zero_diagonal=True, monitor=False)
+    assert np.linalg.norm(u2.array - ro.x) <= 1e-6 * np.linalg.norm(ro.x)
+    # solveNewtonsLinear: residual convention res = A_b u + L_b, u -= du  =>  converges to -A_b^{-1} L_b
+    u_f = api.Vec(np.zeros(n_f))
+    u_p = api.solveNewtonsLinear(A, api.Vec(g["b_f"]), u_f, M, None, linear_method="cg", linear_preconditioner="jacobi",
+                                 monitorNewtonConvergence=False, zero_vec=list(ids))
+    assert np.linalg.norm(u_p.array + ro.x) <= 1e-6 * np.linalg.norm(ro.x)
+    assert np.allclose(u_f.array, oracle.spmv(Mo, u_p.array), rtol=0, atol=1e-10 * np.abs(u_f.array).max())

@@ -12,7 +12,8 @@ def test_mirror_exports_reference_names():
 
     for name in ("v2p m2p arg2v arg2m zero_petsc_vec zero_petsc_mat updateU A_x_b AT_x AT_R_A").split():
         assert callable(getattr(la_utils, name)), name
-    for name in ("assembleLinearSystemBackground transferToForeground zeroDofBackground solveKSP readExOp").split():
+    for name in ("assembleLinearSystemBackground transferToForeground zeroDofBackground solveKSP readExOp "
+                 "createNonzeroDiagonal removeZeroDiagonal getIdentity trimNodes solveNewtonsLinear").split():
         assert callable(getattr(common, name)), name
     # star-import like the reference (common.py:8) re-exports la_utils
     assert common.AT_R_A is la_utils.AT_R_A
@@ -21,6 +22,10 @@ def test_mirror_exports_reference_names():
     sig = inspect.signature(common.solveKSP)
     assert list(sig.parameters) == ["A", "b", "u", "method", "PC", "remove_zero_diagonal", "rtol", "atol", "max_it",
                                     "bfr_tol", "monitor", "gmr_res", "bfr_b"]
+    assert list(inspect.signature(common.trimNodes).parameters) == ["A", "b", "bfr_tol", "target", "zero_vec", "monitor"]
+    assert list(inspect.signature(common.solveNewtonsLinear).parameters) == [
+        "A", "L", "u_f", "M", "u_p", "maxIters", "relativeTolerance", "monitorNewtonConvergence",
+        "moniterLinearConvergence", "linear_method", "linear_preconditioner", "relax_param", "zero_vec"]
     d = {k: v.default for k, v in sig.parameters.items()}
     assert (d["method"], d["PC"], d["rtol"], d["atol"], d["max_it"], d["gmr_res"]) == ("gmres", "jacobi", 1e-8, 1e-9, 1000000, 3000)
 

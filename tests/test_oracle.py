@@ -256,3 +256,42 @@ def test_unfitted_stress_case_generator(oracle, degree, n_cells):
     assert abs(A.val.sum() - 8.0) < 1e-11  # sigma * volume of [-1,1]^3 (stiffness rows sum to 0)
     P, V, scale = _scipy_triple(M, A)
     _assert_matches_scipy(C, P, V, 1e-13 * scale)
+
+
+def test_row_edits_follow_petsc_semantics(oracle):
+    """MatZeroRows without KEEP_NONZERO_PATTERN and `A += diag` over different patterns (trimNodes /
+    removeZeroDiagonal, reference common.py:236-332): dense check + the pattern rules."""
+    rng = np.random.default_rng(11)
+    A = _csr(oracle, 40, 40, rand_csr(rng, 40, 40, 4, empty_frac=0.25))
+    Ad = A.todense()
+    rows = np.array([0, 3, 3, 17, 39])
+    Z = oracle.zero_rows(A, rows, 1.0)
+    Zd = Ad.copy()
+    Zd[rows] = 0.0
+    Zd[rows, rows] = 1.0
+    assert np.array_equal(Z.todense(), Zd)
+    lens = np.diff(Z.rowptr)
+    assert np.all(lens[rows] == 1) and np.array_equal(np.delete(lens, rows), np.delete(np.diff(A.rowptr), rows))
+    Z0 = oracle.zero_rows(A, rows, 0.0)
+    assert np.all(np.diff(Z0.rowptr)[rows] == 0)
+    d = rng.standard_normal(40)
+    D = oracle.add_diagonal(A, d)
+    assert np.array_equal(D.todense(), Ad + np.diag(d))
+    for i in range(40):
+        c = D.colind[D.rowptr[i]:D.rowptr[i + 1]]
+        assert np.all(np.diff(c) > 0) and i in c
+    assert D.nnz == A.nnz + int(np.sum(~np.diag(A.pattern_dense())))
+    # trimNodes on a product with unsupported background functions: empty rows become unit rows
+    M = _csr(oracle, 60, 40, rand_csr(rng, 60, 40, 2, empty_frac=0.5))
+    S = _csr(oracle, 60, 60, rand_csr(rng, 60, 60, 5))
+    C = oracle.AT_R_A(M, oracle.CSR.from_scipy(S.to_scipy() @ S.to_scipy().T))
+    b = rng.standard_normal(40)
+    C2, b2, ids = oracle.trim_nodes(C, b)
+    dg = oracle.diagonal(C)
+    assert np.array_equal(ids, np.flatnonzero(dg <= 1e-9)) and ids.size > 0
+    assert np.all(oracle.diagonal(C2)[ids] == 1.0) and np.all(b2[ids] == 0.0)
+    assert np.array_equal(np.delete(b2, ids), np.delete(b, ids))
+    # getIdentity = removeZeroDiagonal(empty matrix) (reference common.py:254-258)
+    E = oracle.CSR(5, 5, np.zeros(6, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0))
+    I5 = oracle.add_diagonal(E, oracle.create_nonzero_diagonal(E))
+    assert np.array_equal(I5.todense(), np.eye(5))
