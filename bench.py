@@ -348,8 +348,9 @@ def run_ours(args):
         # assembleLinearSystemBackground call as the same Mat: the mirror's CSRMat keeps its device copy,
         # so M crosses PCIe once, outside the step.  A_f and b_f are new host objects on every step (a fresh
         # assemble() per Newton iteration, common.py:432-435) and are uploaded inside the timed region.
-        h2d = sum(t.numel() * t.element_size() for t in hA) + hb.numel() * 8
-        d2h = 2 * n_b * 8
+        # b_b stays on the device between AT_x and solveKSP; u crosses twice (initial guess in, solution out)
+        h2d = sum(t.numel() * t.element_size() for t in hA) + hb.numel() * 8 + n_b * 8
+        d2h = n_b * 8
         u_host = np.zeros(n_b)
         Mh = ref_api.CSRMat((n_f, n_b), *(t.numpy() for t in hM))
 
@@ -403,7 +404,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             dtv = (time.perf_counter() - t0) / n_e2e
             e2e["fixed_pattern"] = {"value": n_f / dtv / 1e6, "unit": UNIT, "ms_per_step": dtv * 1e3,
-                                    "h2d_bytes_per_step": int(nnzA * 8 + n_f * 8)}
+                                    "h2d_bytes_per_step": int(nnzA * 8 + n_f * 8 + n_b * 8)}
             del Ah
         except Exception as exc:  # explanatory only
             e2e["fixed_pattern"] = {"error": str(exc)[:200]}

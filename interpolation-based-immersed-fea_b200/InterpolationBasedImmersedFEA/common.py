@@ -12,8 +12,8 @@ import numpy as np
 
 import iife_b200 as _iife
 from .la_utils import *  # noqa: F401,F403  (the reference star-imports la_utils too, common.py:8)
-from .la_utils import (HAVE_DOLFIN, HAVE_PETSC, CSRMat, Vec, _as_device, _vec_array, arg2m, arg2v, AT_R_A, AT_x,
-                       updateU)
+from .la_utils import (HAVE_DOLFIN, HAVE_PETSC, CSRMat, Vec, _as_device, _to_device, _vec_array, arg2m, arg2v, AT_R_A,
+                       AT_x, updateU)
 
 DEFAULT_LINEAR_SOLVER = 'gmres'  # reference common.py:36
 
@@ -84,10 +84,24 @@ def solveKSP(A, b, u, method='gmres', PC='jacobi',
         A, b = trimNodes(A, b=b, bfr_tol=bfr_tol)  # reference common.py:565-566
     dA = _as_device(arg2m(A))
     bv, uv = arg2v(b), arg2v(u)
-    x = np.ascontiguousarray(_vec_array(uv), dtype=np.float64).copy()
-    info = _iife.ksp_solve(dA, _vec_array(bv), x, _KRYLOV[method], _iife.PC_JACOBI, rtol=rtol, atol=atol,
-                           max_it=max_it, restart=300, hist_len=(4096 if monitor else 0))
-    _vec_array(uv)[:] = x
+    kw = dict(rtol=rtol, atol=atol, max_it=max_it, restart=300, hist_len=(4096 if monitor else 0))
+    uarr = _vec_array(uv)  # u is updated in place (:634-636)
+    direct = isinstance(uarr, np.ndarray) and uarr.dtype == np.float64 and uarr.flags.c_contiguous and uarr.ndim == 1
+    if isinstance(bv, Vec) and bv.device_tensor() is not None and direct and uarr.size > 0:
+        # b was produced on the GPU (AT_x): solve there; only u crosses PCIe (guess in, solution out)
+        import torch
+
+        b_d = bv.device_tensor()
+        x_d = torch.from_numpy(uarr).to(b_d.device)
+        torch.cuda.current_stream(b_d.device).synchronize()
+        info = _iife.ksp_solve(dA, b_d, x_d, _KRYLOV[method], _iife.PC_JACOBI, **kw)
+        torch.from_numpy(uarr).copy_(x_d)
+    elif direct:
+        info = _iife.ksp_solve(dA, _vec_array(bv), uarr, _KRYLOV[method], _iife.PC_JACOBI, **kw)
+    else:
+        x = np.ascontiguousarray(uarr, dtype=np.float64).copy()
+        info = _iife.ksp_solve(dA, _vec_array(bv), x, _KRYLOV[method], _iife.PC_JACOBI, **kw)
+        uarr[:] = x
     last_ksp_info = info
     if monitor:
         # the reference prints the iteration count and PETSc's (always empty) history (:638-641)
@@ -174,9 +188,9 @@ def solveNewtonsLinear(A, L, u_f, M, u_p,
     if method in _DELEGATED_METHODS or pc in _DELEGATED_PCS or method not in _KRYLOV or pc != 'jacobi':
         raise NotImplementedError(f"solveNewtonsLinear(linear_method={method!r}, linear_preconditioner={pc!r})")
     dA, dM = _as_device(arg2m(A_b)), _as_device(arg2m(M))
-    dev = torch.device("cuda", torch.cuda.current_device())
     n_b = dA.shape[0]
-    Lb_d = torch.from_numpy(np.ascontiguousarray(_vec_array(arg2v(L_b)), dtype=np.float64)).to(dev)
+    Lb_d = _to_device(L_b)
+    dev = Lb_d.device
     up_d = torch.zeros(n_b, dtype=torch.float64, device=dev)
     res_d = torch.empty_like(up_d)
     du_d = torch.empty_like(up_d)

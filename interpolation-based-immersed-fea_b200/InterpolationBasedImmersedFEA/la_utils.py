@@ -48,17 +48,42 @@ def _ensure_init():
 # light stand-ins with the PETSc method names used by the reference's callers
 # --------------------------------------------------------------------------------------------------
 class Vec:
-    """Dense fp64 vector with the subset of the ``PETSc.Vec`` API the reference's callers use."""
+    """Dense fp64 vector with the subset of the ``PETSc.Vec`` API the reference's callers use.
 
-    def __init__(self, array):
-        self.array = np.ascontiguousarray(array, dtype=np.float64)
+    Like :class:`CSRMat` the host array is lazy: a vector produced on the GPU (``AT_x``) stays there until
+    somebody reads ``.array``; ``solveKSP`` consumes it without a round trip through host memory.  Reading
+    ``.array`` hands out a mutable numpy array, so from then on the host copy is the only one."""
+
+    def __init__(self, array=None, device=None):
+        if array is None and device is None:
+            raise ValueError("Vec needs a host array or a device tensor")
+        self._array = None if array is None else np.ascontiguousarray(array, dtype=np.float64)
+        self._dev = device if array is None else None  # float64 CUDA tensor holding the current value
+
+    @property
+    def array(self):
+        if self._array is None:
+            _iife.sync()  # the producer ran on the library's stream
+            self._array = self._dev.cpu().numpy()
+        self._dev = None
+        return self._array
+
+    @array.setter
+    def array(self, a):
+        self._array = np.ascontiguousarray(a, dtype=np.float64)
+        self._dev = None
+
+    def device_tensor(self):
+        """The device-resident value, or None when the vector lives on the host."""
+        return self._dev
 
     # PETSc.Vec API
     def getSize(self):
-        return int(self.array.size)
+        return int(self._array.size if self._array is not None else self._dev.numel())
 
     def getSizes(self):
-        return (int(self.array.size), int(self.array.size))
+        n = self.getSize()
+        return (n, n)
 
     def getArray(self):
         return self.array
@@ -88,7 +113,7 @@ class Vec:
         return None
 
     def getOwnershipRange(self):
-        return (0, int(self.array.size))
+        return (0, self.getSize())
 
     def getValue(self, i):
         return float(self.array[i])
@@ -117,7 +142,7 @@ class Vec:
         return self
 
     def __len__(self):
-        return int(self.array.size)
+        return self.getSize()
 
 
 class CSRMat:
@@ -354,6 +379,26 @@ def _as_device(A) -> DeviceMat:
     return arg2m(A).device()
 
 
+def _torch():
+    import torch  # device memory and copies only
+
+    return torch
+
+
+def _to_device(x):
+    """float64 CUDA tensor with the value of a vector (no copy if it already lives on the GPU).  Uploads run
+    on torch's stream and are complete on return, so the library's stream can consume them."""
+    v = arg2v(x)
+    if isinstance(v, Vec) and v.device_tensor() is not None:
+        return v.device_tensor()
+    _ensure_init()
+    torch = _torch()
+    dev = torch.device("cuda", max(_iife.current_device(), 0))
+    t = torch.from_numpy(np.ascontiguousarray(_vec_array(v), dtype=np.float64)).to(dev)
+    torch.cuda.current_stream(dev).synchronize()
+    return t
+
+
 def _vec_array(x) -> np.ndarray:
     v = arg2v(x)
     if isinstance(v, Vec):
@@ -388,6 +433,13 @@ def AT_x(A, x):
     x_v = arg2v(x)
     dev = _as_device(A_m)
     row, col = dev.shape
+    if not HAVE_PETSC and row > 0 and col > 0:
+        # the result stays on the GPU (lazy Vec): the next consumer is solveKSP
+        x_d = _to_device(x_v)
+        y_d = _torch().empty(col, dtype=_torch().float64, device=x_d.device)
+        dev.spmv(x_d, y=y_d, trans=True)
+        _iife.sync()
+        return Vec(device=y_d)
     y = dev.spmv(_vec_array(x_v), trans=True)
     b = zero_petsc_vec(col, comm=A_m.getComm() if hasattr(A_m, "getComm") else None)
     _vec_array(b)[:] = y

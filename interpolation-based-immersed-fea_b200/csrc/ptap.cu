@@ -1129,7 +1129,9 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
       int lg2 = a.logG2 < 2 ? 2 : (a.logG2 > 5 ? 5 : a.logG2);
       if (const char *e1v = getenv("IIFE_PTAP_LG1")) lg1 = atoi(e1v);
       if (const char *e2v = getenv("IIFE_PTAP_LG2")) lg2 = atoi(e2v);
-      slot_kernel_t kern = pick_slot_kernel(lg1, lg2);
+      bool ctail = false;  // compacted second pass over long operand rows (ptap_slots.cuh)
+      if (const char *et = getenv("IIFE_PTAP_CTAIL")) ctail = atoi(et) != 0;
+      slot_kernel_t kern = pick_slot_kernel(lg1, lg2, ctail);
       if (!kern) { rc = set_err(IIFE_ERR_ARG, "no slot kernel for group sizes 2^%d / 2^%d", lg1, lg2); break; }
       int cap1 = SLOT_CAP1[sb], cap2 = SLOT_CAP2[sb];
       size_t per_warp = ((size_t)(32 >> lg1) * cap1 + (size_t)(32 >> lg2) * cap2) * 8;

@@ -23,10 +23,15 @@ constexpr int PS_BATCH = 4;
 
 // items: one per lane (beg/len/w/off in registers); entries e of item `it` add w * x_val[beg+e] into
 // hv[group][slots[off+e]].
-template <int LG>
+//
+// Operand rows longer than the lane group (M rows of 8 entries with 4 lanes per row: one row in eight of the
+// trilinear operator) need a second pass.  CTAIL = false walks all items again and lets the short ones idle;
+// CTAIL = true first compacts the lane numbers of the long items into `tail_src` (32 bytes of shared memory per
+// warp), so the second pass costs steps only for the items that need it.
+template <int LG, bool CTAIL>
 __device__ __forceinline__ void slot_stage(int cnt, int my_beg, int my_len, double my_w, int my_off,
                                            const double *__restrict__ x_val, const unsigned char *__restrict__ slots,
-                                           double *hv, int cap, int lane) {
+                                           double *hv, int cap, int lane, unsigned char *tail_src) {
   constexpr int G = 1 << LG, NG = 32 >> LG;
   const int g = lane >> LG, lg = lane & (G - 1);
   double *hv_g = hv + (size_t)g * cap;
@@ -56,7 +61,31 @@ __device__ __forceinline__ void slot_stage(int cnt, int my_beg, int my_len, doub
       if (sl[b] >= 0) hv_g[sl[b]] += v[b];
     }
   }
-  if (__any_sync(0xffffffffu, my_len > G)) {  // operand rows longer than G: remaining entries
+  const unsigned long_mask = __ballot_sync(0xffffffffu, my_len > G);  // my_len is 0 beyond cnt
+  if (CTAIL && long_mask) {
+    const int n_long = __popc(long_mask);
+    if (my_len > G) tail_src[__popc(long_mask & ((1u << lane) - 1u))] = (unsigned char)lane;
+    __syncwarp();
+    for (int t0 = 0; t0 < n_long; t0 += NG) {
+      const int idx = t0 + g;
+      const int src = idx < n_long ? (int)tail_src[idx] : 0;
+      int beg = __shfl_sync(0xffffffffu, my_beg, src);
+      int len = __shfl_sync(0xffffffffu, my_len, src);
+      int off = __shfl_sync(0xffffffffu, my_off, src);
+      double w = __shfl_sync(0xffffffffu, my_w, src);
+      if (idx >= n_long) len = 0;
+      for (int e = G + lg; __any_sync(0xffffffffu, e < len); e += G) {
+        int s1 = -1;
+        double v = 0.0;
+        if (e < len) {
+          s1 = (int)__ldg(slots + off + e);
+          v = w * __ldg(x_val + beg + e);
+        }
+        __syncwarp();
+        if (s1 >= 0) hv_g[s1] += v;
+      }
+    }
+  } else if (long_mask) {  // operand rows longer than G: remaining entries
     for (int s = 0; s < nsteps; ++s) {
       int it = s * NG + g;
       int src = it & 31;
@@ -80,11 +109,13 @@ __device__ __forceinline__ void slot_stage(int cnt, int my_beg, int my_len, doub
   __syncwarp();
 }
 
-template <int LG1, int LG2>
+template <int LG1, int LG2, bool CTAIL>
 __global__ void __launch_bounds__(256) k_ptap_numeric_slots(PtapArgs a, int cap1, int cap2) {
   constexpr int NG1 = 32 >> LG1, NG2 = 32 >> LG2;
   extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ unsigned char s_tail[8][32];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  unsigned char *tail_src = s_tail[wic];
   const int wpc = blockDim.x >> 5;
   const size_t per_warp = ((size_t)NG1 * cap1 + (size_t)NG2 * cap2) * 8;
   double *h1v = (double *)(smem + per_warp * wic);
@@ -131,7 +162,8 @@ __global__ void __launch_bounds__(256) k_ptap_numeric_slots(PtapArgs a, int cap1
         }
         int total;
         int my_off = warp_excl_scan(my_len, lane, &total);
-        slot_stage<LG1>(min(32, mt_n - base), my_beg, my_len, my_w, my_off, a.a_val, s1 + base_off, h1v, cap1, lane);
+        slot_stage<LG1, CTAIL>(min(32, mt_n - base), my_beg, my_len, my_w, my_off, a.a_val, s1 + base_off, h1v, cap1,
+                               lane, tail_src);
         base_off += total;
       }
     }
@@ -163,7 +195,8 @@ __global__ void __launch_bounds__(256) k_ptap_numeric_slots(PtapArgs a, int cap1
         }
         int total;
         int my_off = warp_excl_scan(my_len, lane, &total);
-        slot_stage<LG2>(min(32, n1 - base), my_beg, my_len, my_w, my_off, a.m_val, s2 + base_off, h2v, cap2, lane);
+        slot_stage<LG2, CTAIL>(min(32, n1 - base), my_beg, my_len, my_w, my_off, a.m_val, s2 + base_off, h2v, cap2,
+                               lane, tail_src);
         base_off += total;
       }
     }
@@ -179,9 +212,9 @@ __global__ void __launch_bounds__(256) k_ptap_numeric_slots(PtapArgs a, int cap1
 }
 
 typedef void (*slot_kernel_t)(PtapArgs, int, int);
-static slot_kernel_t pick_slot_kernel(int lg1, int lg2) {
+static slot_kernel_t pick_slot_kernel(int lg1, int lg2, bool ctail) {
 #define PSK(a_, b_) \
-  if (lg1 == a_ && lg2 == b_) return k_ptap_numeric_slots<a_, b_>;
+  if (lg1 == a_ && lg2 == b_) return ctail ? k_ptap_numeric_slots<a_, b_, true> : k_ptap_numeric_slots<a_, b_, false>;
   PSK(3, 2) PSK(3, 3) PSK(3, 4) PSK(3, 5)
   PSK(4, 2) PSK(4, 3) PSK(4, 4) PSK(4, 5)
   PSK(5, 2) PSK(5, 3) PSK(5, 4) PSK(5, 5)

@@ -24,13 +24,20 @@ REASONS = {
 }
 
 _initialised = False
+_device_index = -1
 
 
 def init(device: int = 0) -> None:
     """Bind this process to one GPU.  Raises if there is no usable sm_100 device (no CPU fallback)."""
-    global _initialised
+    global _initialised, _device_index
     check(lib.iife_init(int(device)))
     _initialised = True
+    _device_index = int(device)
+
+
+def current_device() -> int:
+    """Index of the GPU this process is bound to (-1 before init)."""
+    return _device_index if _initialised else -1
 
 
 def is_initialised() -> bool:
