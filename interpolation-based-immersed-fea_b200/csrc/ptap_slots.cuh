@@ -20,6 +20,7 @@
 namespace iife {
 
 constexpr int PS_BATCH = 4;
+constexpr int SLOT_TAIL_BYTES = 32;  // one lane number per long item of a 32-item chunk
 
 // items: one per lane (beg/len/w/off in registers); entries e of item `it` add w * x_val[beg+e] into
 // hv[group][slots[off+e]].
@@ -113,13 +114,13 @@ template <int LG1, int LG2, bool CTAIL>
 __global__ void __launch_bounds__(256) k_ptap_numeric_slots(PtapArgs a, int cap1, int cap2) {
   constexpr int NG1 = 32 >> LG1, NG2 = 32 >> LG2;
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ unsigned char s_tail[8][32];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  unsigned char *tail_src = s_tail[wic];
   const int wpc = blockDim.x >> 5;
-  const size_t per_warp = ((size_t)NG1 * cap1 + (size_t)NG2 * cap2) * 8;
+  // per warp: h1v[NG1][cap1], h2v[NG2][cap2] (fp64) and SLOT_TAIL_BYTES for the compacted second pass
+  const size_t per_warp = ((size_t)NG1 * cap1 + (size_t)NG2 * cap2) * 8 + SLOT_TAIL_BYTES;
   double *h1v = (double *)(smem + per_warp * wic);
   double *h2v = h1v + (size_t)NG1 * cap1;
+  unsigned char *tail_src = (unsigned char *)(h2v + (size_t)NG2 * cap2);
   const int64_t warp_global = (int64_t)blockIdx.x * wpc + wic;
   const int64_t n_warps = (int64_t)gridDim.x * wpc;
 
