@@ -537,6 +537,7 @@ __global__ void k_ptap_numeric(PtapArgs a) {
 }  // namespace iife
 #include "ptap_warp.cuh"
 #include "ptap_slots.cuh"
+#include "ptap_slots2.cuh"
 namespace iife {
 
 // ------------------------------------------------------------------------------------------------
@@ -1131,10 +1132,13 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
       if (const char *e2v = getenv("IIFE_PTAP_LG2")) lg2 = atoi(e2v);
       bool ctail = true;  // compacted second pass over long operand rows (ptap_slots.cuh): 24.9 -> 22.3 ms
       if (const char *et = getenv("IIFE_PTAP_CTAIL")) ctail = atoi(et) != 0;
-      slot_kernel_t kern = pick_slot_kernel(lg1, lg2, ctail);
+      bool v2 = false;  // experimental kernel of ptap_slots2.cuh (not yet validated on a GPU)
+      if (const char *e2k = getenv("IIFE_PTAP_V2")) v2 = atoi(e2k) != 0;
+      slot_kernel_t kern = v2 ? pick_slot2_kernel(lg1, lg2) : pick_slot_kernel(lg1, lg2, ctail);
       if (!kern) { rc = set_err(IIFE_ERR_ARG, "no slot kernel for group sizes 2^%d / 2^%d", lg1, lg2); break; }
       int cap1 = SLOT_CAP1[sb], cap2 = SLOT_CAP2[sb];
-      size_t per_warp = ((size_t)(32 >> lg1) * cap1 + (size_t)(32 >> lg2) * cap2) * 8 + SLOT_TAIL_BYTES;
+      size_t per_warp = v2 ? slot2_per_warp_bytes(lg1, lg2, cap1, cap2)
+                           : ((size_t)(32 >> lg1) * cap1 + (size_t)(32 >> lg2) * cap2) * 8 + SLOT_TAIL_BYTES;
       size_t smem_max = (size_t)(c.max_smem_optin ? c.max_smem_optin : 227 * 1024);
       int wpc = 8;
       if (const char *ew = getenv("IIFE_PTAP_WPC")) wpc = atoi(ew);
