@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "p2p_dev.cuh"
 #include <math.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <chrono>
 
@@ -258,6 +259,10 @@ __global__ void k_cg_update_scalars(double *sc, int *fl, double *hist, long long
   if (!(sc[S_DELTA] > 0.0)) return;  // reason was set by k_cg_update
   cg_update_scalars(sc, fl, sc[S_RAW + 0], sc[S_RAW + 1], hist, hist_len);
 }
+
+}  // namespace iife
+#include "ksp_persist.cuh"
+namespace iife {
 
 // ------------------------------------------------------------------------------------------------
 // FGMRES kernels.  Device-side small arrays: H (m+1) x m column-major, cs[m], sn[m], rs[m+1], y[m].
@@ -672,8 +677,68 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   }
   int chunk = env_int("IIFE_KSP_CHUNK", 32);
   if (chunk < 1) chunk = 1;
+  // EXPERIMENTAL (ksp_persist.cuh, off by default): one cooperative kernel per chunk of iterations
+  bool persist = false;
+  CgPersist pa{};
+  int pgrid = 0;
+  Tmp<GridBcast> bcast;
+  if (env_int("IIFE_KSP_PERSIST", 0) != 0 && A->sell_state == 1 && (!dist || p2p) && !dbg_nohalo && !dbg_nored) {
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device);
+    if (dist) IIFE_TRY(mat_ensure_sell_order(A, H->n_owned));
+    if (coop && (!dist || A->sell_order) &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persist<4>, VEC_THREADS, 0) == cudaSuccess && per_sm >= 1) {
+      int64_t need = std::max<int64_t>((n + VEC_THREADS - 1) / VEC_THREADS, (A->sell_slices + 7) / 8);
+      int64_t gmax = std::min<int64_t>((int64_t)c.sm_count * per_sm, MAX_PARTIALS);
+      pgrid = (int)std::max<int64_t>(1, std::min<int64_t>(need, gmax));
+      IIFE_TRY(bcast.alloc(1));
+      IIFE_CUDA(cudaMemsetAsync(bcast.p, 0, sizeof(GridBcast), c.stream));
+      pa.sell_ptr = A->sell_ptr;
+      pa.sell_cptr = A->sell_cptr;
+      pa.sell_col = A->sell_col;
+      pa.sell_val = A->sell_val;
+      pa.n_rows = n;
+      pa.n_slices = A->sell_slices;
+      pa.order = dist ? A->sell_order : nullptr;
+      pa.n_interior = dist ? A->sell_n_interior : A->sell_slices;
+      pa.x = x;
+      pa.r = r.p;
+      pa.p = p.p;
+      pa.w = wv.p;
+      pa.dinv = dinv;
+      pa.sc = w.sc;
+      pa.fl = w.fl;
+      pa.hist = w.hist;
+      pa.hist_len = (long long)w.hist_len;
+      pa.partials = w.partials;
+      pa.bc = bcast.p;
+      pa.n_iters = chunk;
+      pa.dist = dist ? 1 : 0;
+      if (dist) {
+        pa.pr = pr;
+        for (int q = 0; q < P2P_MAX_RANKS; ++q) {
+          pa.pt.xbuf[q] = H->peer_xbuf[q];
+          pa.pt.mbox[q] = H->peer_mbox[q];
+          pa.pt.dst_start[q] = H->dst_start[q];
+        }
+        pa.mbox = H->mbox;
+        pa.send_idx = H->send_idx;
+        pa.send_peer = H->send_peer;
+        pa.send_off = H->send_off_dev;
+        pa.total_send = (long long)H->total_send;
+        pa.send_mask = H->send_mask;
+        pa.recv_mask = H->recv_mask;
+        pa.halo_seq = H->dev_seq;
+        pa.iter_ptr = H->dev_seq + 2;
+        pa.push_counter = H->p2p_counter;
+      }
+      persist = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
   // NCCL calls inside the loop: keep to plain stream launches (no graph capture) in that case
-  const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && (!dist || p2p);
+  const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && (!dist || p2p) && !persist;
   auto enqueue_iteration = [&]() -> int {
     IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl);
     if (fused_halo) {
@@ -765,7 +830,12 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
   auto enqueue_chunk = [&](int slot) -> int {
-    if (exec) {
+    if (persist) {
+      void *kargs[] = {(void *)&pa};
+      cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_cg_persist<4>, dim3(pgrid), dim3(VEC_THREADS), kargs, 0, c.stream);
+      if (e != cudaSuccess) return set_err(IIFE_ERR_CUDA, "cooperative CG launch: %s", cudaGetErrorString(e));
+      c.launches++;
+    } else if (exec) {
       cudaError_t e = cudaGraphLaunch(exec, c.stream);
       if (e != cudaSuccess) return set_err(IIFE_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
       c.launches += launches_per_chunk;
