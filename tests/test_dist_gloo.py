@@ -34,7 +34,15 @@ def _worker(rank, world, port, n_cells, out_dir):
         from oracle import oracle as O
         from oracle.synthetic_cube import assemble_cube
 
-        A, M, b = assemble_cube(n_cells)
+        if isinstance(n_cells, tuple):  # ("s2", N_f, degree): unfitted case — rotated background, empty rows of A_b,
+            from iife_b200 import synthetic  # background blocks that do not follow the foreground slabs
+
+            gsy = synthetic.unfitted_operators(n_cells[1], n_cells[2])
+            A = O.CSR(gsy["n_f"], gsy["n_f"], *gsy["A"])
+            M = O.CSR(gsy["n_f"], gsy["n_b"], *gsy["M"])
+            b = gsy["b_f"]
+        else:
+            A, M, b = assemble_cube(n_cells)
         rng = np.random.default_rng(0)
         # break the symmetry/regularity a little: drop the support of two background functions
         n_f, n_b = A.n_rows, M.n_cols
@@ -108,7 +116,7 @@ def _worker(rank, world, port, n_cells, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_cells", [(2, 3), (3, 4)])
+@pytest.mark.parametrize("world,n_cells", [(2, 3), (3, 4), (2, ("s2", 8, 1)), (3, ("s2", 6, 2))])
 def test_row_partitioned_setup(tmp_path, world, n_cells):
     from oracle import oracle as O
 
