@@ -438,6 +438,7 @@ int mat_ensure_transpose(Mat *A) {
     IIFE_TRY(gather_vals_launch(A->val, A->T_perm, A->T->val, A->nnz));
     A->T->dinv_valid = false;
     A->T->T_vals_valid = false;
+    A->T->sell_vals_valid = false;
     A->T_vals_valid = true;
   }
   return IIFE_OK;
