@@ -72,6 +72,30 @@ __device__ __forceinline__ unsigned long long ld_flag_gpu(const unsigned long lo
   return v;
 }
 
+// Polling with acquire loads makes the SM drop its L1 on every probe (CCTL.IVALL in the SASS), which also hits the
+// x gathers of CTAs still multiplying on the same SM: poll relaxed, fence once when the flag has arrived.
+__device__ __forceinline__ bool wait_flag_sys(const unsigned long long *p, unsigned long long seq, int *err) {
+  unsigned long long v;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if (v >= seq) break;
+    if (clock64() - t0 > P2P_SPIN_LIMIT) {
+      atomicExch(err, 1);
+      return false;
+    }
+  }
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  return true;
+}
+__device__ __forceinline__ void wait_flag_gpu(const unsigned long long *p, unsigned long long seq) {
+  unsigned long long v;
+  do {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  } while (v < seq);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
 // one slice of the SELL operator; x is written inside the same kernel, so it is read with ordinary cached
 // loads (valid after a grid barrier) or, for slices that touch ghost entries, through L2 (VIA_L2)
 template <int U, bool VIA_L2>
@@ -163,8 +187,7 @@ __device__ __forceinline__ void persist_reduce(const CgPersist &a, const double 
     }
   } else {
     if (tid == 0) {
-      while (ld_flag_gpu(&a.bc->flag) < bseq) {
-      }
+      wait_flag_gpu(&a.bc->flag, bseq);
       for (int v = 0; v < nv; ++v) s_val[v] = ((volatile double *)a.bc->vals[par])[v];
     }
     __syncthreads();
@@ -236,7 +259,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_persist(CgPersist a) {
       }
     }
     if (a.dist) {
-      if (tid < a.pr.nranks && ((a.recv_mask >> tid) & 1u)) spin_until(&a.mbox->halo_flag[tid], hseq, a.pr.err);
+      if (tid < a.pr.nranks && ((a.recv_mask >> tid) & 1u)) wait_flag_sys(&a.mbox->halo_flag[tid], hseq, a.pr.err);
       __syncthreads();
       for (long long idx = a.n_interior + w0; idx < a.n_slices; idx += nw) {
         const long long s = a.order[idx];
