@@ -1,0 +1,40 @@
+#!/bin/bash
+# First GPU call of the next round: measure the three prepared-but-unmeasured experiments (ROUND_NOTES.md) against
+# the default path in ONE call.  Everything is wrapped in `timeout`; results land in gpurun_out/r2_*.
+# usage (from the repo root):  gpurun --timeout 600 -- 'bash scripts/r2_experiments.sh'
+mkdir -p gpurun_out
+SUB='ptap or unfitted or cube or golden'
+run_bench() {  # $1 = tag, rest = env assignments
+  tag=$1; shift
+  env "$@" timeout 150 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/r2_bench_$tag.json 2> gpurun_out/r2_bench_$tag.err
+  python - "$tag" <<'PY'
+import json, sys
+tag = sys.argv[1]
+try:
+    d = json.load(open(f"gpurun_out/r2_bench_{tag}.json"))
+    r = d["roofline"]
+    print(f"[{tag}] step {d['ms_per_step']:.2f} ms  spmv {r['launch_ms']*1e3:.0f} us  cg/it {r['cg_iteration']['ms']*1e3:.0f} us  ptap numeric {r['ptap_numeric']['ms']:.2f} ms")
+except Exception as exc:
+    print(f"[{tag}] no bench line: {exc}")
+PY
+}
+run_bench default IIFE_NOP=1
+# 1. slot-plan kernel v2
+IIFE_PTAP_V2=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "$SUB" 2>&1 | tail -5 > gpurun_out/r2_tests_v2.log
+tail -1 gpurun_out/r2_tests_v2.log
+run_bench v2 IIFE_PTAP_V2=1
+# 2. SELL path for transposed products
+IIFE_SPMV_SELL_T=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "spmv or cube or golden or end_to_end" 2>&1 | tail -5 > gpurun_out/r2_tests_sellt.log
+tail -1 gpurun_out/r2_tests_sellt.log
+IIFE_SPMV_SELL_T=1 SKIP_FGMRES=1 timeout 120 python scripts/phase_bench.py 184 2>&1 | grep -E "spmvT|spmv\(M\)" > gpurun_out/r2_phase_sellt.log
+cat gpurun_out/r2_phase_sellt.log
+# 3. persistent cooperative CG, single GPU (never leave a hung kernel behind: short timeouts)
+IIFE_KSP_PERSIST=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "ksp or golden or cube or unfitted or end_to_end" 2>&1 | tail -5 > gpurun_out/r2_tests_persist.log
+tail -1 gpurun_out/r2_tests_persist.log
+run_bench persist IIFE_KSP_PERSIST=1
+IIFE_KSP_PERSIST=1 timeout 120 python scripts/small_configs.py > gpurun_out/r2_small_persist.log 2>&1
+timeout 120 python scripts/small_configs.py > gpurun_out/r2_small_default.log 2>&1
+tail -6 gpurun_out/r2_small_default.log gpurun_out/r2_small_persist.log
+# 4. S2 stress case at a size where the hashing kernels matter
+timeout 200 python scripts/phase_bench_s2.py 96:1 64:2 > gpurun_out/r2_phase_s2.log 2>&1
+cat gpurun_out/r2_phase_s2.log
