@@ -253,6 +253,11 @@ __global__ void k_cg_scalars_p2p(double *sc, int *fl, double *hist, long long hi
   *iter = *iter + 1ull;
 }
 
+// A solve that stopped on (p, A p) <= 0 has exchanged reduction 2*iter+1 without finishing iteration `iter`: the
+// next solve on the same halo must not meet those flags again, so every solve starts on a fresh sequence
+// number (all ranks run the same launches, so they stay in step).
+__global__ void k_bump_seq(unsigned long long *iter) { *iter = *iter + 1ull; }
+
 // row-partitioned solver: scalar step after the allreduce of the two raw sums
 __global__ void k_cg_update_scalars(double *sc, int *fl, double *hist, long long hist_len) {
   if (fl[F_REASON] != 0) return;
@@ -642,6 +647,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     for (int q = 0; q < P2P_MAX_RANKS; ++q) pr.peer[q] = H->peer_mbox[q];
     pr.iter = H->dev_seq + 2;
     pr.err = H->p2p_err;
+    IIFE_LAUNCH(k_bump_seq, 1, 1, 0, H->dev_seq + 2);
   }
   // r = b - A x0   (row-partitioned: x0 is staged in p to receive its ghost entries)
   IIFE_LAUNCH(k_copy_gated, g, VEC_THREADS, 0, b, r.p, n, (const int *)nullptr);
