@@ -14,6 +14,7 @@
  *   common.py:364        Mat.multAdd()              (MatMultAdd)    iife_spmv(alpha=1, beta=1 on a copy)
  *   common.py:554-574, 628-636  KSP create/setUp/solve (KSPCG, KSPFGMRES, PCJACOBI)  iife_ksp_solve
  *   common.py:222,305    Mat.getDiagonal()                          iife_mat_get_diagonal
+ *   common.py:483-507    KSP GMRES + computeExtremeSingularValues (estimateConditionNumber)  iife_ksp_solve_hessenberg
  *   common.py:284,327    Mat.zeroRows()  (trimNodes)  (MatZeroRows)  iife_mat_zero_rows
  *   common.py:243-249    A0.setDiagonal(vd); A += A0  (removeZeroDiagonal, getIdentity)  iife_mat_add_diagonal
  *
@@ -178,6 +179,15 @@ typedef struct iife_ksp_result {
 int iife_ksp_solve(iife_mat A, int ksp_type, int pc_type, double rtol, double atol, double dtol,
                    int64_t max_it, int restart, const double *b, double *x, int mem,
                    iife_halo halo, iife_ksp_result *res, double *hist, int64_t hist_len);
+/* FGMRES solve (single GPU) that also returns the k x k upper-triangular factor R (column-major, leading
+ * dimension k, host memory, r_capacity doubles available) of the last cycle's Hessenberg matrix; *k_out = k.
+ * The Givens rotations are orthogonal, so R has the singular values PETSc's
+ * KSPComputeExtremeSingularValues reports for that cycle: estimateConditionNumber, common.py:483-507
+ * (GMRES restart 1000, PC none).  pc_type NONE reproduces PETSc's Hessenberg; JACOBI is the right-preconditioned
+ * operator A D^-1 (PETSc would use D^-1 A). */
+int iife_ksp_solve_hessenberg(iife_mat A, int pc_type, double rtol, double atol, double dtol, int64_t max_it,
+                              int restart, const double *b, double *x, int mem, iife_ksp_result *res, double *R,
+                              int64_t r_capacity, int64_t *k_out);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU) */
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the host framework (torch.distributed) */

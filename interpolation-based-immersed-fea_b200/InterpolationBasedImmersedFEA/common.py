@@ -3,7 +3,8 @@
 ``transferToForeground`` (:123-140), ``zeroDofBackground`` (:120-121), ``solveKSP`` (:509-641), the
 extraction-operator import ``readExOp`` (:645-712, host side) and — SURVEY.md §8f rows N1/N3 — the
 basis-function-removal helpers ``createNonzeroDiagonal`` / ``removeZeroDiagonal`` / ``getIdentity`` /
-``trimNodes`` (:207-332) and the Newton driver for linear systems ``solveNewtonsLinear`` (:335-402).  FEniCS assembly stays on the host
+``trimNodes`` (:207-332), the Newton driver for linear systems ``solveNewtonsLinear`` (:335-402) and
+``estimateConditionNumber`` (:483-507).  FEniCS assembly stays on the host
 exactly as in the reference; everything PETSc did on this path runs in libiife.so on the GPU.
 """
 from __future__ import annotations
@@ -232,6 +233,31 @@ def solveNewtonsLinear(A, L, u_f, M, u_p,
         updateU(u_f)
     print("ERROR: Nonlinear solver failed to converge.")
     raise SystemExit(1)  # the reference calls exit() here (:401-402)
+
+
+def estimateConditionNumber(A, b, u, bfr_tol=None, rtol=1E-8, atol=1E-9, max_it=100000, PC=None):
+    """Extreme singular values from a GMRES(1000) solve (reference common.py:483-507: ``setComputeSingularValues``
+    + ``computeExtremeSingularValues``): the device FGMRES keeps the triangular factor of its Hessenberg matrix,
+    whose singular values are the Hessenberg's; ``u`` receives the solution as in the reference.  ``PC=None`` is
+    PETSc's "none"; 'jacobi' preconditions from the right (A D^-1) where PETSc's GMRES would use D^-1 A.
+    Returns ``(smax, smin)`` like the reference."""
+    if bfr_tol is not None:
+        A, b = trimNodes(A, b=b, bfr_tol=bfr_tol)
+    if PC in (None, 'none'):
+        pc = _iife.PC_NONE
+    elif PC == 'jacobi':
+        pc = _iife.PC_JACOBI
+    else:
+        raise NotImplementedError(f"estimateConditionNumber(PC={PC!r})")
+    dA = _as_device(arg2m(A))
+    uarr = _vec_array(arg2v(u))
+    x = np.ascontiguousarray(uarr, dtype=np.float64).copy()
+    info, R = _iife.ksp_hessenberg(dA, _vec_array(arg2v(b)), x, pc_type=pc, rtol=rtol, atol=atol, max_it=max_it, restart=1000)
+    uarr[:] = x
+    if R.size == 0:
+        return 0.0, 0.0
+    sv = np.linalg.svd(R, compute_uv=False)
+    return float(sv.max()), float(sv.min())
 
 
 def read_exop_triplets(fileNames):

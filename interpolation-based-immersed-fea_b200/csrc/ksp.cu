@@ -873,6 +873,15 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   return rc;
 }
 
+// iife_ksp_solve_hessenberg (row N4: estimateConditionNumber, reference common.py:483-507) asks the FGMRES
+// driver to keep the triangular factor of the last cycle's Hessenberg matrix on the host
+struct HessenbergKeep {
+  bool want = false;
+  int m = 0, k = 0;
+  std::vector<double> H;  // (m+1) x m column-major, rotations applied (upper triangular in its first k columns)
+};
+static HessenbergKeep g_hess;
+
 // ------------------------------------------------------------------------------------------------
 // FGMRES driver (device pointers)
 // ------------------------------------------------------------------------------------------------
@@ -993,6 +1002,13 @@ static int fgmres_solve(Mat *A, Halo *H, const double *dinv, const double *b, do
       }
     }
     if (rc != IIFE_OK) break;
+    if (g_hess.want) {  // the stream is idle here (last poll); F_LOC_IT = inner iterations of this cycle
+      g_hess.m = m;
+      g_hess.k = hf->fl[F_LOC_IT];
+      g_hess.H.resize(hs);
+      cudaError_t he = cudaMemcpy(g_hess.H.data(), gs.H, hs * sizeof(double), cudaMemcpyDeviceToHost);
+      if (he != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "Hessenberg readback: %s", cudaGetErrorString(he)); break; }
+    }
     // build the solution from however many inner iterations were completed in this cycle
     IIFE_LAUNCH(k_gm_solve_y, 1, 32, 0, gs, w.fl);
     IIFE_LAUNCH(k_gm_build_x, g, VEC_THREADS, (size_t)(m + 1) * sizeof(double), x, (double *const *)ztab.p, n, gs, w.fl,
@@ -1113,6 +1129,29 @@ extern "C" int iife_ksp_solve(iife_mat A_, int ksp_type, int pc_type, double rto
   IIFE_NEED_INIT();
   return ksp_solve_common((Mat *)A_, (Halo *)halo, ksp_type, pc_type, rtol, atol, dtol, max_it, restart, b, x, mem, res,
                           hist, hist_len);
+}
+
+extern "C" int iife_ksp_solve_hessenberg(iife_mat A_, int pc_type, double rtol, double atol, double dtol, int64_t max_it,
+                                         int restart, const double *b, double *x, int mem, iife_ksp_result *res,
+                                         double *R, int64_t r_capacity, int64_t *k_out) {
+  IIFE_NEED_INIT();
+  if (!k_out) return set_err(IIFE_ERR_ARG, "k_out is NULL");
+  *k_out = 0;
+  g_hess.want = true;
+  g_hess.k = 0;
+  int rc = ksp_solve_common((Mat *)A_, nullptr, IIFE_KSP_FGMRES, pc_type, rtol, atol, dtol, max_it, restart, b, x, mem, res,
+                            nullptr, 0);
+  g_hess.want = false;
+  if (rc != IIFE_OK) return rc;
+  const int64_t k = g_hess.k;
+  *k_out = k;
+  if (k > 0 && R) {
+    if (r_capacity < k * k) return set_err(IIFE_ERR_ARG, "R holds %lld doubles, %lld needed", (long long)r_capacity, (long long)(k * k));
+    const int m1 = g_hess.m + 1;
+    for (int64_t c = 0; c < k; ++c)
+      for (int64_t i = 0; i < k; ++i) R[c * k + i] = (i <= c) ? g_hess.H[(size_t)c * m1 + (size_t)i] : 0.0;
+  }
+  return IIFE_OK;
 }
 
 extern "C" int iife_ksp_solve_dist(iife_mat A_local, iife_halo H, int ksp_type, int pc_type, double rtol, double atol,

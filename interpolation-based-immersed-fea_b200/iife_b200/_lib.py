@@ -70,6 +70,8 @@ PROTOTYPES = {
     "iife_spmv_dist": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "iife_allreduce_sum": (c_int, [c_vp, c_i64]),
     "iife_alltoallv_bytes": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "iife_ksp_solve_hessenberg": (c_int, [c_vp, c_int, c_dbl, c_dbl, c_dbl, c_i64, c_int, c_vp, c_vp, c_int, P(KspResult),
+                                           c_vp, c_i64, P(c_i64)]),
     "iife_ksp_solve_dist": (c_int, [c_vp, c_vp, c_int, c_int, c_dbl, c_dbl, c_dbl, c_i64, c_int, c_vp, c_vp,
                                     P(KspResult), c_vp, c_i64]),
     "iife_synth_cube_counts": (c_int, [c_i64, c_i64, c_i64, P(c_i64), P(c_i64)]),

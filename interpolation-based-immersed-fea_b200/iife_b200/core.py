@@ -360,6 +360,26 @@ def ksp_solve(A: DeviceMat, b, x, ksp_type=KSP_FGMRES, pc_type=PC_JACOBI, rtol=1
     return KSPInfo(int(res.iterations), int(res.reason), float(res.rnorm), float(res.rnorm0), hist[:hist_len])
 
 
+def ksp_hessenberg(A: DeviceMat, b, x, pc_type=PC_NONE, rtol=1e-8, atol=1e-9, dtol=1e4, max_it=100000, restart=1000):
+    """FGMRES solve (host numpy ``b``/``x``; ``x`` is updated in place) that also returns the triangular factor R
+    (k x k) of the last cycle's Hessenberg matrix: ``np.linalg.svd(R)`` gives the singular values behind the
+    reference's ``estimateConditionNumber`` (common.py:483-507).  Returns (KSPInfo, R)."""
+    n = A.shape[0]
+    if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous and x.shape == (n,)):
+        raise TypeError("x must be a contiguous float64 numpy vector of length n (it is updated in place)")
+    bh = _host_f64(b, n)
+    restart = int(restart) if int(restart) >= 1 else 30  # the library's default
+    m = max(1, min(restart, int(max_it) if max_it > 0 else restart, 10000))
+    R = np.zeros(m * m, dtype=np.float64)
+    k = ctypes.c_int64(0)
+    res = _lib.KspResult()
+    check(lib.iife_ksp_solve_hessenberg(A.handle, int(pc_type), rtol, atol, dtol, int(max_it), int(restart), _ptr(bh)[0],
+                                        _ptr(x)[0], MEM_HOST, ctypes.byref(res), _ptr(R)[0], int(R.size), ctypes.byref(k)))
+    kk = int(k.value)
+    info = KSPInfo(int(res.iterations), int(res.reason), float(res.rnorm), float(res.rnorm0), np.zeros(0))
+    return info, R[:kk * kk].reshape((kk, kk), order="F").copy()
+
+
 def synth_cube(n_bg_cells: int, sigma: float = 1.0, row_begin: int = 0, row_end: int | None = None, b_f=None):
     """Generate the S1 cube operands on the device.  Returns (A_f, M) as DeviceMat; fills ``b_f``
     (device tensor of length row_end-row_begin) if given."""

@@ -271,9 +271,12 @@ int oracle_cg_jacobi(i64 n, const i64 *rp, const i32 *ci, const double *v, const
 }
 
 /* ---- KSPFGMRES(m), right Jacobi, true residual norm, classical Gram-Schmidt ---- */
-int oracle_fgmres_jacobi(i64 n, const i64 *rp, const i32 *ci, const double *v, const double *dinv_in, const double *b,
-                         double *x, double rtol, double atol, double dtol, i64 max_it, int m, i64 *its_out,
-                         double *rnorm_out, double *hist, i64 hist_len) {
+/* R_out (optional, m x m column-major, leading dimension m) receives the triangular factor of the LAST cycle's
+ * Hessenberg matrix and *k_out its order: the rotations are orthogonal, so R has the singular values of the
+ * (k+1) x k Hessenberg that KSPComputeExtremeSingularValues works on (reference common.py:483-507). */
+static int fgmres_impl(i64 n, const i64 *rp, const i32 *ci, const double *v, const double *dinv_in, const double *b,
+                       double *x, double rtol, double atol, double dtol, i64 max_it, int m, i64 *its_out,
+                       double *rnorm_out, double *hist, i64 hist_len, double *R_out, i64 *k_out) {
   if (m < 1) m = 30;
   if (max_it > 0 && (i64)m > max_it) m = (int)max_it;
   double **V = (double **)calloc((size_t)m + 1, sizeof(double *));
@@ -359,6 +362,11 @@ int oracle_fgmres_jacobi(i64 n, const i64 *rp, const i32 *ci, const double *v, c
         else if (its >= max_it) reason = -3;
       }
     }
+    if (R_out && j > 0) {
+      for (int c = 0; c < j; ++c)
+        for (int i = 0; i < j; ++i) R_out[(size_t)c * m + i] = (i <= c) ? H[(size_t)c * m1 + i] : 0.0;
+      if (k_out) *k_out = j;
+    }
     /* x += Z y with H(0:j,0:j) y = rs(0:j) */
     for (int i = j - 1; i >= 0; --i) {
       double s = 0.0;
@@ -378,4 +386,19 @@ int oracle_fgmres_jacobi(i64 n, const i64 *rp, const i32 *ci, const double *v, c
   for (int k = 0; k <= m; ++k) { free(V[k]); free(Z[k]); }
   free(V); free(Z); free(H); free(cs); free(sn); free(rs); free(y); free(hcol);
   return reason;
+}
+
+int oracle_fgmres_jacobi(i64 n, const i64 *rp, const i32 *ci, const double *v, const double *dinv_in, const double *b,
+                         double *x, double rtol, double atol, double dtol, i64 max_it, int m, i64 *its_out,
+                         double *rnorm_out, double *hist, i64 hist_len) {
+  return fgmres_impl(n, rp, ci, v, dinv_in, b, x, rtol, atol, dtol, max_it, m, its_out, rnorm_out, hist, hist_len, NULL,
+                     NULL);
+}
+
+/* caller: m must already be clipped the way fgmres_impl clips it (m >= 1, m <= max_it when max_it > 0) */
+int oracle_fgmres_hessenberg(i64 n, const i64 *rp, const i32 *ci, const double *v, const double *dinv_in,
+                             const double *b, double *x, double rtol, double atol, double dtol, i64 max_it, int m,
+                             i64 *its_out, double *rnorm_out, double *R_out, i64 *k_out) {
+  if (k_out) *k_out = 0;
+  return fgmres_impl(n, rp, ci, v, dinv_in, b, x, rtol, atol, dtol, max_it, m, its_out, rnorm_out, NULL, 0, R_out, k_out);
 }

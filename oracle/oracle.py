@@ -58,6 +58,7 @@ def lib():
         _lib.oracle_max_threads.restype = ctypes.c_int
         _lib.oracle_cg_jacobi.restype = ctypes.c_int
         _lib.oracle_fgmres_jacobi.restype = ctypes.c_int
+        _lib.oracle_fgmres_hessenberg.restype = ctypes.c_int
     return _lib
 
 
@@ -309,3 +310,39 @@ def solve_ksp(A: CSR, b: np.ndarray, x0: np.ndarray | None = None, method: str =
     else:
         raise NotImplementedError(method)
     return KSPResult(x, int(its.value), int(reason), float(rn.value), hist[:hist_len])
+
+
+def estimate_condition_number(A: CSR, b: np.ndarray, x0: np.ndarray | None = None, bfr_tol=None, rtol: float = 1e-8,
+                              atol: float = 1e-9, max_it: int = 100000, PC=None, restart: int = 1000):
+    """estimateConditionNumber (reference common.py:483-507): GMRES(1000) with ``ksp.setComputeSingularValues``,
+    then ``computeExtremeSingularValues`` = extreme singular values of the Hessenberg matrix of the last cycle.
+    PETSc's KSPGMRES and the FGMRES restated here build the same Hessenberg matrix when there is no
+    preconditioner (the reference's default ``PC=None`` -> "none"); with Jacobi this restatement is the
+    right-preconditioned operator A D^-1 (PETSc: left, D^-1 A).  Returns (smax, smin, KSPResult)."""
+    if bfr_tol is not None:
+        A, b, _ = trim_nodes(A, b, bfr_tol=bfr_tol)
+    n = A.n_rows
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(n) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+    if PC == "jacobi":
+        dinv = jacobi_inverse(A)
+        dp = _p(dinv, _c_f64p)
+    elif PC in (None, "none"):
+        dp = ctypes.cast(None, _c_f64p)
+    else:
+        raise NotImplementedError(PC)
+    m = max(1, int(restart))
+    if max_it > 0:
+        m = min(m, int(max_it))
+    R = np.zeros((m, m), dtype=np.float64, order="F")
+    its, k, rn = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_double(0.0)
+    reason = lib().oracle_fgmres_hessenberg(ctypes.c_int64(n), _p(A.rowptr, _c_i64p), _p(A.colind, _c_i32p), _p(A.val, _c_f64p),
+                                            dp, _p(b, _c_f64p), _p(x, _c_f64p), ctypes.c_double(rtol), ctypes.c_double(atol),
+                                            ctypes.c_double(1e4), ctypes.c_int64(max_it), ctypes.c_int(m), ctypes.byref(its),
+                                            ctypes.byref(rn), _p(R, _c_f64p), ctypes.byref(k))
+    kk = int(k.value)
+    res = KSPResult(x, int(its.value), int(reason), float(rn.value), np.zeros(0))
+    if kk == 0:
+        return 0.0, 0.0, res
+    sv = np.linalg.svd(R[:kk, :kk], compute_uv=False)
+    return float(sv.max()), float(sv.min()), res

@@ -529,3 +529,25 @@ def test_trim_nodes_and_newton_through_the_mirror(iife, oracle, capsys):
                                  monitorNewtonConvergence=False, zero_vec=list(ids))
     assert np.linalg.norm(u_p.array + ro.x) <= 1e-6 * np.linalg.norm(ro.x)
     assert np.allclose(u_f.array, oracle.spmv(Mo, u_p.array), rtol=0, atol=1e-10 * np.abs(u_f.array).max())
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("IIFE_TEST_UNVERIFIED"),
+                    reason="written after the round's GPU budget was spent: enable with IIFE_TEST_UNVERIFIED=1")
+def test_condition_estimate_matches_oracle(iife, oracle):
+    """iife_ksp_solve_hessenberg / estimateConditionNumber (reference common.py:483-507) against the oracle."""
+    from InterpolationBasedImmersedFEA import common as api
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, b = assemble_cube(5)
+    C = oracle.AT_R_A(M, A)
+    bb = oracle.AT_x(M, b)
+    smax_o, smin_o, ro = oracle.estimate_condition_number(C, bb)
+    info, R = iife.ksp_hessenberg(dmat(iife, C), bb, np.zeros(C.n_rows))
+    assert info.reason == ro.reason and abs(info.iterations - ro.iterations) <= 1 and R.shape[0] == info.iterations
+    assert np.allclose(np.tril(R, -1), 0.0)
+    sv = np.linalg.svd(R, compute_uv=False)
+    assert abs(sv.max() - smax_o) <= 1e-6 * smax_o and abs(sv.min() - smin_o) <= 1e-4 * smax_o
+    u = api.Vec(np.zeros(C.n_rows))
+    smax, smin = api.estimateConditionNumber(api.CSRMat((C.n_rows, C.n_cols), C.rowptr, C.colind, C.val), api.Vec(bb), u)
+    assert abs(smax - smax_o) <= 1e-6 * smax_o and abs(smin - smin_o) <= 1e-4 * smax_o
+    assert np.linalg.norm(u.array - ro.x) <= 1e-6 * np.linalg.norm(ro.x)

@@ -13,7 +13,8 @@ def test_mirror_exports_reference_names():
     for name in ("v2p m2p arg2v arg2m zero_petsc_vec zero_petsc_mat updateU A_x_b AT_x AT_R_A").split():
         assert callable(getattr(la_utils, name)), name
     for name in ("assembleLinearSystemBackground transferToForeground zeroDofBackground solveKSP readExOp "
-                 "createNonzeroDiagonal removeZeroDiagonal getIdentity trimNodes solveNewtonsLinear").split():
+                 "createNonzeroDiagonal removeZeroDiagonal getIdentity trimNodes solveNewtonsLinear "
+                 "estimateConditionNumber").split():
         assert callable(getattr(common, name)), name
     # star-import like the reference (common.py:8) re-exports la_utils
     assert common.AT_R_A is la_utils.AT_R_A
@@ -26,6 +27,8 @@ def test_mirror_exports_reference_names():
     assert list(inspect.signature(common.solveNewtonsLinear).parameters) == [
         "A", "L", "u_f", "M", "u_p", "maxIters", "relativeTolerance", "monitorNewtonConvergence",
         "moniterLinearConvergence", "linear_method", "linear_preconditioner", "relax_param", "zero_vec"]
+    assert list(inspect.signature(common.estimateConditionNumber).parameters) == ["A", "b", "u", "bfr_tol", "rtol", "atol",
+                                                                                   "max_it", "PC"]
     d = {k: v.default for k, v in sig.parameters.items()}
     assert (d["method"], d["PC"], d["rtol"], d["atol"], d["max_it"], d["gmr_res"]) == ("gmres", "jacobi", 1e-8, 1e-9, 1000000, 3000)
 

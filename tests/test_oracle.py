@@ -295,3 +295,29 @@ def test_row_edits_follow_petsc_semantics(oracle):
     E = oracle.CSR(5, 5, np.zeros(6, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0))
     I5 = oracle.add_diagonal(E, oracle.create_nonzero_diagonal(E))
     assert np.array_equal(I5.todense(), np.eye(5))
+
+
+def test_condition_estimate_from_the_hessenberg(oracle):
+    """estimateConditionNumber (reference common.py:483-507): when GMRES runs through the whole Krylov space the
+    Hessenberg matrix is orthogonally similar to A, so its extreme singular values are A's — up to the loss of
+    orthogonality of classical Gram-Schmidt without refinement (PETSc's default, restated as such: 6e-5 here);
+    after fewer steps they lie inside [smin(A), smax(A)]."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(5)
+    n = 30
+    S = sp.random(n, n, density=0.2, random_state=5, format="csr") + sp.diags(np.linspace(1.0, 9.0, n))
+    S = S.tocsr()
+    S.sort_indices()
+    A = oracle.CSR.from_scipy(S)
+    sv = np.linalg.svd(S.toarray(), compute_uv=False)
+    b = rng.standard_normal(n)
+    smax, smin, res = oracle.estimate_condition_number(A, b, rtol=0.0, atol=0.0, max_it=n)
+    assert res.iterations == n
+    assert abs(smax - sv.max()) <= 1e-3 * sv.max() and abs(smin - sv.min()) <= 1e-3 * sv.max()
+    smax2, smin2, res2 = oracle.estimate_condition_number(A, b, rtol=1e-3, atol=0.0)
+    assert 0 < res2.iterations < n and res2.reason == 2
+    assert sv.min() * (1 - 1e-6) <= smin2 <= smax2 <= sv.max() * (1 + 1e-6)
+    # the solve itself is the ordinary one
+    x = oracle.solve_ksp(A, b, method="gmres", PC=None, rtol=1e-3, atol=0.0, restart=1000)
+    assert x.iterations == res2.iterations and np.array_equal(x.x, res2.x)
