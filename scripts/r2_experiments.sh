@@ -38,6 +38,9 @@ tail -6 gpurun_out/r2_small_default.log gpurun_out/r2_small_persist.log
 # 3b. row N4 (never run on a GPU so far)
 IIFE_TEST_UNVERIFIED=1 timeout 90 python -m pytest tests -q -m gpu --tb=short -k condition_estimate 2>&1 | tail -15 > gpurun_out/r2_tests_n4.log
 tail -1 gpurun_out/r2_tests_n4.log
+# 3c. randomised parity sweep (hypothesis), also never run on a GPU so far
+IIFE_TEST_UNVERIFIED=1 timeout 400 python -m pytest tests/test_gpu_fuzz.py -q -x --tb=short 2>&1 | tail -25 > gpurun_out/r2_tests_fuzz.log
+tail -1 gpurun_out/r2_tests_fuzz.log
 # 4. S2 stress case at a size where the hashing kernels matter
 timeout 200 python scripts/phase_bench_s2.py 96:1 64:2 > gpurun_out/r2_phase_s2.log 2>&1
 cat gpurun_out/r2_phase_s2.log
