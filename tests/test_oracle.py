@@ -321,3 +321,37 @@ def test_condition_estimate_from_the_hessenberg(oracle):
     # the solve itself is the ordinary one
     x = oracle.solve_ksp(A, b, method="gmres", PC=None, rtol=1e-3, atol=0.0, restart=1000)
     assert x.iterations == res2.iterations and np.array_equal(x.x, res2.x)
+
+
+def test_oracle_sweep_against_scipy(oracle):
+    """hypothesis sweep: structural pattern and values of the oracle's triple product, its transpose and its
+    row edits against scipy / dense numpy on irregular shapes (empty rows, heavy rows, stored zeros)."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(seed=st.integers(0, 2 ** 31 - 1), n_f=st.integers(1, 300), n_b=st.integers(1, 120),
+           m_len=st.sampled_from([0.5, 3.0, 12.0]), a_len=st.sampled_from([1.0, 6.0, 30.0]),
+           empty=st.sampled_from([0.0, 0.3, 0.8]))
+    def sweep(seed, n_f, n_b, m_len, a_len, empty):
+        rng = np.random.default_rng(seed)
+        M = _csr(oracle, n_f, n_b, rand_csr(rng, n_f, n_b, m_len, empty_frac=empty))
+        A = _csr(oracle, n_f, n_f, rand_csr(rng, n_f, n_f, a_len, empty_frac=empty / 2))
+        A.val[rng.random(A.nnz) < 0.1] = 0.0  # stored zeros stay in the pattern
+        C = oracle.AT_R_A(M, A)
+        P, V, scale = _scipy_triple(M, A)
+        _assert_matches_scipy(C, P, V, 1e-13 * max(scale, 1e-300))
+        T = oracle.transpose(M)
+        S = M.to_scipy().T.tocsr()
+        S.sort_indices()
+        assert np.array_equal(T.rowptr, S.indptr) and np.array_equal(T.colind, S.indices) and np.array_equal(T.val, S.data)
+        rows = rng.choice(n_f, size=max(1, n_f // 4))
+        Z = oracle.zero_rows(A, rows, 1.0)
+        Zd = A.todense() if n_f <= 60 else None
+        if Zd is not None:
+            Zd[rows] = 0.0
+            Zd[rows, rows] = 1.0
+            assert np.array_equal(Z.todense(), Zd)
+        assert np.all(np.diff(Z.rowptr)[rows] == 1)
+
+    sweep()
