@@ -88,3 +88,41 @@ def test_readexop_semantics_on_shipped_operators():
     assert M2.colind[M2.rowptr[odd - 1]:M2.rowptr[odd]].max() < m
     s2 = np.add.reduceat(M2.val, M2.rowptr[:-1][np.diff(M2.rowptr) > 0])
     assert np.allclose(s2, 1.0, atol=1e-12)
+
+
+def test_vec_is_lazy_about_device_data(monkeypatch):
+    """A vector produced on the GPU stays there until ``.array`` is read; from then on the host copy is the only one
+    (the mirror hands out a mutable numpy array).  The device tensor is faked: this is host logic."""
+    from InterpolationBasedImmersedFEA import la_utils
+
+    class FakeTensor:
+        def __init__(self, a):
+            self.a, self.downloads = np.asarray(a, dtype=np.float64), 0
+
+        def numel(self):
+            return self.a.size
+
+        def cpu(self):
+            self.downloads += 1
+            return self
+
+        def numpy(self):
+            return self.a.copy()
+
+    synced = []
+    monkeypatch.setattr(la_utils._iife, "sync", lambda: synced.append(1))
+    t = FakeTensor([1.0, 2.0, 3.0])
+    v = la_utils.Vec(device=t)
+    assert v.getSize() == 3 and len(v) == 3 and v.getOwnershipRange() == (0, 3) and t.downloads == 0
+    assert v.device_tensor() is t
+    a = v.array
+    assert t.downloads == 1 and synced == [1] and np.array_equal(a, [1.0, 2.0, 3.0])
+    assert v.device_tensor() is None  # the host array may be modified from here on
+    a[0] = 5.0
+    assert v.array[0] == 5.0 and t.downloads == 1
+    v2 = la_utils.Vec(np.zeros(2))
+    assert v2.device_tensor() is None and v2.getSize() == 2
+    v2.array = [1, 2]
+    assert v2.array.dtype == np.float64 and v2.norm() == pytest.approx(np.sqrt(5.0))
+    with pytest.raises(ValueError):
+        la_utils.Vec()
