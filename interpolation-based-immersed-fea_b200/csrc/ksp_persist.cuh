@@ -196,8 +196,10 @@ __device__ __forceinline__ void persist_reduce(const CgPersist &a, const double 
   __syncthreads();  // s_val is reused by the next reduction
 }
 
+// minBlocks = 4 (<= 64 registers): with ptxas' own choice (48 registers, 36 bytes of spills) the slice loop keeps
+// one load in flight instead of U (checked in the SASS; the same thing happened to the dot-fused SELL kernel)
 template <int U>
-__global__ void __launch_bounds__(VEC_THREADS) k_cg_persist(CgPersist a) {
+__global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_persist(CgPersist a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[32];
   __shared__ double s_val[4];

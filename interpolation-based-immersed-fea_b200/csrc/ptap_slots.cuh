@@ -19,6 +19,17 @@
 
 namespace iife {
 
+// Tuning knob (compile time): `make EXTRA_NVCCFLAGS=-DIIFE_SLOT_MINBLOCKS=4` lets ptxas use 64 registers for the
+// slot-plan kernels (its own choice for <4,2> is 48 registers + 24 bytes of spills); unmeasured so far.
+#ifndef IIFE_SLOT_MINBLOCKS
+#define IIFE_SLOT_MINBLOCKS 0
+#endif
+#if IIFE_SLOT_MINBLOCKS > 0
+#define IIFE_SLOT_BOUNDS __launch_bounds__(256, IIFE_SLOT_MINBLOCKS)
+#else
+#define IIFE_SLOT_BOUNDS __launch_bounds__(256)
+#endif
+
 constexpr int PS_BATCH = 4;
 constexpr int SLOT_TAIL_BYTES = 32;  // one lane number per long item of a 32-item chunk
 
@@ -111,7 +122,7 @@ __device__ __forceinline__ void slot_stage(int cnt, int my_beg, int my_len, doub
 }
 
 template <int LG1, int LG2, bool CTAIL>
-__global__ void __launch_bounds__(256) k_ptap_numeric_slots(PtapArgs a, int cap1, int cap2) {
+__global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots(PtapArgs a, int cap1, int cap2) {
   constexpr int NG1 = 32 >> LG1, NG2 = 32 >> LG2;
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;

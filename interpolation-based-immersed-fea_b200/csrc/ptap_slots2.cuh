@@ -97,7 +97,7 @@ __device__ __forceinline__ void slot_stage2(int my_beg, int my_len, double my_w,
 }
 
 template <int LG1, int LG2>
-__global__ void __launch_bounds__(256) k_ptap_numeric_slots2(PtapArgs a, int cap1, int cap2) {
+__global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots2(PtapArgs a, int cap1, int cap2) {
   constexpr int NG1 = 32 >> LG1, NG2 = 32 >> LG2;
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;

@@ -17,6 +17,18 @@ namespace iife {
 
 constexpr int SPMV_THREADS = 256;
 
+// Tuning knob (compile time, unmeasured so far): `make EXTRA_NVCCFLAGS=-DIIFE_SELL_MINBLOCKS=4` gives the SELL kernels
+// 64 registers.  ptxas' own choice (40) leaves the dot-fused variant with one load in flight where the plain one
+// has U (SASS: 3.3 against 6.1 pending load registers on average; 12.5 for both with 64 registers).
+#ifndef IIFE_SELL_MINBLOCKS
+#define IIFE_SELL_MINBLOCKS 0
+#endif
+#if IIFE_SELL_MINBLOCKS > 0
+#define IIFE_SELL_BOUNDS __launch_bounds__(SPMV_THREADS, IIFE_SELL_MINBLOCKS)
+#else
+#define IIFE_SELL_BOUNDS __launch_bounds__(SPMV_THREADS)
+#endif
+
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 
@@ -269,7 +281,7 @@ __global__ void k_sell_compact(const int *__restrict__ sell_ptr, const int *__re
 }
 
 template <bool DOT, int U>
-__global__ void __launch_bounds__(SPMV_THREADS)
+__global__ void IIFE_SELL_BOUNDS
 k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr, const int *__restrict__ sell_col,
             const double *__restrict__ sell_val, int64_t n_rows, int64_t n_slices, const double *__restrict__ x, double *__restrict__ y,
             double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *__restrict__ counter,

@@ -6,7 +6,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libiife.so"))
+# IIFE_LIB selects another build of the same library (tuning variants: `make BUILD=... LIB=../lib/tuned/libiife.so
+# EXTRA_NVCCFLAGS=...`); it must still be called libiife.so
+LIB_PATH = os.path.normpath(os.environ.get("IIFE_LIB") or os.path.join(_HERE, "..", "lib", "libiife.so"))
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

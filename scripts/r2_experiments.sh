@@ -23,6 +23,16 @@ run_bench default IIFE_NOP=1
 IIFE_PTAP_V2=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "$SUB" 2>&1 | tail -5 > gpurun_out/r2_tests_v2.log
 tail -1 gpurun_out/r2_tests_v2.log
 run_bench v2 IIFE_PTAP_V2=1
+# 1b. register-budget variants (scripts/build_variants.sh builds lib/tuned/libiife.so with 64 registers for the SELL and
+#     slot-plan kernels; the .so travels with the snapshot)
+TUNED=$PWD/interpolation-based-immersed-fea_b200/lib/tuned/libiife.so
+if [ -f "$TUNED" ]; then
+  IIFE_LIB=$TUNED timeout 150 python -m pytest tests -q -m gpu --tb=line -k "ptap or spmv or ksp or cube or golden or unfitted" 2>&1 | tail -5 > gpurun_out/r2_tests_tuned.log
+  tail -1 gpurun_out/r2_tests_tuned.log
+  run_bench tuned IIFE_LIB=$TUNED
+  run_bench tuned_fuseddot IIFE_LIB=$TUNED IIFE_SELL_FUSED_DOT=1
+  run_bench tuned_v2 IIFE_LIB=$TUNED IIFE_PTAP_V2=1
+fi
 # 2. SELL path for transposed products
 IIFE_SPMV_SELL_T=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "spmv or cube or golden or end_to_end" 2>&1 | tail -5 > gpurun_out/r2_tests_sellt.log
 tail -1 gpurun_out/r2_tests_sellt.log
