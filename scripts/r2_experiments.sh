@@ -32,6 +32,7 @@ if [ -f "$TUNED" ]; then
   run_bench tuned IIFE_LIB=$TUNED
   run_bench tuned_fuseddot IIFE_LIB=$TUNED IIFE_SELL_FUSED_DOT=1
   run_bench tuned_v2 IIFE_LIB=$TUNED IIFE_PTAP_V2=1
+  run_bench tuned_u8 IIFE_LIB=$TUNED IIFE_SELL_UNROLL=8
 fi
 # 2. SELL path for transposed products
 IIFE_SPMV_SELL_T=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "spmv or cube or golden or end_to_end" 2>&1 | tail -5 > gpurun_out/r2_tests_sellt.log
