@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of the next round: measure the three prepared-but-unmeasured experiments (ROUND_NOTES.md) against
 # the default path in ONE call.  Everything is wrapped in `timeout`; results land in gpurun_out/r2_*.
-# usage (from the repo root):  gpurun --timeout 600 -- 'bash scripts/r2_experiments.sh'
+# usage (from the repo root):  gpurun --timeout 1200 -- 'bash scripts/r2_experiments.sh'   (about 10 minutes)
 mkdir -p gpurun_out
 SUB='ptap or unfitted or cube or golden'
 run_bench() {  # $1 = tag, rest = env assignments
