@@ -832,8 +832,8 @@ extern "C" int iife_spmv(iife_mat A_, int trans, double alpha, const double *x, 
     A = A->T;
     // EXPERIMENTAL, off by default (not yet run on a GPU): M^T has uniform 27-entry rows, so its products
     // (AT_x, reference la_utils.py:143-163) can take the SELL-32 kernel instead of the CSR one (1.05 ms = 0.37 of peak)
-    static const bool sell_t = getenv("IIFE_SPMV_SELL_T") != nullptr;
-    if (sell_t && alpha == 1.0 && beta == 0.0) IIFE_TRY(mat_ensure_sell(A));
+    const char *sell_t = getenv("IIFE_SPMV_SELL_T");  // read per call: scripts/compare_variants.py toggles it
+    if (sell_t && atoi(sell_t) != 0 && alpha == 1.0 && beta == 0.0) IIFE_TRY(mat_ensure_sell(A));
   }
   if (mem == IIFE_MEM_DEVICE) return spmv_launch(A, alpha, x, beta, y);
   Tmp<double> dx, dy;

@@ -18,6 +18,9 @@ except Exception as exc:
     print(f"[{tag}] no bench line: {exc}")
 PY
 }
+# 0. A/B of every experimental kernel against the default one in one process (says which variant is wrong and where)
+timeout 240 python scripts/compare_variants.py > gpurun_out/r2_compare.log 2>&1
+cat gpurun_out/r2_compare.log
 run_bench default IIFE_NOP=1
 # 1. slot-plan kernel v2
 IIFE_PTAP_V2=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "$SUB" 2>&1 | tail -5 > gpurun_out/r2_tests_v2.log
