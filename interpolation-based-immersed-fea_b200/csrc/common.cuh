@@ -104,6 +104,9 @@ struct Mat {
   uint64_t fp = 0;
   bool fp_valid = false;
   int max_row_len = -1;  // lazily computed
+  // identity of the VALUES: uid is unique per matrix object, val_version counts iife_mat_update_values calls
+  // (plans that precompute from an operand's values — ptap_prog.cuh — key on the pair)
+  uint64_t uid = 0, val_version = 0;
   // SELL-32 copy used by the KSP operator (spmv.cu): slices of 32 rows, column-major inside a slice
   int sell_state = 0;  // 0 not tried, 1 built, -1 rejected (padding too large)
   int64_t sell_slices = 0, sell_padded = 0;

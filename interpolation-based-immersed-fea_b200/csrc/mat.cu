@@ -6,7 +6,9 @@
 namespace iife {
 
 int mat_alloc(Mat **out, int64_t n_rows, int64_t n_cols, int64_t nnz) {
+  static uint64_t next_uid = 1;
   Mat *A = new Mat();
+  A->uid = next_uid++;
   A->n_rows = n_rows;
   A->n_cols = n_cols;
   A->nnz = nnz;
@@ -604,6 +606,7 @@ int iife_mat_update_values(iife_mat A_, const double *val, int mem) {
   Mat *A = (Mat *)A_;
   if (!A || !val) return set_err(IIFE_ERR_ARG, "NULL argument");
   IIFE_TRY(copy_in(A->val, val, (size_t)A->nnz * sizeof(double), mem));
+  A->val_version++;
   A->T_vals_valid = false;
   A->dinv_valid = false;
   A->sell_vals_valid = false;

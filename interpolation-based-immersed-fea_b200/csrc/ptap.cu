@@ -19,6 +19,7 @@
 // column lists.  Table sizes come from a ladder of levels; a row whose table overflows at one level
 // is retried at the next, the last level keeps its tables in global memory, so any input works.
 #include "common.cuh"
+#include <algorithm>
 #include <list>
 #include <stdlib.h>
 
@@ -70,6 +71,14 @@ struct Plan {
   double *g_vals = nullptr;
   size_t g_keys_n = 0, g_vals_n = 0;
   int *err_flag = nullptr;
+  // v3 stage-2 gather program of the small-row bin (ptap_prog.cuh, experimental)
+  int pg_state = 0;  // 0 not built, 1 built, -1 not possible (memory)
+  int64_t pg_rows = 0, pg_total_steps = 0;
+  int *pg_steps = nullptr;
+  long long *pg_off = nullptr;
+  unsigned char *pg_lane_out = nullptr, *pg_maxg = nullptr, *pg_slot = nullptr;
+  double *pg_val = nullptr;
+  uint64_t pg_m_uid = 0, pg_m_version = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -538,6 +547,7 @@ __global__ void k_ptap_numeric(PtapArgs a) {
 #include "ptap_warp.cuh"
 #include "ptap_slots.cuh"
 #include "ptap_slots2.cuh"
+#include "ptap_prog.cuh"
 namespace iife {
 
 // ------------------------------------------------------------------------------------------------
@@ -724,6 +734,12 @@ static int plan_free(Plan *P) {
   if (P->mt_alen) dev_free_t(P->mt_alen, (size_t)P->nnzR);
   if (P->inter_mbeg) dev_free_t(P->inter_mbeg, (size_t)P->inter_total);
   if (P->inter_mlen) dev_free_t(P->inter_mlen, (size_t)P->inter_total);
+  if (P->pg_steps) dev_free_t(P->pg_steps, (size_t)P->pg_rows);
+  if (P->pg_off) dev_free_t(P->pg_off, (size_t)P->pg_rows + 1);
+  if (P->pg_lane_out) dev_free_t(P->pg_lane_out, (size_t)P->pg_rows * 32);
+  if (P->pg_maxg) dev_free_t(P->pg_maxg, (size_t)P->pg_rows);
+  if (P->pg_slot) dev_free_t(P->pg_slot, (size_t)P->pg_total_steps * 32);
+  if (P->pg_val) dev_free_t(P->pg_val, (size_t)P->pg_total_steps * 32);
   delete P;
   return IIFE_OK;
 }
@@ -1073,6 +1089,51 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
 
 int gather_vals_launch(const double *val, const int *perm, double *out, int64_t nnz);  // mat.cu
 
+// Builds (or refreshes, when the values of M changed) the stage-2 gather program of the small-row bin.
+// `a` carries the operands, the plan arrays and the bin's row list.  pg_state stays -1 when it does not fit.
+static int prog_ensure(Plan *P, const Mat *M, PtapArgs a) {
+  Ctx &c = ctx();
+  if (P->pg_state == -1) return IIFE_OK;
+  if (P->pg_state == 1 && P->pg_m_uid == M->uid && P->pg_m_version == M->val_version) return IIFE_OK;
+  const int64_t n = a.n_rows;
+  const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)c.sm_count * 8);
+  ProgArgs pg{};
+  if (P->pg_state == 0) {
+    P->pg_rows = n;
+    IIFE_TRY(dev_alloc_t(&P->pg_steps, (size_t)n));
+    IIFE_TRY(dev_alloc_t(&P->pg_off, (size_t)n + 1));
+    pg.steps = P->pg_steps;
+    IIFE_LAUNCH(k_prog_build<false>, grid, 256, 0, a, pg);
+    IIFE_CHECK_LAUNCH();
+    int64_t total = 0;
+    IIFE_TRY(exclusive_scan_i32_i64(P->pg_steps, P->pg_off, n, &total));
+    size_t free_b = 0, total_b = 0;
+    IIFE_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if ((size_t)total * 32 * 9 + ((size_t)n * 33) > free_b / 2) {
+      P->pg_state = -1;  // keep the scatter kernels
+      return IIFE_OK;
+    }
+    P->pg_total_steps = total;
+    IIFE_TRY(dev_alloc_t(&P->pg_slot, (size_t)total * 32));
+    IIFE_TRY(dev_alloc_t(&P->pg_val, (size_t)total * 32));
+    IIFE_TRY(dev_alloc_t(&P->pg_lane_out, (size_t)n * 32));
+    IIFE_TRY(dev_alloc_t(&P->pg_maxg, (size_t)n));
+  }
+  pg.steps = P->pg_steps;
+  pg.off = P->pg_off;
+  pg.lane_out = P->pg_lane_out;
+  pg.maxg = P->pg_maxg;
+  pg.slot = P->pg_slot;
+  pg.val = P->pg_val;
+  IIFE_CUDA(cudaMemsetAsync(P->pg_slot, 0xFF, (size_t)(P->pg_total_steps ? P->pg_total_steps * 32 : 1), c.stream));
+  IIFE_LAUNCH(k_prog_build<true>, grid, 256, 0, a, pg);
+  IIFE_CHECK_LAUNCH();
+  P->pg_m_uid = M->uid;
+  P->pg_m_version = M->val_version;
+  P->pg_state = 1;
+  return IIFE_OK;
+}
+
 static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
   Ctx &c = ctx();
   if (M->n_rows != P->n_k || M->n_cols != P->n_ccols || M->nnz != P->nnzM || A->n_rows != P->n_f || A->nnz != P->nnzA)
@@ -1134,6 +1195,40 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
       if (const char *et = getenv("IIFE_PTAP_CTAIL")) ctail = atoi(et) != 0;
       bool v2 = false;  // experimental kernel of ptap_slots2.cuh (not yet validated on a GPU)
       if (const char *e2k = getenv("IIFE_PTAP_V2")) v2 = atoi(e2k) != 0;
+      if (sb == 0) {  // experimental stage-2 gather program (ptap_prog.cuh): small-row bin only
+        const char *e3 = getenv("IIFE_PTAP_V3");
+        if (e3 && atoi(e3) != 0 && SLOT_CAP2[0] <= 32 && SLOT_CAP1[0] < PROG_IDLE) {
+          if ((rc = prog_ensure(P, M, a)) != IIFE_OK) break;
+          prog_kernel_t pk = P->pg_state == 1 ? pick_prog_kernel(lg1) : nullptr;
+          if (pk) {
+            ProgArgs pg{};
+            pg.steps = P->pg_steps;
+            pg.off = P->pg_off;
+            pg.lane_out = P->pg_lane_out;
+            pg.maxg = P->pg_maxg;
+            pg.slot = P->pg_slot;
+            pg.val = P->pg_val;
+            const int cap1p = SLOT_CAP1[0];
+            int wpcp = 8;
+            const size_t smemp = prog_per_warp_bytes(lg1, cap1p) * wpcp;
+            if (smemp > 48 * 1024) {
+              cudaError_t e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp);
+              if (e != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e)); break; }
+            }
+            int per_smp = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_smp, pk, wpcp * 32, smemp) != cudaSuccess || per_smp < 1) {
+              cudaGetLastError();
+              per_smp = 1;
+            }
+            int64_t ctasp = std::min<int64_t>((cnt + wpcp - 1) / wpcp, (int64_t)c.sm_count * per_smp);
+            pk<<<(int)ctasp, wpcp * 32, smemp, c.stream>>>(a, pg, cap1p);
+            c.launches++;
+            cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) { rc = set_err(IIFE_ERR_CUDA, "program kernel launch: %s", cudaGetErrorString(le)); break; }
+            continue;
+          }
+        }
+      }
       slot_kernel_t kern = v2 ? pick_slot2_kernel(lg1, lg2) : pick_slot_kernel(lg1, lg2, ctail);
       if (!kern) { rc = set_err(IIFE_ERR_ARG, "no slot kernel for group sizes 2^%d / 2^%d", lg1, lg2); break; }
       int cap1 = SLOT_CAP1[sb], cap2 = SLOT_CAP2[sb];

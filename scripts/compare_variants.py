@@ -2,6 +2,7 @@
 variables read at call time), so that one GPU call tells which variant is wrong and where.  Development aid.
 
   IIFE_PTAP_V2=1      slot-plan numeric kernel v2           -> values of A_b against the default kernel, per bin
+  IIFE_PTAP_V3=1      stage 2 as a gather program (small-row bin)
   IIFE_PTAP_CTAIL=0   default kernel without the compacted second pass
   IIFE_SPMV_SELL_T=1  SELL path for M^T x                  -> against the CSR path
   IIFE_KSP_PERSIST=1  persistent cooperative CG            -> iterations / reason / history / solution
@@ -63,7 +64,8 @@ for name, g in cases(sys.argv[1:] or ["8", "23", "46"]):
     C0 = plan.numeric(M, A)
     rp, ci, v0 = C0.to_csr(np.int64)
     row_of = np.repeat(np.arange(n_b), np.diff(rp))
-    for tag, kw in (("PTAP_V2", dict(IIFE_PTAP_V2=1)), ("PTAP_CTAIL=0", dict(IIFE_PTAP_CTAIL=0))):
+    for tag, kw in (("PTAP_V2", dict(IIFE_PTAP_V2=1)), ("PTAP_V3", dict(IIFE_PTAP_V3=1)),
+                    ("PTAP_V3 again (program cached)", dict(IIFE_PTAP_V3=1)), ("PTAP_CTAIL=0", dict(IIFE_PTAP_CTAIL=0))):
         with env(**kw):
             try:
                 v = plan.numeric(M, A, check_errors=True).values()

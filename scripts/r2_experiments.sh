@@ -26,6 +26,10 @@ run_bench default IIFE_NOP=1
 IIFE_PTAP_V2=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "$SUB" 2>&1 | tail -5 > gpurun_out/r2_tests_v2.log
 tail -1 gpurun_out/r2_tests_v2.log
 run_bench v2 IIFE_PTAP_V2=1
+# 1a. stage 2 as a gather program
+IIFE_PTAP_V3=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "$SUB" 2>&1 | tail -5 > gpurun_out/r2_tests_v3.log
+tail -1 gpurun_out/r2_tests_v3.log
+run_bench v3 IIFE_PTAP_V3=1
 # 1b. register-budget variants (scripts/build_variants.sh builds lib/tuned/libiife.so with 64 registers for the SELL and
 #     slot-plan kernels; the .so travels with the snapshot)
 TUNED=$PWD/interpolation-based-immersed-fea_b200/lib/tuned/libiife.so
@@ -35,6 +39,7 @@ if [ -f "$TUNED" ]; then
   run_bench tuned IIFE_LIB=$TUNED
   run_bench tuned_fuseddot IIFE_LIB=$TUNED IIFE_SELL_FUSED_DOT=1
   run_bench tuned_v2 IIFE_LIB=$TUNED IIFE_PTAP_V2=1
+  run_bench tuned_v3 IIFE_LIB=$TUNED IIFE_PTAP_V3=1
   run_bench tuned_u8 IIFE_LIB=$TUNED IIFE_SELL_UNROLL=8
 fi
 # 2. SELL path for transposed products
