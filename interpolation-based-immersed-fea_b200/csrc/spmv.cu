@@ -72,6 +72,57 @@ k_spmv(const int *__restrict__ rowptr, const int *__restrict__ colind, const dou
   }
 }
 
+// EXPERIMENTAL (IIFE_SPMV_ILP=1, off by default, not yet run on a GPU): y = A x for operators with very short rows
+// (the extraction operator M: 1-8 entries per row).  k_spmv keeps one row per lane group in flight, and a row is a
+// chain of three dependent loads (row pointer -> column -> x): measured 0.45 of the copy peak on M.  Here a lane
+// group walks TWO rows at a time with their loads interleaved, which doubles the bytes in flight per SM.
+template <int LPR>
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv_ilp2(const int *__restrict__ rowptr, const int *__restrict__ colind, const double *__restrict__ val,
+            int64_t n_rows, const double *__restrict__ x, double *__restrict__ y) {
+  constexpr int RPB = SPMV_THREADS / LPR;
+  const int lg = threadIdx.x % LPR;
+  const int64_t row0 = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR;
+  const int64_t stride = (int64_t)gridDim.x * RPB;
+  const int64_t n_iter = (n_rows + 2 * stride - 1) / (2 * stride);  // uniform trip count: shuffles use the full mask
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t i0 = row0 + 2 * it * stride, i1 = i0 + stride;
+    int b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+    if (i0 < n_rows) {
+      b0 = __ldg(rowptr + i0);
+      e0 = __ldg(rowptr + i0 + 1);
+    }
+    if (i1 < n_rows) {
+      b1 = __ldg(rowptr + i1);
+      e1 = __ldg(rowptr + i1 + 1);
+    }
+    double s0 = 0.0, s1 = 0.0;
+    int p0 = b0 + lg, p1 = b1 + lg;
+    while (__any_sync(0xffffffffu, p0 < e0 || p1 < e1)) {
+      int c0 = 0, c1 = 0;
+      double v0 = 0.0, v1 = 0.0;
+      if (p0 < e0) {
+        c0 = ld_stream(colind + p0);
+        v0 = ld_stream(val + p0);
+      }
+      if (p1 < e1) {
+        c1 = ld_stream(colind + p1);
+        v1 = ld_stream(val + p1);
+      }
+      if (p0 < e0) s0 = fma(v0, __ldg(x + c0), s0);
+      if (p1 < e1) s1 = fma(v1, __ldg(x + c1), s1);
+      p0 += LPR;
+      p1 += LPR;
+    }
+    s0 = group_sum<LPR>(s0);
+    s1 = group_sum<LPR>(s1);
+    if (lg == 0) {
+      if (i0 < n_rows) y[i0] = s0;
+      if (i1 < n_rows) y[i1] = s1;
+    }
+  }
+}
+
 // w = A p, dot = (p, w).  Rows of A index p as well (A square on the local row block).
 template <int LPR>
 __global__ void __launch_bounds__(SPMV_THREADS)
@@ -765,6 +816,17 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
   int lpr = spmv_pick_lpr(A);
   int g = spmv_grid(A->n_rows, lpr);
   bool plain = (alpha == 1.0 && beta == 0.0);
+  if (plain && lpr <= 8) {
+    const char *ilp = getenv("IIFE_SPMV_ILP");  // experimental two-rows-in-flight kernel for short rows
+    if (ilp && atoi(ilp) != 0) {
+      int g2 = spmv_grid((A->n_rows + 1) / 2, lpr);
+      if (lpr == 2) IIFE_LAUNCH((k_spmv_ilp2<2>), g2, SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, x, y);
+      else if (lpr == 4) IIFE_LAUNCH((k_spmv_ilp2<4>), g2, SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, x, y);
+      else IIFE_LAUNCH((k_spmv_ilp2<8>), g2, SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, x, y);
+      IIFE_CHECK_LAUNCH();
+      return IIFE_OK;
+    }
+  }
 #define SPMV_CASE(L)                                                                                              \
   case L:                                                                                                         \
     if (plain) IIFE_LAUNCH((k_spmv<L, true>), g, SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, alpha, x, beta, y); \

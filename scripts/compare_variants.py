@@ -5,6 +5,7 @@ variables read at call time), so that one GPU call tells which variant is wrong 
   IIFE_PTAP_V3=1      stage 2 as a gather program (small-row bin)
   IIFE_PTAP_CTAIL=0   default kernel without the compacted second pass
   IIFE_SPMV_SELL_T=1  SELL path for M^T x                  -> against the CSR path
+  IIFE_SPMV_ILP=1     two rows in flight per lane group for short rows (M x)  -> against k_spmv
   IIFE_KSP_PERSIST=1  persistent cooperative CG            -> iterations / reason / history / solution
 
 usage: python scripts/compare_variants.py [N_b ...]      (default 8 23 46; plus the S2 cases 20:1 and 14:2)"""
@@ -82,6 +83,13 @@ for name, g in cases(sys.argv[1:] or ["8", "23", "46"]):
             report("SPMV_SELL_T", bb0, M.spmv(b_f, trans=True))
         except Exception as exc:
             print(f"  SPMV_SELL_T: FAILED {exc}", flush=True)
+    xb = np.linspace(-1.0, 1.0, n_b)
+    uf0 = M.spmv(xb)
+    with env(IIFE_SPMV_ILP=1):
+        try:
+            report("SPMV_ILP (M x)", uf0, M.spmv(xb))
+        except Exception as exc:
+            print(f"  SPMV_ILP: FAILED {exc}", flush=True)
     for kt, kname in ((I.KSP_CG, "cg"),):
         x0 = np.zeros(n_b)
         i0 = I.ksp_solve(C0, bb0, x0, kt, I.PC_JACOBI, hist_len=4000)

@@ -47,6 +47,8 @@ IIFE_SPMV_SELL_T=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "sp
 tail -1 gpurun_out/r2_tests_sellt.log
 IIFE_SPMV_SELL_T=1 SKIP_FGMRES=1 timeout 120 python scripts/phase_bench.py 184 2>&1 | grep -E "spmvT|spmv\(M\)" > gpurun_out/r2_phase_sellt.log
 cat gpurun_out/r2_phase_sellt.log
+IIFE_SPMV_ILP=1 SKIP_FGMRES=1 timeout 120 python scripts/phase_bench.py 184 2>&1 | grep -E "spmv\(M\)" > gpurun_out/r2_phase_ilp.log
+cat gpurun_out/r2_phase_ilp.log
 # 3. persistent cooperative CG, single GPU (never leave a hung kernel behind: short timeouts)
 IIFE_KSP_PERSIST=1 timeout 120 python -m pytest tests -q -m gpu --tb=line -k "ksp or golden or cube or unfitted or end_to_end" 2>&1 | tail -5 > gpurun_out/r2_tests_persist.log
 tail -1 gpurun_out/r2_tests_persist.log
