@@ -1,5 +1,5 @@
 #!/bin/bash
-# First GPU call of the next round: measure the three prepared-but-unmeasured experiments (ROUND_NOTES.md) against
+# First GPU call of the next round: measure the prepared-but-unmeasured experiments (ROUND_NOTES.md) against
 # the default path in ONE call.  Everything is wrapped in `timeout`; results land in gpurun_out/r2_*.
 # usage (from the repo root):  gpurun --timeout 1200 -- 'bash scripts/r2_experiments.sh'   (about 10 minutes)
 mkdir -p gpurun_out
