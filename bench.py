@@ -43,12 +43,21 @@ def measured_peak():
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # --------------------------------------------------------------------------------------------------
+def host_threads():
+    """Hardware threads this process may use.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1, which
+    made the round-1 CPU arm single-threaded at N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def pick_threads(O, C, x):
     """Fastest OpenMP thread count for the SpMV on this host (vCPU counts over-promise on shared boxes)."""
     best, best_t = 1, float("inf")
-    n = O.max_threads()
-    cand = sorted({1, 2, 4, 8, 16, 32, 64, n, max(1, n // 2)})
-    for th in [c for c in cand if c <= n]:
+    n = host_threads()
+    cand = sorted({max(1, n // 4), max(1, n // 2), n})
+    for th in cand:
         O.set_threads(th)
         O.spmv(C, x)
         t0 = time.perf_counter()
@@ -62,6 +71,7 @@ def pick_threads(O, C, x):
 
 
 def cpu_step(O, M, A, b_f, method="cg"):
+    """The reference's call sequence (la_utils.py:165-182, :143-163, common.py:554-574) on the oracle port."""
     C = O.AT_R_A(M, A)
     bb = O.AT_x(M, b_f)
     r = O.solve_ksp(C, bb, method=method, PC="jacobi", rtol=1e-8, atol=1e-9)
@@ -69,43 +79,67 @@ def cpu_step(O, M, A, b_f, method="cg"):
 
 
 def cpu_operands(n_cells):
-    from iife_b200 import synthetic
+    """S1 cube operands from the oracle's own threaded generator: nothing of the product is imported."""
     from oracle import oracle as O
+    from oracle import synthetic_cube
 
-    g = synthetic.cube_operators(n_cells)
-    A = O.CSR(g["n_f"], g["n_f"], *g["A"])
-    M = O.CSR(g["n_f"], g["n_b"], *g["M"])
-    return O, A, M, g["b_f"], g
+    O.set_threads(host_threads())
+    A, M, b_f = synthetic_cube.cube_operators_fast(n_cells)
+    return O, A, M, b_f, {"n_f": A.n_rows, "n_b": M.n_cols}
 
 
 def run_reference(args):
-    """`--impl reference`: PETSc is not installable here, so the reference arm is the
-    oracle port of the reference's own call sequence on all usable host threads, on a bounded sample."""
+    """`--impl reference`: PETSc is not installable here, so the reference arm is the oracle port
+    of the reference's own call sequence on all usable host threads, on the SAME workload as our arm (--cells,
+    default N_b = 184).  The number of timed steps is bounded by a wall-clock budget (IIFE_REF_BUDGET_S, 240 s):
+    `steps_timed` in the line says how many of the requested steps were run; ms_per_step is their mean."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    total_steps = args.steps + args.warmup
-    n_cells = args.cpu_cells or (92 if total_steps <= 8 else (64 if total_steps <= 30 else 46))
-    O, A, M, b_f, g = cpu_operands(n_cells)
-    C, bb, r = cpu_step(O, M, A, b_f)
-    threads = pick_threads(O, C, np.ones(C.n_rows))
-    for _ in range(max(args.warmup - 1, 0)):
-        cpu_step(O, M, A, b_f)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    budget = float(os.environ.get("IIFE_REF_BUDGET_S", "240"))
+    t_start = time.perf_counter()
+    n_cells = args.cpu_cells or args.cells
+    fallback = None
+    try:
+        O, A, M, b_f, g = cpu_operands(n_cells)
+        C, bb, r = cpu_step(O, M, A, b_f)  # warm-up step 1 (also the operands of the thread-count probe)
+    except MemoryError as exc:
+        fallback = f"MemoryError at N_b={n_cells} ({exc}); fell back to N_b=92"
+        n_cells = 92
+        O, A, M, b_f, g = cpu_operands(n_cells)
         C, bb, r = cpu_step(O, M, A, b_f)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    threads = pick_threads(O, C, np.ones(C.n_rows))
+    t0 = time.perf_counter()
+    cpu_step(O, M, A, b_f)  # warm-up step 2, timed to size the rest
+    t_one = time.perf_counter() - t0
+    left = budget - (time.perf_counter() - t_start)
+    n_warm = 2
+    while n_warm < args.warmup and left > (args.steps + 1) * t_one:  # further warm-up only if all steps still fit
+        cpu_step(O, M, A, b_f)
+        n_warm += 1
+        left = budget - (time.perf_counter() - t_start)
+    n_timed = int(max(1, min(args.steps, left // max(t_one, 1e-9))))
+    t0 = time.perf_counter()
+    for _ in range(n_timed):
+        C, bb, r = cpu_step(O, M, A, b_f)
+    dt = (time.perf_counter() - t0) / n_timed
     val = g["n_f"] / dt / 1e6
-    sample = f"synthetic S1 cube N_b={n_cells} (n_f={g['n_f']}, nnz(A_f)={A.nnz}), {r.iterations} CG iterations per step"
+    sample = (f"synthetic S1 cube N_b={n_cells} (n_f={g['n_f']}, nnz(A_f)={A.nnz}), {r.iterations} CG iterations per step, "
+              f"{n_timed} of {args.steps} steps timed after {n_warm} warm-up steps, {dt:.2f} s/step")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"S1 fitted cube, bounded CPU sample N_b={n_cells}", "n_f": g["n_f"], "n_b": g["n_b"],
-                   "ksp": "cg+jacobi rtol=1e-8 atol=1e-9", "note": "CPU restatement (oracle port), not PETSc"},
+        "config": {"workload": f"BASELINE config 5: synthetic S1 fitted cube N_b={n_cells}", "n_f": g["n_f"], "n_b": g["n_b"],
+                   "nnz_A_f": A.nnz, "nnz_M": M.nnz, "nnz_A_b": C.nnz,
+                   "ksp": "cg+jacobi rtol=1e-8 atol=1e-9 zero guess", "cg_iterations": r.iterations,
+                   "steps_timed": n_timed, "warmup_run": n_warm, "host_threads": host_threads(),
+                   "note": "CPU restatement (oracle port) of la_utils.AT_R_A + AT_x + solveKSP(cg, jacobi), not PETSc"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if fallback:
+        line["config"]["fallback"] = fallback
     print(json.dumps(line))
 
 
@@ -418,13 +452,13 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu:
         try:
-            n_cpu = args.cpu_cells or 64
+            n_cpu = args.cpu_cells or 92
             O, Ac, Mc, bfc, g = cpu_operands(n_cpu)
             Cc, bbc, rc = cpu_step(O, Mc, Ac, bfc)
             threads = pick_threads(O, Cc, np.ones(Cc.n_rows))
             t0 = time.perf_counter()
             reps = 0
-            while reps < 3 and (time.perf_counter() - t0) < 20.0:
+            while reps < 8 and (time.perf_counter() - t0) < 20.0:
                 Cc, bbc, rc = cpu_step(O, Mc, Ac, bfc)
                 reps += 1
             dt = (time.perf_counter() - t0) / reps

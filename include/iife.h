@@ -113,8 +113,11 @@ int iife_mat_update_values(iife_mat A, const double *val, int mem);
 int iife_mat_get_info(iife_mat A, int64_t *n_rows, int64_t *n_cols, int64_t *nnz);
 /* copy out; any of rowptr / colind / val may be NULL */
 int iife_mat_get_csr(iife_mat A, void *rowptr, void *colind, double *val, int idx_bytes, int mem);
-/* raw device pointers (int32 rowptr[n_rows+1], int32 colind[nnz], double val[nnz]); valid until destroy */
+/* raw device pointers (int32 rowptr[n_rows+1], int32 colind[nnz], double val[nnz]); valid until destroy.
+ * A caller that WRITES values through `val` must call iife_mat_touch afterwards: plans and operator copies that
+ * were precomputed from the old values (transpose, SELL copy, Jacobi diagonal, PtAP templates) key on it. */
 int iife_mat_device_ptrs(iife_mat A, void **rowptr, void **colind, void **val);
+int iife_mat_touch(iife_mat A);
 /* 64-bit fingerprint of (shape, rowptr, colind): the key of the symbolic-plan cache */
 int iife_mat_fingerprint(iife_mat A, uint64_t *fp);
 /* explicit transpose as a new matrix, rows column-sorted (MatTranspose, la_utils.py:178) */
@@ -147,6 +150,20 @@ int iife_plan_get_info(iife_plan P, int64_t *n_b, int64_t *nnz_c, int64_t *nnz_i
  * 8K/4K, [4] CTA hashing with global-memory tables, [5] slot plan 128/32, [6] slot plan 256/256 (tests use it to
  * prove that every kernel of the ladder is exercised) */
 int iife_plan_bin_counts(iife_plan P, int64_t *counts7);
+/* template plan of the numeric phase (built on the first numeric call, rebuilt when the values of M change):
+ * rows of the slot-plan bins that share structure and M values with at least IIFE_TPL_MIN_ROWS (32) others run one
+ * precompiled gather program per group.  n_templates groups cover n_rows rows in n_chunks work items;
+ * lane_use2[0..1] = mean fraction of busy lanes in the two gather stages.  All zero before the first numeric call. */
+int iife_plan_tpl_info(iife_plan P, int64_t *n_templates, int64_t *n_rows, int64_t *n_chunks, double *lane_use2);
+/* host-only self-check hook of the template compiler (no device needed): compiles the gather program of one output
+ * row given as raw description — len1[n0] operand row lengths of A_f, w[n0] = R[i,:], slot1 = destination of every
+ * stage-1 term, len2[n1] lengths of the M rows, mval / slot2 per stage-2 term — and interprets it on the CPU with
+ * a_vals = the operand rows of A_f back to back; c_out[n2] receives the output row.  info10: S1, S2, extra slots of
+ * both stages, staging steps, program bytes, lane use x1000 of both stages, shared-memory conflict degree x1000 of
+ * the gather reads of both stages (1000 = conflict free). */
+int iife_tpl_emulate_row(int n0, const int *len1, const double *w, const unsigned char *slot1, int n1, const int *len2,
+                         const double *mval, const unsigned char *slot2, int n2, const double *a_vals, double *c_out,
+                         int *info10);
 /* numeric phase; *C == NULL creates the result matrix, otherwise refills its values (reuse) */
 int iife_ptap_numeric(iife_plan P, iife_mat M, iife_mat A, iife_mat *C);
 /* general triple product C = R A P with an explicit restriction R (n_out x nJ), A (nJ x nK), P (nK x n_cols):

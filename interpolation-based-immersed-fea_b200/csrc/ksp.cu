@@ -95,6 +95,7 @@ __device__ __forceinline__ bool grid_reduce(double (&acc)[NR], double *partials,
 __device__ __forceinline__ void cg_init_scalars(double *sc, int *fl, double zz, double zr, double zbzb, double *hist,
                                                 long long hist_len) {
   double dp = sqrt(zz), beta = zr, rho0 = sqrt(zbzb);
+  if (rho0 == 0.0) rho0 = dp;  // KSPConvergedDefault: zero right-hand side with a nonzero guess -> initial residual norm
   sc[S_DP] = dp;
   sc[S_BETA] = beta;
   sc[S_BETA_OLD] = beta;
@@ -282,6 +283,7 @@ __device__ __forceinline__ void gm_cycle_scalars(double *sc, int *fl, GmresSmall
   double res = sqrt(vv);
   if (first_cycle) {
     double rho0 = sqrt(bb2);
+    if (rho0 == 0.0) rho0 = res;  // KSPConvergedDefault: zero right-hand side with a nonzero guess
     sc[S_RHO0] = rho0;
     sc[S_TTOL] = fmax(sc[S_RTOL] * rho0, sc[S_ATOL]);
     fl[F_ITS] = 0;

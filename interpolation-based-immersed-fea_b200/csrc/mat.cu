@@ -644,6 +644,17 @@ int iife_mat_device_ptrs(iife_mat A_, void **rowptr, void **colind, void **val) 
   return IIFE_OK;
 }
 
+// values were written through the raw pointer of iife_mat_device_ptrs: drop everything cached from the old ones
+int iife_mat_touch(iife_mat A_) {
+  Mat *A = (Mat *)A_;
+  if (!A) return set_err(IIFE_ERR_ARG, "NULL matrix");
+  A->val_version++;
+  A->T_vals_valid = false;
+  A->dinv_valid = false;
+  A->sell_vals_valid = false;
+  return IIFE_OK;
+}
+
 int iife_mat_fingerprint(iife_mat A_, uint64_t *fp) {
   IIFE_NEED_INIT();
   Mat *A = (Mat *)A_;

@@ -79,6 +79,18 @@ struct Plan {
   unsigned char *pg_lane_out = nullptr, *pg_maxg = nullptr, *pg_slot = nullptr;
   double *pg_val = nullptr;
   uint64_t pg_m_uid = 0, pg_m_version = 0;
+  // template plan (ptap_tpl.cuh): rows of the slot-plan bins whose structure AND M / R values are shared by many
+  // rows run a precompiled gather program; the others ("rest") stay on the per-row kernels
+  int tp_state = 0;  // 0 not built, 1 built (possibly with no template)
+  uint64_t tp_m_uid = 0, tp_m_version = 0, tp_r_uid = 0, tp_r_version = 0;
+  int tp_n_tpl = 0, tp_n_chunks = 0, tp_chunk_rows = 0;
+  int64_t tp_n_rows = 0, tp_list_n = 0, tp_rest5 = 0, tp_rest6 = 0;
+  unsigned char *tp_blobs = nullptr;
+  size_t tp_blob_bytes = 0;
+  long long *tp_blob_off = nullptr;
+  int *tp_chunks = nullptr, *tp_rows = nullptr, *tp_rest_rows = nullptr;
+  int tp_s_cap = 0, tp_o1_cap = 0, tp_o2_cap = 0;
+  double tp_use1 = 0.0, tp_use2 = 0.0;  // mean lane use of the two gather stages, weighted by rows
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -548,6 +560,7 @@ __global__ void k_ptap_numeric(PtapArgs a) {
 #include "ptap_slots.cuh"
 #include "ptap_slots2.cuh"
 #include "ptap_prog.cuh"
+#include "ptap_tpl.cuh"
 namespace iife {
 
 // ------------------------------------------------------------------------------------------------
@@ -713,6 +726,36 @@ static int mean_nonempty_logG(const Mat *X, int *logG) {
 
 int transpose_build(const Mat *A, Mat **T_out, int **perm_out);  // mat.cu
 
+static void pg_free(Plan *P) {
+  if (P->pg_steps) dev_free_t(P->pg_steps, (size_t)P->pg_rows);
+  if (P->pg_off) dev_free_t(P->pg_off, (size_t)P->pg_rows + 1);
+  if (P->pg_lane_out) dev_free_t(P->pg_lane_out, (size_t)P->pg_rows * 32);
+  if (P->pg_maxg) dev_free_t(P->pg_maxg, (size_t)P->pg_rows);
+  if (P->pg_slot) dev_free_t(P->pg_slot, (size_t)P->pg_total_steps * 32);
+  if (P->pg_val) dev_free_t(P->pg_val, (size_t)P->pg_total_steps * 32);
+  P->pg_steps = nullptr;
+  P->pg_off = nullptr;
+  P->pg_lane_out = P->pg_maxg = P->pg_slot = nullptr;
+  P->pg_val = nullptr;
+  P->pg_rows = P->pg_total_steps = 0;
+  P->pg_state = 0;
+}
+
+static void tpl_free(Plan *P) {
+  if (P->tp_blobs) dev_free_t(P->tp_blobs, P->tp_blob_bytes);
+  if (P->tp_blob_off) dev_free_t(P->tp_blob_off, (size_t)P->tp_n_tpl);
+  if (P->tp_chunks) dev_free_t(P->tp_chunks, (size_t)P->tp_n_chunks * 3);
+  if (P->tp_rows) dev_free_t(P->tp_rows, (size_t)P->tp_n_rows);
+  if (P->tp_rest_rows) dev_free_t(P->tp_rest_rows, (size_t)P->tp_list_n);
+  P->tp_blobs = nullptr;
+  P->tp_blob_off = nullptr;
+  P->tp_chunks = P->tp_rows = P->tp_rest_rows = nullptr;
+  P->tp_blob_bytes = 0;
+  P->tp_n_tpl = P->tp_n_chunks = 0;
+  P->tp_n_rows = P->tp_list_n = P->tp_rest5 = P->tp_rest6 = 0;
+  P->tp_state = 0;
+}
+
 static int plan_free(Plan *P) {
   if (!P) return IIFE_OK;
   if (P->MT) mat_free(P->MT);
@@ -734,12 +777,8 @@ static int plan_free(Plan *P) {
   if (P->mt_alen) dev_free_t(P->mt_alen, (size_t)P->nnzR);
   if (P->inter_mbeg) dev_free_t(P->inter_mbeg, (size_t)P->inter_total);
   if (P->inter_mlen) dev_free_t(P->inter_mlen, (size_t)P->inter_total);
-  if (P->pg_steps) dev_free_t(P->pg_steps, (size_t)P->pg_rows);
-  if (P->pg_off) dev_free_t(P->pg_off, (size_t)P->pg_rows + 1);
-  if (P->pg_lane_out) dev_free_t(P->pg_lane_out, (size_t)P->pg_rows * 32);
-  if (P->pg_maxg) dev_free_t(P->pg_maxg, (size_t)P->pg_rows);
-  if (P->pg_slot) dev_free_t(P->pg_slot, (size_t)P->pg_total_steps * 32);
-  if (P->pg_val) dev_free_t(P->pg_val, (size_t)P->pg_total_steps * 32);
+  pg_free(P);
+  tpl_free(P);
   delete P;
   return IIFE_OK;
 }
@@ -1089,6 +1128,255 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
 
 int gather_vals_launch(const double *val, const int *perm, double *out, int64_t nnz);  // mat.cu
 
+// ------------------------------------------------------------------------------------------------
+// template plan (ptap_tpl.cuh / ptap_tpl_host.h)
+// ------------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static void tpl_parse_raw(const unsigned char *rec, tpl::Raw &r) {
+  const int *hd = (const int *)(rec + TPLR_INTS);
+  r.n0 = hd[0];
+  r.n1 = hd[1];
+  r.n2 = hd[2];
+  const int T1 = hd[3], T2 = hd[4];
+  r.len1.resize((size_t)r.n0);
+  r.w.resize((size_t)r.n0);
+  for (int q = 0; q < r.n0; ++q) {
+    r.len1[(size_t)q] = rec[TPLR_LEN1 + q];
+    r.w[(size_t)q] = ((const double *)(rec + TPLR_W))[q];
+  }
+  r.slot1.assign(rec + TPLR_SLOT1, rec + TPLR_SLOT1 + T1);
+  r.len2.resize((size_t)r.n1);
+  for (int q = 0; q < r.n1; ++q) r.len2[(size_t)q] = rec[TPLR_LEN2 + q];
+  r.slot2.assign(rec + TPLR_SLOT2, rec + TPLR_SLOT2 + T2);
+  r.mval.assign((const double *)(rec + TPLR_MVAL), (const double *)(rec + TPLR_MVAL) + T2);
+}
+
+// Groups the rows of the slot-plan bins by (structure, values of R and M), compiles a gather program per group
+// on the host and splits the bins into templated rows and the rest.  `a` carries the operands and plan arrays
+// with the CURRENT values of R (= M^T) and M.  *rebuilt = true when the row lists changed.
+static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *rebuilt) {
+  Ctx &c = ctx();
+  *rebuilt = false;
+  if (P->tp_state == 1 && P->tp_m_uid == M->uid && P->tp_m_version == M->val_version && P->tp_r_uid == Rm->uid &&
+      P->tp_r_version == Rm->val_version)
+    return IIFE_OK;
+  tpl_free(P);
+  *rebuilt = true;
+  P->tp_m_uid = M->uid;
+  P->tp_m_version = M->val_version;
+  P->tp_r_uid = Rm->uid;
+  P->tp_r_version = Rm->val_version;
+  P->tp_state = 1;
+  const int64_t n5 = P->bin_off[N_NUM_LEVELS + 1] - P->bin_off[N_NUM_LEVELS];
+  const int64_t n = P->bin_off[N_NUM_LEVELS + 2] - P->bin_off[N_NUM_LEVELS];
+  int min_rows = env_int("IIFE_TPL_MIN_ROWS", 32);
+  const int max_tpl = std::max(1, std::min(env_int("IIFE_TPL_MAX", 1024), 4096));
+  if (n < min_rows || !P->packed_meta || n > 0x7fffffff) return IIFE_OK;
+  const int *list = P->bin_rows + P->bin_off[N_NUM_LEVELS];
+  a.rows = list;
+  a.n_rows = n;
+  Tmp<unsigned long long> h1, h2, h1s;
+  Tmp<int> pos, spos, head, run_of, run_start, sel_d, n_sel_d;
+  IIFE_TRY(h1.alloc((size_t)n));
+  IIFE_TRY(h2.alloc((size_t)n));
+  IIFE_TRY(h1s.alloc((size_t)n));
+  IIFE_TRY(pos.alloc((size_t)n));
+  IIFE_TRY(spos.alloc((size_t)n));
+  IIFE_TRY(head.alloc((size_t)n + 1));
+  IIFE_TRY(run_of.alloc((size_t)n + 1));
+  const int hgrid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)c.sm_count * 8);
+  IIFE_LAUNCH(k_tpl_hash, hgrid, 256, 0, a, h1.p, h2.p);
+  IIFE_LAUNCH(k_tpl_iota, grid_for(n), 256, 0, pos.p, (long long)n);
+  IIFE_CHECK_LAUNCH();
+  {
+    size_t tmp_bytes = 0;
+    IIFE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h1.p, h1s.p, pos.p, spos.p, (int)n, 0, 64, c.stream));
+    Tmp<unsigned char> tmp;
+    IIFE_TRY(tmp.alloc(tmp_bytes));
+    IIFE_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, h1.p, h1s.p, pos.p, spos.p, (int)n, 0, 64, c.stream));
+    c.launches += 8;  // the passes of the library sort (plan build only, never in a numeric call)
+  }
+  IIFE_LAUNCH(k_tpl_heads, grid_for(n), 256, 0, h1s.p, (long long)n, head.p);
+  int64_t n_runs = 0;
+  IIFE_TRY(exclusive_scan_i32(head.p, run_of.p, n, &n_runs));
+  if (n_runs == n) return IIFE_OK;  // nothing repeats
+  IIFE_TRY(run_start.alloc((size_t)n_runs + 1));
+  IIFE_LAUNCH(k_tpl_run_starts, grid_for(n), 256, 0, head.p, run_of.p, (long long)n, run_start.p);
+  constexpr int SEL_CAP = 8192;
+  IIFE_TRY(sel_d.alloc(2 * SEL_CAP));
+  IIFE_TRY(n_sel_d.alloc(1));
+  int n_sel = 0;
+  for (;;) {  // more candidates than SEL_CAP: raise the bar (which ones were kept would not be deterministic)
+    IIFE_CUDA(cudaMemsetAsync(n_sel_d.p, 0, sizeof(int), c.stream));
+    IIFE_LAUNCH(k_tpl_select, grid_for(n_runs), 256, 0, run_start.p, (long long)n_runs, (long long)n, min_rows, SEL_CAP, sel_d.p, n_sel_d.p);
+    IIFE_CHECK_LAUNCH();
+    IIFE_TRY(read_int(n_sel_d.p, &n_sel));
+    if (n_sel <= SEL_CAP) break;
+    min_rows *= 4;
+  }
+  if (n_sel == 0) return IIFE_OK;
+  std::vector<int> sel((size_t)2 * n_sel);
+  IIFE_CUDA(cudaMemcpyAsync(sel.data(), sel_d.p, sel.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  IIFE_CUDA(cudaStreamSynchronize(c.stream));
+  {
+    std::vector<std::pair<int, int>> runs((size_t)n_sel);
+    for (int k = 0; k < n_sel; ++k) runs[(size_t)k] = {sel[(size_t)2 * k], sel[(size_t)2 * k + 1]};
+    std::sort(runs.begin(), runs.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) {
+      return x.second != y.second ? x.second > y.second : x.first < y.first;
+    });
+    if (n_sel > max_tpl) n_sel = max_tpl;
+    runs.resize((size_t)n_sel);
+    std::sort(runs.begin(), runs.end());  // templated rows are laid out in sorted-hash order
+    sel.resize((size_t)2 * n_sel);
+    for (int k = 0; k < n_sel; ++k) {
+      sel[(size_t)2 * k] = runs[(size_t)k].first;
+      sel[(size_t)2 * k + 1] = runs[(size_t)k].second;
+    }
+  }
+  const int n_tpl = n_sel;
+  IIFE_CUDA(cudaMemcpyAsync(sel_d.p, sel.data(), sel.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+  // ---- representative rows -> host -> programs
+  std::vector<unsigned char> raw((size_t)n_tpl * TPLR_STRIDE);
+  {
+    Tmp<unsigned char> raw_d;
+    IIFE_TRY(raw_d.alloc(raw.size()));
+    IIFE_LAUNCH(k_tpl_extract, std::min(n_tpl, c.sm_count * 4), 256, 0, a, (const int *)sel_d.p, (const int *)spos.p, n_tpl, raw_d.p);
+    IIFE_CHECK_LAUNCH();
+    IIFE_CUDA(cudaMemcpyAsync(raw.data(), raw_d.p, raw.size(), cudaMemcpyDeviceToHost, c.stream));
+    IIFE_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  const size_t warp_budget = (size_t)env_int("IIFE_TPL_WARP_SMEM", 20 * 1024);
+  std::vector<tpl::Program> progs((size_t)n_tpl);
+  std::vector<int> valid((size_t)n_tpl, 0);
+  std::vector<long long> blob_off((size_t)n_tpl, 0);
+  size_t blob_total = 0;
+  int s_cap = 2, o1_cap = 2, o2_cap = 2, n_valid = 0;
+  for (int t = 0; t < n_tpl; ++t) {
+    tpl::Raw r;
+    tpl_parse_raw(raw.data() + (size_t)t * TPLR_STRIDE, r);
+    tpl::Program &pr = progs[(size_t)t];
+    if (!tpl::compile(r, pr)) continue;
+    if (((size_t)pr.s_cap + pr.o1_cap + pr.o2_cap) * 8 + tpl::MAX_N0 * 4 > warp_budget) continue;
+    valid[(size_t)t] = 1;
+    ++n_valid;
+    blob_off[(size_t)t] = (long long)blob_total;
+    blob_total += pr.blob.size();
+    s_cap = std::max(s_cap, pr.s_cap);
+    o1_cap = std::max(o1_cap, pr.o1_cap);
+    o2_cap = std::max(o2_cap, pr.o2_cap);
+  }
+  if (n_valid == 0) return IIFE_OK;
+  // buffers start on 16-byte boundaries
+  s_cap = (s_cap + 1) & ~1;
+  o1_cap = (o1_cap + 1) & ~1;
+  o2_cap = (o2_cap + 1) & ~1;
+  std::vector<unsigned char> blobs(blob_total);
+  for (int t = 0; t < n_tpl; ++t)
+    if (valid[(size_t)t]) memcpy(blobs.data() + blob_off[(size_t)t], progs[(size_t)t].blob.data(), progs[(size_t)t].blob.size());
+  // ---- membership and row lists
+  Tmp<int> valid_d, tpl_of, f_sorted, f_rest, off_sorted, off_rest, ranges_d;
+  IIFE_TRY(valid_d.alloc((size_t)n_tpl));
+  IIFE_TRY(tpl_of.alloc((size_t)n));
+  IIFE_TRY(f_sorted.alloc((size_t)n + 1));
+  IIFE_TRY(f_rest.alloc((size_t)n + 1));
+  IIFE_TRY(off_sorted.alloc((size_t)n + 1));
+  IIFE_TRY(off_rest.alloc((size_t)n + 1));
+  IIFE_TRY(ranges_d.alloc((size_t)2 * n_tpl));
+  IIFE_CUDA(cudaMemcpyAsync(valid_d.p, valid.data(), (size_t)n_tpl * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+  IIFE_CUDA(cudaMemsetAsync(tpl_of.p, 0xFF, (size_t)n * sizeof(int), c.stream));
+  {
+    dim3 g(64, (unsigned)std::min(n_tpl, 65535));
+    k_tpl_assign<<<g, 256, 0, c.stream>>>(sel_d.p, valid_d.p, n_tpl, spos.p, h2.p, tpl_of.p);
+    c.launches++;
+  }
+  IIFE_LAUNCH(k_tpl_flags, grid_for(n), 256, 0, tpl_of.p, spos.p, (long long)n, f_sorted.p, f_rest.p);
+  IIFE_CHECK_LAUNCH();
+  int64_t n_t = 0, n_rest = 0;
+  IIFE_TRY(exclusive_scan_i32(f_sorted.p, off_sorted.p, n, &n_t));
+  IIFE_TRY(exclusive_scan_i32(f_rest.p, off_rest.p, n, &n_rest));
+  if (n_t == 0) return IIFE_OK;
+  int rest5 = 0;
+  IIFE_TRY(read_int(off_rest.p + n5, &rest5));
+  P->tp_n_rows = n_t;
+  P->tp_list_n = n;
+  P->tp_n_tpl = n_tpl;
+  IIFE_TRY(dev_alloc_t(&P->tp_rows, (size_t)n_t));
+  IIFE_TRY(dev_alloc_t(&P->tp_rest_rows, (size_t)n));
+  IIFE_LAUNCH(k_tpl_scatter, grid_for(n), 256, 0, list, tpl_of.p, spos.p, off_sorted.p, off_rest.p, (long long)n, P->tp_rows, P->tp_rest_rows);
+  IIFE_LAUNCH(k_tpl_ranges, (n_tpl + 255) / 256, 256, 0, sel_d.p, n_tpl, off_sorted.p, ranges_d.p);
+  IIFE_CHECK_LAUNCH();
+  std::vector<int> ranges((size_t)2 * n_tpl);
+  IIFE_CUDA(cudaMemcpyAsync(ranges.data(), ranges_d.p, ranges.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  IIFE_CUDA(cudaStreamSynchronize(c.stream));
+  const int chunk_rows = std::max(1, std::min(env_int("IIFE_TPL_CHUNK", TPL_CHUNK), 1024));
+  std::vector<int> chunks;
+  double u1 = 0.0, u2 = 0.0;
+  for (int t = 0; t < n_tpl; ++t) {
+    if (!valid[(size_t)t]) continue;
+    const int b = ranges[(size_t)2 * t], e = ranges[(size_t)2 * t + 1];
+    u1 += progs[(size_t)t].use1 * (e - b);
+    u2 += progs[(size_t)t].use2 * (e - b);
+    for (int r0 = b; r0 < e; r0 += chunk_rows) {
+      chunks.push_back(t);
+      chunks.push_back(r0);
+      chunks.push_back(std::min(chunk_rows, e - r0));
+    }
+  }
+  P->tp_use1 = u1 / (double)n_t;
+  P->tp_use2 = u2 / (double)n_t;
+  P->tp_chunk_rows = chunk_rows;
+  P->tp_n_chunks = (int)(chunks.size() / 3);
+  P->tp_blob_bytes = blob_total;
+  IIFE_TRY(dev_alloc_t(&P->tp_chunks, chunks.size()));
+  IIFE_TRY(dev_alloc_t(&P->tp_blobs, blob_total));
+  IIFE_TRY(dev_alloc_t(&P->tp_blob_off, (size_t)n_tpl));
+  IIFE_CUDA(cudaMemcpyAsync(P->tp_chunks, chunks.data(), chunks.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+  IIFE_CUDA(cudaMemcpyAsync(P->tp_blobs, blobs.data(), blob_total, cudaMemcpyHostToDevice, c.stream));
+  IIFE_CUDA(cudaMemcpyAsync(P->tp_blob_off, blob_off.data(), (size_t)n_tpl * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+  IIFE_CUDA(cudaStreamSynchronize(c.stream));  // the host vectors above go out of scope
+  P->tp_rest5 = rest5;
+  P->tp_rest6 = n_rest - rest5;
+  P->tp_s_cap = s_cap;
+  P->tp_o1_cap = o1_cap;
+  P->tp_o2_cap = o2_cap;
+  return IIFE_OK;
+}
+
+static int tpl_launch(Plan *P, PtapArgs a) {
+  Ctx &c = ctx();
+  TplArgs t{};
+  t.blobs = P->tp_blobs;
+  t.blob_off = P->tp_blob_off;
+  t.chunks = P->tp_chunks;
+  t.n_chunks = P->tp_n_chunks;
+  t.rows = P->tp_rows;
+  t.s_cap = P->tp_s_cap;
+  t.o1_cap = P->tp_o1_cap;
+  t.o2_cap = P->tp_o2_cap;
+  const size_t per_warp = (size_t)tpl::MAX_N0 * 4 + ((size_t)t.s_cap + t.o1_cap + t.o2_cap) * 8;
+  const size_t smem_max = (size_t)(c.max_smem_optin ? c.max_smem_optin : 227 * 1024);
+  int wpc = std::max(1, std::min(env_int("IIFE_TPL_WPC", 8), 32));
+  while (wpc > 1 && per_warp * wpc > smem_max) wpc >>= 1;
+  const size_t smem = per_warp * wpc;
+  if (smem > smem_max) return set_err(IIFE_ERR_STATE, "template kernel needs %zu B of shared memory per warp", per_warp);
+  if (smem > 48 * 1024) IIFE_CUDA(cudaFuncSetAttribute(k_ptap_numeric_tpl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ptap_numeric_tpl, wpc * 32, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  const int64_t ctas = std::min<int64_t>(((int64_t)t.n_chunks + wpc - 1) / wpc, (int64_t)c.sm_count * per_sm);
+  k_ptap_numeric_tpl<<<(int)ctas, wpc * 32, smem, c.stream>>>(a, t);
+  c.launches++;
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) return set_err(IIFE_ERR_CUDA, "template kernel launch: %s", cudaGetErrorString(le));
+  return IIFE_OK;
+}
+
 // Builds (or refreshes, when the values of M changed) the stage-2 gather program of the small-row bin.
 // `a` carries the operands, the plan arrays and the bin's row list.  pg_state stays -1 when it does not fit.
 static int prog_ensure(Plan *P, const Mat *M, PtapArgs a) {
@@ -1181,11 +1469,30 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
     a.mt_alen = P->packed_meta ? P->mt_alen : nullptr;
     a.inter_mbeg = P->packed_meta ? P->inter_mbeg : nullptr;
     a.inter_mlen = P->packed_meta ? P->inter_mlen : nullptr;
+    // template rows first (ptap_tpl.cuh): IIFE_PTAP_TPL=0 keeps every row on the per-row kernels
+    bool use_tpl = false;
+    {
+      const char *et = getenv("IIFE_PTAP_TPL");
+      if (!et || atoi(et) != 0) {
+        bool rebuilt = false;
+        if ((rc = tpl_ensure(P, Rm, M, a, &rebuilt)) != IIFE_OK) break;
+        if (rebuilt) pg_free(P);  // the gather program of ptap_prog.cuh is laid out for the old "rest" list
+        use_tpl = P->tp_n_rows > 0;
+        if (use_tpl && (rc = tpl_launch(P, a)) != IIFE_OK) break;
+      } else if (P->tp_state == 1) {
+        tpl_free(P);
+        pg_free(P);
+      }
+    }
     for (int sb = 0; sb < 2; ++sb) {  // slot-plan rows (ptap_slots.cuh)
       int l = N_NUM_LEVELS + sb;
       int64_t cnt = P->bin_off[l + 1] - P->bin_off[l];
-      if (cnt == 0) continue;
       a.rows = P->bin_rows + P->bin_off[l];
+      if (use_tpl) {  // what the templates did not take
+        cnt = sb == 0 ? P->tp_rest5 : P->tp_rest6;
+        a.rows = P->tp_rest_rows + (sb == 0 ? 0 : P->tp_rest5);
+      }
+      if (cnt == 0) continue;
       a.n_rows = cnt;
       int lg1 = a.logG1 < 3 ? 3 : (a.logG1 > 5 ? 5 : a.logG1);
       int lg2 = a.logG2 < 2 ? 2 : (a.logG2 > 5 ? 5 : a.logG2);
@@ -1317,6 +1624,7 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
     C->T_vals_valid = false;
     C->dinv_valid = false;
     C->sell_vals_valid = false;
+    C->val_version++;
   } while (0);
   if (rc != IIFE_OK) {
     if (created) mat_free(C);
@@ -1414,6 +1722,69 @@ int iife_plan_bin_counts(iife_plan P_, int64_t *counts7) {
   Plan *P = (Plan *)P_;
   if (!P || !counts7) return set_err(IIFE_ERR_ARG, "NULL argument");
   for (int l = 0; l < N_BINS; ++l) counts7[l] = P->bin_off[l + 1] - P->bin_off[l];
+  return IIFE_OK;
+}
+
+int iife_plan_tpl_info(iife_plan P_, int64_t *n_templates, int64_t *n_rows, int64_t *n_chunks, double *lane_use2) {
+  Plan *P = (Plan *)P_;
+  if (!P) return set_err(IIFE_ERR_ARG, "NULL plan");
+  int64_t nt = 0;
+  if (P->tp_state == 1 && P->tp_n_rows > 0) nt = P->tp_n_tpl;
+  if (n_templates) *n_templates = nt;
+  if (n_rows) *n_rows = P->tp_state == 1 ? P->tp_n_rows : 0;
+  if (n_chunks) *n_chunks = P->tp_state == 1 ? P->tp_n_chunks : 0;
+  if (lane_use2) {
+    lane_use2[0] = P->tp_use1;
+    lane_use2[1] = P->tp_use2;
+  }
+  return IIFE_OK;
+}
+
+// Host-only: compiles the gather program of one row description and runs the CPU interpreter on it (the CUDA
+// kernel executes the same program).  No device needed; used by the CPU tests of the program compiler.
+int iife_tpl_emulate_row(int n0, const int *len1, const double *w, const unsigned char *slot1, int n1, const int *len2,
+                         const double *mval, const unsigned char *slot2, int n2, const double *a_vals, double *c_out,
+                         int *info10) {
+  if (!len1 || !w || !slot1 || !len2 || !mval || !slot2 || !a_vals || !c_out) return set_err(IIFE_ERR_ARG, "NULL argument");
+  tpl::Raw r;
+  r.n0 = n0;
+  r.n1 = n1;
+  r.n2 = n2;
+  if (n0 < 0 || n1 < 0 || n2 < 0) return set_err(IIFE_ERR_ARG, "negative size");
+  r.len1.assign(len1, len1 + n0);
+  r.w.assign(w, w + n0);
+  int T1 = 0, T2 = 0;
+  for (int q = 0; q < n0; ++q) T1 += len1[q];
+  r.len2.assign(len2, len2 + n1);
+  for (int q = 0; q < n1; ++q) T2 += len2[q];
+  r.slot1.assign(slot1, slot1 + T1);
+  r.slot2.assign(slot2, slot2 + T2);
+  r.mval.assign(mval, mval + T2);
+  tpl::Program pr;
+  if (!tpl::compile(r, pr)) return set_err(IIFE_ERR_UNSUPPORTED, "row does not fit the template kernel's limits");
+  std::vector<const double *> rows((size_t)n0);
+  {
+    const double *p = a_vals;
+    for (int q = 0; q < n0; ++q) {
+      rows[(size_t)q] = p;
+      p += len1[q];
+    }
+  }
+  tpl::interpret(pr.blob.data(), rows.data(), c_out);
+  if (info10) {
+    tpl::Header h;
+    memcpy(&h, pr.blob.data(), sizeof(h));
+    info10[0] = h.S1;
+    info10[1] = h.S2;
+    info10[2] = h.nx1;
+    info10[3] = h.nx2;
+    info10[4] = h.stg_steps;
+    info10[5] = h.blob_bytes;
+    info10[6] = (int)(pr.use1 * 1000.0);
+    info10[7] = (int)(pr.use2 * 1000.0);
+    info10[8] = (int)(pr.conf1 * 1000.0);
+    info10[9] = (int)(pr.conf2 * 1000.0);
+  }
   return IIFE_OK;
 }
 

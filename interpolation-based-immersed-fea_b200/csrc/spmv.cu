@@ -17,11 +17,12 @@ namespace iife {
 
 constexpr int SPMV_THREADS = 256;
 
-// Tuning knob (compile time, unmeasured so far): `make EXTRA_NVCCFLAGS=-DIIFE_SELL_MINBLOCKS=4` gives the SELL kernels
-// 64 registers.  ptxas' own choice (40) leaves the dot-fused variant with one load in flight where the plain one
-// has U (SASS: 3.3 against 6.1 pending load registers on average; 12.5 for both with 64 registers).
+// Register budget of the SELL kernels: minBlocks = 4 gives them 64 registers.  ptxas' own choice (40) leaves the
+// dot-fused variant with one load in flight where the plain one has U (SASS: 3.3 against 6.1 pending load registers
+// on average; 12.5 for both with 64 registers).  Measured at N_b=184 (gpurun_out r2 A/B, profiles/r02_ab.md):
+// plain SpMV 293 -> 280 us, CG iteration 421 -> 407 us, and 395 us with the dot fused (which was a loss at 40).
 #ifndef IIFE_SELL_MINBLOCKS
-#define IIFE_SELL_MINBLOCKS 0
+#define IIFE_SELL_MINBLOCKS 4
 #endif
 #if IIFE_SELL_MINBLOCKS > 0
 #define IIFE_SELL_BOUNDS __launch_bounds__(SPMV_THREADS, IIFE_SELL_MINBLOCKS)
@@ -72,10 +73,10 @@ k_spmv(const int *__restrict__ rowptr, const int *__restrict__ colind, const dou
   }
 }
 
-// EXPERIMENTAL (IIFE_SPMV_ILP=1, off by default, not yet run on a GPU): y = A x for operators with very short rows
-// (the extraction operator M: 1-8 entries per row).  k_spmv keeps one row per lane group in flight, and a row is a
-// chain of three dependent loads (row pointer -> column -> x): measured 0.45 of the copy peak on M.  Here a lane
-// group walks TWO rows at a time with their loads interleaved, which doubles the bytes in flight per SM.
+// y = A x for operators with very short rows (the extraction operator M: 1-8 entries per row).  k_spmv keeps one
+// row per lane group in flight, and a row is a chain of three dependent loads (row pointer -> column -> x):
+// measured 0.45 of the copy peak on M.  Here a lane group walks TWO rows at a time with their loads interleaved,
+// which doubles the bytes in flight per SM: 0.915 -> 0.771 ms on M at N_b=184.  IIFE_SPMV_ILP=0 disables it.
 template <int LPR>
 __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv_ilp2(const int *__restrict__ rowptr, const int *__restrict__ colind, const double *__restrict__ val,
@@ -817,8 +818,8 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
   int g = spmv_grid(A->n_rows, lpr);
   bool plain = (alpha == 1.0 && beta == 0.0);
   if (plain && lpr <= 8) {
-    const char *ilp = getenv("IIFE_SPMV_ILP");  // experimental two-rows-in-flight kernel for short rows
-    if (ilp && atoi(ilp) != 0) {
+    const char *ilp = getenv("IIFE_SPMV_ILP");  // two-rows-in-flight kernel for short rows (default on)
+    if (!ilp || atoi(ilp) != 0) {
       int g2 = spmv_grid((A->n_rows + 1) / 2, lpr);
       if (lpr == 2) IIFE_LAUNCH((k_spmv_ilp2<2>), g2, SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, x, y);
       else if (lpr == 4) IIFE_LAUNCH((k_spmv_ilp2<4>), g2, SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, x, y);
@@ -848,7 +849,9 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
 int spmv_dot_launch(const Mat *A, const double *p, double *w, double *dot_out, double *partials,
                     unsigned int *counter, const int *flag, const P2PRed *red) {
   if (sell_ready(A)) {
-    static const bool fused = getenv("IIFE_SELL_FUSED_DOT") != nullptr;
+    // dot fused into the SpMV (default since the kernel has 64 registers: 407 -> 395 us per CG iteration);
+    // IIFE_SELL_FUSED_DOT=0 selects the plain SpMV followed by the dot kernel
+    static const bool fused = !(getenv("IIFE_SELL_FUSED_DOT") && atoi(getenv("IIFE_SELL_FUSED_DOT")) == 0);
     if (fused) return launch_sell(A, true, p, w, dot_out, partials, counter, flag, red);
     // plain SpMV followed by the dot kernel, both gated by the reason flag
     IIFE_TRY(launch_sell(A, false, p, w, nullptr, nullptr, nullptr, flag));
@@ -892,10 +895,11 @@ extern "C" int iife_spmv(iife_mat A_, int trans, double alpha, const double *x, 
   if (trans) {
     IIFE_TRY(mat_ensure_transpose(A));
     A = A->T;
-    // EXPERIMENTAL, off by default (not yet run on a GPU): M^T has uniform 27-entry rows, so its products
-    // (AT_x, reference la_utils.py:143-163) can take the SELL-32 kernel instead of the CSR one (1.05 ms = 0.37 of peak)
+    // M^T has near-uniform rows (27 entries on the cube), so its products (AT_x, reference la_utils.py:143-163)
+    // take the SELL-32 kernel on a SELL copy of the cached transpose: 1.05 -> 0.41 ms (0.37 -> 0.93 of the copy
+    // peak) at N_b=184.  mat_ensure_sell keeps CSR when padding would exceed 25 %.  IIFE_SPMV_SELL_T=0 disables.
     const char *sell_t = getenv("IIFE_SPMV_SELL_T");  // read per call: scripts/compare_variants.py toggles it
-    if (sell_t && atoi(sell_t) != 0 && alpha == 1.0 && beta == 0.0) IIFE_TRY(mat_ensure_sell(A));
+    if ((!sell_t || atoi(sell_t) != 0) && alpha == 1.0 && beta == 0.0) IIFE_TRY(mat_ensure_sell(A));
   }
   if (mem == IIFE_MEM_DEVICE) return spmv_launch(A, alpha, x, beta, y);
   Tmp<double> dx, dy;

@@ -39,6 +39,7 @@ PROTOTYPES = {
     "iife_mat_get_info": (c_int, [c_vp, P(c_i64), P(c_i64), P(c_i64)]),
     "iife_mat_get_csr": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int]),
     "iife_mat_device_ptrs": (c_int, [c_vp, P(c_vp), P(c_vp), P(c_vp)]),
+    "iife_mat_touch": (c_int, [c_vp]),
     "iife_mat_fingerprint": (c_int, [c_vp, P(ctypes.c_uint64)]),
     "iife_mat_transpose": (c_int, [c_vp, P(c_vp)]),
     "iife_mat_get_diagonal": (c_int, [c_vp, c_vp, c_int]),
@@ -53,6 +54,8 @@ PROTOTYPES = {
     "iife_rap_numeric": (c_int, [c_vp, c_vp, c_vp, c_vp, P(c_vp)]),
     "iife_plan_bin_counts": (c_int, [c_vp, P(c_i64)]),
     "iife_plan_check": (c_int, [c_vp]),
+    "iife_plan_tpl_info": (c_int, [c_vp, P(c_i64), P(c_i64), P(c_i64), c_vp]),
+    "iife_tpl_emulate_row": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "iife_ptap_numeric": (c_int, [c_vp, c_vp, c_vp, P(c_vp)]),
     "iife_plan_destroy": (c_int, [c_vp]),
     "iife_ptap": (c_int, [c_vp, c_vp, P(c_vp), P(c_int)]),

@@ -283,6 +283,13 @@ class PtapPlan:
         check(lib.iife_plan_bin_counts(self._h, c))
         return list(c)
 
+    def tpl_info(self):
+        """template plan of the numeric phase (include/iife.h: iife_plan_tpl_info); zeros before the first numeric call"""
+        a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        use = (ctypes.c_double * 2)()
+        check(lib.iife_plan_tpl_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), use))
+        return {"templates": int(a.value), "rows": int(b.value), "chunks": int(c.value), "lane_use": [use[0], use[1]]}
+
     def matches(self, M: DeviceMat, A: DeviceMat) -> bool:
         m = ctypes.c_int(0)
         check(lib.iife_plan_matches(self._h, M.handle, A.handle, ctypes.byref(m)))

@@ -228,6 +228,7 @@ int oracle_cg_jacobi(i64 n, const i64 *rp, const i32 *ci, const double *v, const
   }
   double dp = sqrt(dot(n, z, z));
   double rho0 = sqrt(dot(n, w, w));
+  if (rho0 == 0.0) rho0 = dp; /* KSPConvergedDefault: zero rhs, nonzero guess -> initial residual norm */
   double ttol = fmax(rtol * rho0, atol);
   if (hist && hist_len > 0) hist[0] = dp;
   reason = converged_default(dp, ttol, atol, dtol, rho0);
@@ -302,6 +303,10 @@ static int fgmres_impl(i64 n, const i64 *rp, const i32 *ci, const double *v, con
     for (i64 k = 0; k < n; ++k) V[0][k] = b[k] - V[0][k];
     res = sqrt(dot(n, V[0], V[0]));
     if (first && hist && hist_len > 0) hist[0] = res;
+    if (first && rho0 == 0.0) { /* KSPConvergedDefault: zero rhs, nonzero guess -> initial residual norm */
+      rho0 = res;
+      ttol = fmax(rtol * rho0, atol);
+    }
     first = 0;
     reason = converged_default(res, ttol, atol, dtol, rho0);
     if (!reason && its >= max_it) reason = -3;
@@ -401,4 +406,72 @@ int oracle_fgmres_hessenberg(i64 n, const i64 *rp, const i32 *ci, const double *
                              i64 *its_out, double *rnorm_out, double *R_out, i64 *k_out) {
   if (k_out) *k_out = 0;
   return fgmres_impl(n, rp, ci, v, dinv_in, b, x, rtol, atol, dtol, max_it, m, its_out, rnorm_out, NULL, 0, R_out, k_out);
+}
+
+/* ---- synthetic S1 fitted cube (BASELINE config 5): the operands of bench.py's CPU arm ----
+ * Same construction as the host generator of the product's bench tooling (iife_b200/synthetic.py:
+ * cube_operators) and its device twin (csrc/synth.cu), restated here so that the CPU arm builds its operands
+ * without importing the product: P1 stiffness + sigma*mass on the Kuhn triangulation of a (2N)^3 grid from the
+ * 8x27 per-cell table `coef` (corner c, neighbour offset d), M = trilinear interpolation from the N^3
+ * background grid, b_f = load of f = 1.  Pass 1 (a_rp/m_rp NULL-able value arrays): row lengths; pass 2: fill.
+ * tests/test_oracle.py checks it bit for bit against the numpy generator. */
+static const int S1_OFFS[15][3] = {
+    /* (dx,dy,dz) in the order dz, dy, dx ascending, all components >= 0 or all <= 0 */
+    {-1, -1, -1}, {0, -1, -1}, {-1, 0, -1}, {0, 0, -1}, {-1, -1, 0}, {0, -1, 0}, {-1, 0, 0}, {0, 0, 0},
+    {1, 0, 0},    {0, 1, 0},   {1, 1, 0},   {0, 0, 1},  {1, 0, 1},   {0, 1, 1},  {1, 1, 1}};
+
+void oracle_synth_cube_lengths(i64 n_bg_cells, i64 *a_len, i64 *m_len) {
+  const i64 nv = 2 * n_bg_cells + 1, n_f = nv * nv * nv;
+#pragma omp parallel for schedule(static)
+  for (i64 j = 0; j < n_f; ++j) {
+    const i64 x = j % nv, y = (j / nv) % nv, z = j / (nv * nv);
+    int la = 0;
+    for (int o = 0; o < 15; ++o) {
+      const i64 xx = x + S1_OFFS[o][0], yy = y + S1_OFFS[o][1], zz = z + S1_OFFS[o][2];
+      la += (xx >= 0 && yy >= 0 && zz >= 0 && xx < nv && yy < nv && zz < nv);
+    }
+    a_len[j] = la;
+    m_len[j] = (i64)((x & 1) + 1) * ((y & 1) + 1) * ((z & 1) + 1);
+  }
+}
+
+void oracle_synth_cube_fill(i64 n_bg_cells, const double *coef /* 8 x 27 */, const double *load8, const i64 *a_rp,
+                            i32 *a_ci, double *a_v, const i64 *m_rp, i32 *m_ci, double *m_v, double *b_f) {
+  const i64 nv = 2 * n_bg_cells + 1, nb = n_bg_cells + 1, n_f = nv * nv * nv, ncell = nv - 1;
+#pragma omp parallel for schedule(static)
+  for (i64 j = 0; j < n_f; ++j) {
+    const i64 x = j % nv, y = (j / nv) % nv, z = j / (nv * nv);
+    int cell_ok[8];
+    double b = 0.0;
+    for (int c = 0; c < 8; ++c) {
+      const i64 cx = x - (c & 1), cy = y - ((c >> 1) & 1), cz = z - ((c >> 2) & 1);
+      cell_ok[c] = (cx >= 0 && cy >= 0 && cz >= 0 && cx < ncell && cy < ncell && cz < ncell);
+      if (cell_ok[c]) b += load8[c];
+    }
+    b_f[j] = b;
+    i64 p = a_rp[j];
+    for (int o = 0; o < 15; ++o) {
+      const int dx = S1_OFFS[o][0], dy = S1_OFFS[o][1], dz = S1_OFFS[o][2];
+      const i64 xx = x + dx, yy = y + dy, zz = z + dz;
+      if (!(xx >= 0 && yy >= 0 && zz >= 0 && xx < nv && yy < nv && zz < nv)) continue;
+      const int d = (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1);
+      double v = 0.0;
+      for (int c = 0; c < 8; ++c)
+        if (cell_ok[c]) v += coef[c * 27 + d];
+      a_ci[p] = (i32)(xx + nv * (yy + nv * zz));
+      a_v[p] = v;
+      ++p;
+    }
+    const i64 bx0 = x >> 1, by0 = y >> 1, bz0 = z >> 1;
+    const int nx = (int)(x & 1) + 1, ny = (int)(y & 1) + 1, nz = (int)(z & 1) + 1;
+    const double w = ((x & 1) ? 0.5 : 1.0) * ((y & 1) ? 0.5 : 1.0) * ((z & 1) ? 0.5 : 1.0);
+    i64 q = m_rp[j];
+    for (int kz = 0; kz < nz; ++kz)
+      for (int ky = 0; ky < ny; ++ky)
+        for (int kx = 0; kx < nx; ++kx) {
+          m_ci[q] = (i32)((bx0 + kx) + nb * ((by0 + ky) + nb * (bz0 + kz)));
+          m_v[q] = w;
+          ++q;
+        }
+  }
 }

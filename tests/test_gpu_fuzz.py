@@ -1,8 +1,7 @@
 """Randomised parity sweep of the CUDA path against the oracle (hypothesis): shapes, row-length distributions,
 empty rows/columns, single rows, rows far longer than a warp, stored zeros.  Same bars as test_gpu_parity.py.
 
-Gated: written after the round's GPU budget was spent, so it has not run on a GPU yet.  Enable with
-IIFE_TEST_UNVERIFIED=1 (scripts/r2_experiments.sh does); drop the gate once it has passed."""
+First run on a B200 in round 2 (2 passed); part of the `-m gpu` suite since."""
 import os
 
 import numpy as np
@@ -10,9 +9,7 @@ import pytest
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("IIFE_TEST_UNVERIFIED"),
-                                 reason="not yet run on a GPU: enable with IIFE_TEST_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _random_csr(rng, n_rows, n_cols, mean_len, heavy_rows, empty_frac, zero_frac):

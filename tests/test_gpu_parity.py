@@ -225,6 +225,54 @@ def test_ptap_every_numeric_kernel_is_exercised(iife, oracle):
     print("rows per numeric kernel:", seen.tolist())
 
 
+@pytest.mark.parametrize("min_rows", [None, "2"])
+def test_ptap_template_kernel(iife, oracle, monkeypatch, min_rows):
+    """Rows that share structure and M values run one precompiled gather program (csrc/ptap_tpl.cuh): the cube's
+    interior rows with the default threshold, every face/edge variant too with a threshold of 2.  Checked against
+    the oracle, against the per-row kernels (IIFE_PTAP_TPL=0), after a value update of A_f, and after a value
+    update of M (which must rebuild the templates)."""
+    from oracle.synthetic_cube import assemble_cube
+
+    if min_rows:
+        monkeypatch.setenv("IIFE_TPL_MIN_ROWS", min_rows)
+    A, M, _ = assemble_cube(6)
+    dM, dA, dC, C, plan = check_ptap(iife, oracle, M, A)
+    ti = plan.tpl_info()
+    n_b = M.n_cols
+    assert ti["templates"] >= (1 if not min_rows else 8) and ti["rows"] >= 5 ** 3, ti
+    if min_rows:
+        assert ti["rows"] >= n_b - 8, ti  # everything but the 8 corner rows repeats
+    assert ti["lane_use"][0] > 0.5 and ti["lane_use"][1] > 0.5, ti
+    v_tpl = dC.values().copy()
+    monkeypatch.setenv("IIFE_PTAP_TPL", "0")
+    v_row = plan.numeric(dM, dA, check_errors=True).values()
+    assert plan.tpl_info()["rows"] == 0
+    monkeypatch.delenv("IIFE_PTAP_TPL")
+    bound = oracle.AT_R_A(abs_csr(oracle, M), abs_csr(oracle, A))
+    assert np.all(np.abs(v_tpl - v_row) <= VAL_TOL * bound.val)
+    # new values of A_f on the same templates
+    rng = np.random.default_rng(3)
+    A2 = oracle.CSR(A.n_rows, A.n_cols, A.rowptr, A.colind, A.val * (1 + 0.3 * rng.standard_normal(A.nnz)))
+    dA.update_values(A2.val)
+    v2 = plan.numeric(dM, dA, check_errors=True).values()
+    assert plan.tpl_info()["rows"] == ti["rows"]
+    C2 = oracle.AT_R_A(M, A2)
+    b2 = oracle.AT_R_A(abs_csr(oracle, M), abs_csr(oracle, A2))
+    assert np.all(np.abs(v2 - C2.val) <= VAL_TOL * b2.val)
+    # new values of M: the groups are value dependent, so the template plan is rebuilt (here: nothing repeats)
+    M3 = oracle.CSR(M.n_rows, M.n_cols, M.rowptr, M.colind, M.val * (1 + 0.3 * rng.random(M.nnz)))
+    dM.update_values(M3.val)
+    v3 = plan.numeric(dM, dA, check_errors=True).values()
+    assert plan.tpl_info()["rows"] < ti["rows"]
+    C3 = oracle.AT_R_A(M3, A2)
+    b3 = oracle.AT_R_A(abs_csr(oracle, M3), abs_csr(oracle, A2))
+    assert np.all(np.abs(v3 - C3.val) <= VAL_TOL * b3.val)
+    # and back
+    dM.update_values(M.val)
+    v4 = plan.numeric(dM, dA, check_errors=True).values()
+    assert plan.tpl_info()["rows"] == ti["rows"] and np.array_equal(v4, v2)
+
+
 def test_ptap_numeric_reuse_and_cache(iife, oracle):
     """config 4 pattern: same M, same A_f pattern, new values many times on one symbolic plan."""
     from oracle.synthetic_cube import assemble_cube
@@ -531,8 +579,6 @@ def test_trim_nodes_and_newton_through_the_mirror(iife, oracle, capsys):
     assert np.allclose(u_f.array, oracle.spmv(Mo, u_p.array), rtol=0, atol=1e-10 * np.abs(u_f.array).max())
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("IIFE_TEST_UNVERIFIED"),
-                    reason="written after the round's GPU budget was spent: enable with IIFE_TEST_UNVERIFIED=1")
 def test_condition_estimate_matches_oracle(iife, oracle):
     """iife_ksp_solve_hessenberg / estimateConditionNumber (reference common.py:483-507) against the oracle."""
     from InterpolationBasedImmersedFEA import common as api
