@@ -247,9 +247,9 @@ def run_ours(args):
     peak, peak_src = measured_peak()
 
     if world > 1:
-        from iife_b200 import dist as idist
+        import bench_dist
 
-        return idist.bench_distributed(args, I, stream, peak, peak_src, METRIC, UNIT)
+        return bench_dist.run(args, I, stream, peak, peak_src, METRIC, UNIT, ClockSampler)
 
     N = args.cells
     sz = synthetic.cube_sizes(N)
@@ -345,6 +345,11 @@ def run_ours(args):
         cg_times.append(e0.elapsed_time(e1))
     t_cg = sorted(cg_times)[1]
     del plan, Cn
+    # the three scalars bench_dist.py compares the row-partitioned result with (same N_b)
+    Cw.spmv(xs, y)
+    torch.cuda.synchronize()
+    parity_scalars = {"sum_b_b": float(bb.sum().item()), "norm_A_b_ones": float(torch.linalg.vector_norm(y).item()),
+                      "norm_u_b": float(torch.linalg.vector_norm(x).item()), "cg_iterations": int(info_cg.iterations)}
 
     traffic = None
     try:
@@ -476,7 +481,7 @@ def run_ours(args):
                    "nnz_A_f": nnzA, "nnz_M": nnzM, "nnz_A_b": nnzC, "ksp": "cg+jacobi rtol=1e-8 atol=1e-9 zero guess",
                    "cg_iterations": info.iterations, "cg_reason": info.reason_name, "plan_cached": bool(state["cached"]),
                    "cold_ptap_symbolic_plus_numeric_ms": t_cold * 1e3, "l2": "inputs larger than L2 (no flush)",
-                   "parallelism": "1 GPU"},
+                   "parallelism": "1 GPU", "single_gpu": parity_scalars},
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))

@@ -36,6 +36,34 @@ except Exception:  # pragma: no cover
     _dolfin = None
     HAVE_DOLFIN = False
 
+if HAVE_DOLFIN:
+    # the reference module star-imports dolfin (la_utils.py:6-8) and every demo relies on getting dolfin's names
+    # through `from InterpolationBasedImmersedFEA.la_utils import *` (demos/poisson.py:14-16)
+    from dolfin import *  # type: ignore # noqa: F401,F403,E402
+    try:
+        from dolfin.cpp.log import *  # type: ignore # noqa: F401,F403,E402
+    except Exception:  # pragma: no cover
+        pass
+    try:  # module-level settings of the reference (la_utils.py:12-26)
+        INFO = LogLevel.INFO  # noqa: F405
+        set_log_level(INFO)  # noqa: F405
+        parameters['std_out_all_processes'] = False  # noqa: F405
+        worldcomm = MPI.comm_world  # noqa: F405
+        mpirank = MPI.rank(worldcomm)  # noqa: F405
+        mpisize = MPI.size(worldcomm)  # noqa: F405
+        DOLFIN_FUNCTION = function.function.Function  # noqa: F405
+        DOLFIN_VECTOR = cpp.la.Vector  # noqa: F405
+        DOLFIN_MATRIX = cpp.la.Matrix  # noqa: F405
+        DOLFIN_PETSCVECTOR = cpp.la.PETScVector  # noqa: F405
+        DOLFIN_PETSCMATRIX = cpp.la.PETScMatrix  # noqa: F405
+    except Exception:  # pragma: no cover - a dolfin without these names
+        worldcomm, mpirank, mpisize = None, 0, 1
+else:
+    worldcomm, mpirank, mpisize = None, 0, 1
+if HAVE_PETSC:
+    PETSC4PY_VECTOR = PETSc.Vec
+    PETSC4PY_MATRIX = PETSc.Mat
+
 
 def _ensure_init():
     if not _iife.is_initialised():
@@ -306,10 +334,13 @@ def arg2v(x):
     if HAVE_PETSC and isinstance(x, PETSc.Vec):
         return x
     if HAVE_DOLFIN:
-        if isinstance(x, _dolfin.function.function.Function):
-            return _dolfin.as_backend_type(x.vector()).vec()
-        if isinstance(x, (_dolfin.cpp.la.PETScVector, _dolfin.cpp.la.Vector)):
-            return _dolfin.as_backend_type(x).vec()
+        try:
+            if isinstance(x, _dolfin.function.function.Function):
+                return _dolfin.as_backend_type(x.vector()).vec()
+            if isinstance(x, (_dolfin.cpp.la.PETScVector, _dolfin.cpp.la.Vector)):
+                return _dolfin.as_backend_type(x).vec()
+        except AttributeError:  # pragma: no cover - a dolfin build without these classes
+            pass
     if isinstance(x, np.ndarray):
         return Vec(x)
     raise TypeError("Type " + str(type(x)) + " is not supported yet.")
@@ -321,8 +352,12 @@ def arg2m(A):
         return A
     if HAVE_PETSC and isinstance(A, PETSc.Mat):
         return A
-    if HAVE_DOLFIN and isinstance(A, (_dolfin.cpp.la.PETScMatrix, _dolfin.cpp.la.Matrix)):
-        return _dolfin.as_backend_type(A).mat()
+    if HAVE_DOLFIN:
+        try:
+            if isinstance(A, (_dolfin.cpp.la.PETScMatrix, _dolfin.cpp.la.Matrix)):
+                return _dolfin.as_backend_type(A).mat()
+        except AttributeError:  # pragma: no cover
+            pass
     try:
         import scipy.sparse as sp
 

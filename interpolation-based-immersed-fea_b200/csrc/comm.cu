@@ -223,6 +223,24 @@ int iife_halo_destroy(iife_halo H_) {
   if (ctx().init) cudaStreamSynchronize(ctx().stream);
   dev_free_t(H->send_idx, (size_t)H->total_send);
   dev_free_t(H->send_buf, (size_t)H->total_send);
+  // peer-memory path (p2p.cu): plain cudaMalloc allocations and IPC mappings
+  for (int q = 0; q < P2P_MAX_RANKS; ++q) {
+    if (H->peer_xbuf[q] && H->peer_xbuf[q] != H->xbuf) cudaIpcCloseMemHandle(H->peer_xbuf[q]);
+    if (H->peer_mbox[q] && H->peer_mbox[q] != H->mbox) cudaIpcCloseMemHandle(H->peer_mbox[q]);
+  }
+  cudaFree(H->send_peer);
+  cudaFree(H->send_off_dev);
+  cudaFree(H->brow);
+  cudaFree(H->bptr);
+  cudaFree(H->bpeer);
+  cudaFree(H->bdst);
+  cudaFree(H->bmask);
+  cudaFree(H->xbuf);
+  cudaFree(H->mbox);
+  cudaFree(H->dev_seq);
+  cudaFree(H->p2p_counter);
+  cudaFree(H->p2p_err);
+  cudaGetLastError();
   delete H;
   return IIFE_OK;
 }

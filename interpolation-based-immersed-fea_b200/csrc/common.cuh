@@ -138,7 +138,9 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
 // w = A p and *dot_out = sum_i p_i w_i over the rows of A (partials + deterministic last-block
 // reduce); if flag != nullptr and *flag != 0 the kernel is a no-op.
 int spmv_dot_launch(const Mat *A, const double *p, double *w, double *dot_out, double *partials,
-                    unsigned int *counter, const int *flag, const struct P2PRed *red = nullptr);
+                    unsigned int *counter, const int *flag, const struct P2PRed *red = nullptr,
+                    const struct HaloWait *hw = nullptr);
+bool mat_sell_ready(const Mat *A);
 int spmv_pick_lpr(const Mat *A);
 // SELL-32 operator copy: builds it on first use (returns IIFE_OK with A->sell_state == -1 if the
 // padding would exceed 1.25x nnz, in which case callers stay on CSR) and refreshes values.
@@ -171,6 +173,14 @@ struct Halo {
   unsigned int *p2p_counter = nullptr;    // device [1]
   int *p2p_err = nullptr;                 // device [1]
   unsigned int send_mask = 0, recv_mask = 0;
+  // push plan by OWNED ROW (three-kernel CG iteration, ksp.cu): the thread that updates p[i] also stores it into the
+  // neighbours' ghost slots.  brow: sorted owned rows that are sent anywhere; entries bptr[k]..bptr[k+1] of
+  // (bpeer, bdst) say where; bmask: one bit per owned row (is it in brow?)
+  int n_brow = 0;
+  int *brow = nullptr, *bptr = nullptr;
+  unsigned char *bpeer = nullptr;
+  long long *bdst = nullptr;
+  unsigned int *bmask = nullptr;
 };
 
 constexpr int P2P_MAX_RANKS = 16;

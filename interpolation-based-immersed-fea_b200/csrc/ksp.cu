@@ -26,7 +26,8 @@ namespace iife {
 enum {
   S_BETA = 0, S_BETA_OLD, S_DELTA, S_DP, S_TTOL, S_RHO0, S_RTOL, S_ATOL, S_DTOL, S_SCALE, S_RES, S_TT,
   S_RAW = 12,  // 3 raw (rank-local) sums awaiting the allreduce in the row-partitioned solver
-  S_COUNT = 16
+  S_BETA2 = 16,  // three-kernel CG iteration: (z_k, r_k) of iteration k in slot k & 1
+  S_COUNT = 20
 };
 // flag slots
 enum { F_REASON = 0, F_ITS, F_LOC_IT, F_MAXIT, F_HAPEND, F_COUNT = 8 };
@@ -181,6 +182,8 @@ k_cg_p(const double *__restrict__ r, const double *__restrict__ dinv, double *__
 // MODE 0: single GPU (scalar step by the last CTA).  MODE 1: row-partitioned with NCCL (raw sums out).
 // MODE 2: row-partitioned over peer memory: delta is summed from the ranks' partials waiting in the
 // mailbox (prologue), the two new partial sums are pushed to every rank by the last CTA (epilogue).
+// MODE 3: as 2 inside the three-kernel iteration (k_cg_p_push does the scalar step): beta of this iteration is in
+// the slot S_BETA2 + (iteration & 1), `it_rel` = iteration index since the start of the solve.
 template <int MODE>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
@@ -191,11 +194,11 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
   __shared__ double out[2];
   __shared__ bool last;
   double delta;
-  if (MODE == 2) {
+  if (MODE == 2 || MODE == 3) {
     __shared__ double s_delta;
     if (threadIdx.x < 32) {
       double d;
-      p2p_wait_sum(pr, 2ull * (*pr.iter) + 1ull, &d, 1);
+      p2p_wait_sum(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 1ull, &d, 1);
       if (threadIdx.x == 0) {
         s_delta = d;
         if (blockIdx.x == 0) sc[S_DELTA] = d;
@@ -216,7 +219,12 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
     }
     return;
   }
-  double alpha = sc[S_BETA] / delta;
+  double beta_now = sc[S_BETA];
+  if (MODE == 3) {
+    const unsigned long long it_rel = *pr.iter + (unsigned long long)pr.k_off - pr.iter[1];
+    beta_now = sc[S_BETA2 + (int)(it_rel & 1ull)];
+  }
+  double alpha = beta_now / delta;
   double acc[2] = {0.0, 0.0};
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -229,8 +237,8 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
     acc[1] = fma(z, z, acc[1]);
   }
   if (grid_reduce<2>(acc, partials, counter, out, red, &last)) {
-    if (MODE == 2) {
-      p2p_push(pr, 2ull * (*pr.iter) + 2ull, out, 2, threadIdx.x);
+    if (MODE == 2 || MODE == 3) {
+      p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 2ull, out, 2, threadIdx.x);
     } else if (threadIdx.x == 0) {
       if (MODE == 1) {
         sc[S_RAW + 0] = out[0];
@@ -252,6 +260,109 @@ __global__ void k_cg_scalars_p2p(double *sc, int *fl, double *hist, long long hi
   if (threadIdx.x != 0) return;
   cg_update_scalars(sc, fl, v[0], v[1], hist, hist_len);
   *iter = *iter + 1ull;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Three-kernel CG iteration of the row-partitioned solver over peer memory (IIFE_CG_FUSED3, default on):
+//   k_cg_p_push      scalar step of the PREVIOUS iteration (every CTA sums the ranks' (z.r, z.z) partials from the
+//                    mailbox in rank order and takes the same decision; CTA 0 records it), p = z + (beta/beta_old) p,
+//                    and the thread that updates a boundary row stores it straight into the neighbours' ghost slots;
+//                    the last CTA raises the halo flags
+//   k_spmv_sell      waits for the neighbours' flags in its prologue (HaloWait), w = A p, partial (p, w) pushed
+//   k_cg_update<3>   waits for delta, x / r update, partial (z.r, z.z) pushed
+// instead of five (p update, halo kernel, SpMV, update, scalar kernel).  All sequence numbers are the device
+// counters of the halo (dev_seq[0] exchanges, dev_seq[2] iterations, dev_seq[3] = iteration counter at the start
+// of the solve) plus the iteration's index k inside the captured chunk; k_cg_chunk_end moves the counters once per chunk,
+// so no kernel reads a counter that another CTA of the same kernel writes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_p_push(const double *__restrict__ r, const double *__restrict__ dinv, double *__restrict__ p, int64_t n, double *sc,
+            int *fl, double *hist, long long hist_len, P2PRed pr, RowPush rp) {
+  if (fl[F_REASON] != 0) return;  // set by an earlier kernel (CTA 0 of THIS kernel can only reach the same verdict)
+  __shared__ double s_bb;
+  __shared__ int s_stop;
+  __shared__ bool last;
+  const unsigned long long git = *pr.iter + (unsigned long long)pr.k_off;
+  const unsigned long long it_rel = git - pr.iter[1];
+  const bool first = (it_rel == 0ull);
+  if (!first) {
+    if (threadIdx.x < 32) {
+      double v[2];
+      p2p_wait_sum(pr, 2ull * (git - 1ull) + 2ull, v, 2);
+      if (threadIdx.x == 0) {
+        // KSPSolve_CG after the update of iteration it_rel-1: beta_old <- beta, beta = (z, r), dp = ||z||, its, test
+        const double beta_old = sc[S_BETA2 + (int)((it_rel - 1ull) & 1ull)];
+        const double beta = v[0], dp = sqrt(v[1]);
+        const int its = (int)it_rel;
+        int reason = 0, its_out = its;
+        if (isnan(dp) || isinf(dp)) reason = IIFE_KSP_DIVERGED_NANORINF;
+        else if (dp <= sc[S_TTOL]) reason = (dp < sc[S_ATOL]) ? IIFE_KSP_CONVERGED_ATOL : IIFE_KSP_CONVERGED_RTOL;
+        else if (dp >= sc[S_DTOL] * sc[S_RHO0]) reason = IIFE_KSP_DIVERGED_DTOL;
+        else if (its >= fl[F_MAXIT]) reason = IIFE_KSP_DIVERGED_ITS;
+        else if (beta == 0.0) { reason = IIFE_KSP_CONVERGED_ATOL; its_out = its + 1; }
+        else if (beta < 0.0) { reason = IIFE_KSP_DIVERGED_INDEFINITE_PC; its_out = its + 1; }
+        else if (isnan(beta) || isinf(beta)) { reason = IIFE_KSP_DIVERGED_NANORINF; its_out = its + 1; }
+        s_bb = beta / beta_old;
+        s_stop = reason;
+        if (blockIdx.x == 0) {
+          sc[S_BETA2 + (int)(it_rel & 1ull)] = beta;
+          sc[S_BETA_OLD] = beta_old;
+          sc[S_BETA] = beta;
+          sc[S_DP] = dp;
+          log_hist(hist, hist_len, its, dp);
+          fl[F_ITS] = its_out;
+          if (reason) {
+            __threadfence();
+            fl[F_REASON] = reason;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (s_stop) return;
+  }
+  const double bb = first ? 0.0 : s_bb;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool stored = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double z = (dinv ? dinv[i] : 1.0) * r[i];
+    const double pn = first ? z : fma(bb, p[i], z);
+    p[i] = pn;
+    if ((__ldg(rp.bmask + (i >> 5)) >> (i & 31)) & 1u) {  // a boundary row: its neighbours' ghost copies
+      int lo = 0, hi = rp.n_brow;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(rp.brow + mid) < (int)i) lo = mid + 1;
+        else hi = mid;
+      }
+      for (int e = __ldg(rp.bptr + lo); e < __ldg(rp.bptr + lo + 1); ++e) rp.pt.xbuf[rp.bpeer[e]][rp.bdst[e]] = pn;
+      stored = true;
+    }
+  }
+  if (stored) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(rp.counter, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  const int q = threadIdx.x;
+  if (q < rp.nranks && ((rp.send_mask >> q) & 1u)) st_flag(&rp.pt.mbox[q]->halo_flag[rp.me], *rp.seq_base + (unsigned long long)pr.k_off + 1ull);
+  if (threadIdx.x == 0) *rp.counter = 0u;
+}
+
+// end of a captured chunk of `chunk` iterations: the counters the kernels above offset with k
+__global__ void k_cg_chunk_end(unsigned long long *dev_seq, int chunk) {
+  dev_seq[0] += (unsigned long long)chunk;
+  dev_seq[2] += (unsigned long long)chunk;
+}
+
+// start of a solve on the three-kernel path: fresh iteration sequence (see k_bump_seq), its start, beta_0
+__global__ void k_cg_fused3_begin(unsigned long long *dev_seq, double *sc) {
+  dev_seq[3] = dev_seq[2];
+  sc[S_BETA2] = sc[S_BETA];
 }
 
 // A solve that stopped on (p, A p) <= 0 has exchanged reduction 2*iter+1 without finishing iteration `iter`: the
@@ -685,6 +796,35 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   }
   int chunk = env_int("IIFE_KSP_CHUNK", 32);
   if (chunk < 1) chunk = 1;
+  // three-kernel iteration of the peer-memory path (k_cg_p_push / SpMV with halo wait / k_cg_update<3>)
+  const bool fused3 = p2p && !fused_halo && mat_sell_ready(A) && H->bmask && env_int("IIFE_CG_FUSED3", 1) != 0 && !dbg_nohalo &&
+                      !dbg_nored && env_int("IIFE_KSP_PERSIST", 0) == 0;
+  RowPush rpush{};
+  HaloWait hwait{};
+  if (fused3) {
+    IIFE_LAUNCH(k_cg_fused3_begin, 1, 1, 0, H->dev_seq, w.sc);
+    rpush.n_brow = H->n_brow;
+    rpush.brow = H->brow;
+    rpush.bptr = H->bptr;
+    rpush.bpeer = H->bpeer;
+    rpush.bdst = H->bdst;
+    rpush.bmask = H->bmask;
+    for (int q = 0; q < P2P_MAX_RANKS; ++q) {
+      rpush.pt.xbuf[q] = H->peer_xbuf[q];
+      rpush.pt.mbox[q] = H->peer_mbox[q];
+      rpush.pt.dst_start[q] = H->dst_start[q];
+    }
+    rpush.me = H->me;
+    rpush.nranks = H->nranks;
+    rpush.send_mask = H->send_mask;
+    rpush.seq_base = H->dev_seq;
+    rpush.counter = H->p2p_counter;
+    hwait.flags = H->mbox->halo_flag;
+    hwait.seq_base = H->dev_seq;
+    hwait.nranks = H->nranks;
+    hwait.recv_mask = H->recv_mask;
+    hwait.err = H->p2p_err;
+  }
   // EXPERIMENTAL (ksp_persist.cuh, off by default): one cooperative kernel per chunk of iterations
   bool persist = false;
   CgPersist pa{};
@@ -747,7 +887,18 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   }
   // NCCL calls inside the loop: keep to plain stream launches (no graph capture) in that case
   const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && (!dist || p2p) && !persist;
-  auto enqueue_iteration = [&]() -> int {
+  auto enqueue_iteration = [&](int k) -> int {
+    if (fused3) {
+      P2PRed prk = pr;
+      prk.k_off = k;
+      HaloWait hwk = hwait;
+      hwk.k_off = k;
+      IIFE_LAUNCH(k_cg_p_push, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl, w.hist, (long long)w.hist_len, prk, rpush);
+      IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl, &prk, &hwk));
+      IIFE_LAUNCH(k_cg_update<3>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
+                  w.hist, (long long)w.hist_len, prk);
+      return IIFE_OK;
+    }
     IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl);
     if (fused_halo) {
       IIFE_TRY(spmv_dot_halo_launch(A, H, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl,
@@ -813,7 +964,8 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     cudaError_t e = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
       int rc = IIFE_OK;
-      for (int k = 0; k < chunk && rc == IIFE_OK; ++k) rc = enqueue_iteration();
+      for (int k = 0; k < chunk && rc == IIFE_OK; ++k) rc = enqueue_iteration(k);
+      if (fused3 && rc == IIFE_OK) IIFE_LAUNCH(k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
       e = cudaStreamEndCapture(c.stream, &graph);
       if (rc == IIFE_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
       if (rc != IIFE_OK || e != cudaSuccess || !exec) {
@@ -848,7 +1000,8 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
       if (e != cudaSuccess) return set_err(IIFE_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
       c.launches += launches_per_chunk;
     } else {
-      for (int k = 0; k < chunk; ++k) IIFE_TRY(enqueue_iteration());
+      for (int k = 0; k < chunk; ++k) IIFE_TRY(enqueue_iteration(k));
+      if (fused3) IIFE_LAUNCH(k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
       IIFE_CUDA(cudaGetLastError());
     }
     IIFE_CUDA(cudaMemcpyAsync(hf[slot].fl, w.fl, sizeof(int) * F_COUNT, cudaMemcpyDeviceToHost, c.stream));

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "p2p_dev.cuh"
 #include <string.h>
+#include <algorithm>
 
 namespace iife {
 
@@ -184,6 +185,43 @@ int iife_halo_p2p_attach(iife_halo H_, const void *all_handles, const int64_t *d
   IIFE_CUDA(cudaMalloc((void **)&H->send_off_dev, off.size() * sizeof(int)));
   if (!peer.empty()) IIFE_CUDA(cudaMemcpy(H->send_peer, peer.data(), peer.size(), cudaMemcpyHostToDevice));
   IIFE_CUDA(cudaMemcpy(H->send_off_dev, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // push plan by owned row (three-kernel CG iteration): invert send_idx
+  {
+    std::vector<int> idx((size_t)H->total_send);
+    if (H->total_send) IIFE_CUDA(cudaMemcpy(idx.data(), H->send_idx, idx.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    struct Ent { int row; unsigned char peer; long long dst; };
+    std::vector<Ent> ent((size_t)H->total_send);
+    for (int64_t k = 0; k < H->total_send; ++k) {
+      const int q = peer[(size_t)k];
+      ent[(size_t)k] = {idx[(size_t)k], (unsigned char)q, (long long)H->dst_start[q] + (k - H->send_off[q])};
+    }
+    std::stable_sort(ent.begin(), ent.end(), [](const Ent &a, const Ent &b) { return a.row < b.row; });
+    std::vector<int> brow, bptr;
+    std::vector<unsigned char> bpeer(ent.size());
+    std::vector<long long> bdst(ent.size());
+    std::vector<unsigned int> bmask((size_t)(H->n_owned + 31) / 32 + 1, 0u);
+    for (size_t k = 0; k < ent.size(); ++k) {
+      if (k == 0 || ent[k].row != ent[k - 1].row) {
+        brow.push_back(ent[k].row);
+        bptr.push_back((int)k);
+        bmask[(size_t)ent[k].row >> 5] |= 1u << (ent[k].row & 31);
+      }
+      bpeer[k] = ent[k].peer;
+      bdst[k] = ent[k].dst;
+    }
+    bptr.push_back((int)ent.size());
+    H->n_brow = (int)brow.size();
+    IIFE_CUDA(cudaMalloc((void **)&H->brow, (brow.size() + 1) * sizeof(int)));
+    IIFE_CUDA(cudaMalloc((void **)&H->bptr, bptr.size() * sizeof(int)));
+    IIFE_CUDA(cudaMalloc((void **)&H->bpeer, bpeer.size() + 1));
+    IIFE_CUDA(cudaMalloc((void **)&H->bdst, (bdst.size() + 1) * sizeof(long long)));
+    IIFE_CUDA(cudaMalloc((void **)&H->bmask, bmask.size() * sizeof(unsigned int)));
+    if (!brow.empty()) IIFE_CUDA(cudaMemcpy(H->brow, brow.data(), brow.size() * sizeof(int), cudaMemcpyHostToDevice));
+    IIFE_CUDA(cudaMemcpy(H->bptr, bptr.data(), bptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!bpeer.empty()) IIFE_CUDA(cudaMemcpy(H->bpeer, bpeer.data(), bpeer.size(), cudaMemcpyHostToDevice));
+    if (!bdst.empty()) IIFE_CUDA(cudaMemcpy(H->bdst, bdst.data(), bdst.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    IIFE_CUDA(cudaMemcpy(H->bmask, bmask.data(), bmask.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+  }
   H->p2p = true;
   return IIFE_OK;
 }

@@ -18,8 +18,32 @@ struct P2PRed {
   int me, nranks;
   Mailbox *mbox;                 // my mailbox
   Mailbox *peer[P2P_MAX_RANKS];  // everybody's mailbox (peer mappings)
-  const unsigned long long *iter;  // device iteration counter: reductions 2*iter+1 (delta) and 2*iter+2 (z.r, z.z)
+  const unsigned long long *iter;  // device iteration counter: reductions 2*it+1 (delta) and 2*it+2 (z.r, z.z), it = *iter + k_off
   int *err;
+  int k_off;                     // iteration index inside a graph-captured chunk (the counter moves once per chunk)
+};
+
+// SpMV prologue of the three-kernel CG iteration: wait until the ghost entries of exchange *seq_base + k_off + 1 arrived
+struct HaloWait {
+  const unsigned long long *flags;     // my mailbox's halo_flag[] (nullptr: no wait)
+  const unsigned long long *seq_base;  // device halo sequence counter (moves once per chunk)
+  int k_off, nranks;
+  unsigned int recv_mask;
+  int *err;
+};
+
+// boundary rows of p and where they go (Halo::brow...)
+struct RowPush {
+  int n_brow;
+  const int *brow, *bptr;
+  const unsigned char *bpeer;
+  const long long *bdst;
+  const unsigned int *bmask;
+  PeerTable pt;
+  int me, nranks;
+  unsigned int send_mask;
+  const unsigned long long *seq_base;  // halo sequence counter
+  unsigned int *counter;               // CTAs that finished pushing
 };
 
 __device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v) {

@@ -173,7 +173,7 @@ k_spmv_dot(const int *__restrict__ rowptr, const int *__restrict__ colind, const
     }
     if (pr.enabled) {  // row-partitioned solver: hand the partial to every rank (no wait here)
       __syncthreads();
-      p2p_push(pr, 2ull * (*pr.iter) + 1ull, &s_sum, 1, threadIdx.x);
+      p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 1ull, &s_sum, 1, threadIdx.x);
     }
   }
 }
@@ -337,10 +337,15 @@ __global__ void IIFE_SELL_BOUNDS
 k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr, const int *__restrict__ sell_col,
             const double *__restrict__ sell_val, int64_t n_rows, int64_t n_slices, const double *__restrict__ x, double *__restrict__ y,
             double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *__restrict__ counter,
-            const int *__restrict__ flag, P2PRed pr) {
+            const int *__restrict__ flag, P2PRed pr, HaloWait hw) {
   if (flag && *flag != 0) return;  // converged: the rest of the enqueued chunk is a row of no-ops
   __shared__ double red[32];
   __shared__ bool is_last;
+  if (hw.flags) {  // three-kernel CG iteration: the neighbours' k_cg_p_push stores the ghost entries of x
+    const int q = threadIdx.x;
+    if (q < hw.nranks && ((hw.recv_mask >> q) & 1u)) spin_until(hw.flags + q, *hw.seq_base + (unsigned long long)hw.k_off + 1ull, hw.err);
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -375,7 +380,7 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr,
       }
       if (pr.enabled) {  // row-partitioned solver: hand the partial to every rank (no wait here)
         __syncthreads();
-        p2p_push(pr, 2ull * (*pr.iter) + 1ull, &s_sum, 1, threadIdx.x);
+        p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 1ull, &s_sum, 1, threadIdx.x);
       }
     }
   }
@@ -492,7 +497,7 @@ k_spmv_sell_halo(const int *__restrict__ sell_ptr, const int *__restrict__ sell_
     }
     if (pr.enabled) {
       __syncthreads();
-      p2p_push(pr, 2ull * (*pr.iter) + 1ull, &s_sum, 1, threadIdx.x);
+      p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 1ull, &s_sum, 1, threadIdx.x);
     }
   }
 }
@@ -571,7 +576,7 @@ k_vec_dot(const double *__restrict__ x, const double *__restrict__ y, int64_t n,
     }
     if (pr.enabled) {
       __syncthreads();
-      p2p_push(pr, 2ull * (*pr.iter) + 1ull, &s_sum, 1, threadIdx.x);
+      p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 1ull, &s_sum, 1, threadIdx.x);
     }
   }
 }
@@ -606,15 +611,17 @@ static int sell_unroll() {
 }
 
 static int launch_sell(const Mat *A, bool dot, const double *x, double *y, double *dot_out, double *partials,
-                       unsigned int *counter, const int *flag, const P2PRed *red_in = nullptr) {
+                       unsigned int *counter, const int *flag, const P2PRed *red_in = nullptr, const HaloWait *hw_in = nullptr) {
   P2PRed pr{};
   if (red_in) pr = *red_in;
+  HaloWait hw{};
+  if (hw_in) hw = *hw_in;
   int64_t need = (A->sell_slices + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
 #define SELL_GO(D, UU)                                                                                              \
   {                                                                                                                 \
     int g = resident_grid(k_spmv_sell<D, UU>, need);                                                                \
     IIFE_LAUNCH((k_spmv_sell<D, UU>), g, SPMV_THREADS, 0, A->sell_ptr, A->sell_cptr, A->sell_col, A->sell_val, A->n_rows, \
-                A->sell_slices, x, y, dot_out, partials, counter, flag, pr);                                        \
+                A->sell_slices, x, y, dot_out, partials, counter, flag, pr, hw);                                    \
   }
   int u = sell_unroll();
   if (dot) {
@@ -791,6 +798,7 @@ int mat_ensure_sell(Mat *A) {
 }
 
 static bool sell_ready(const Mat *A) { return A->sell_state == 1 && A->sell_vals_valid; }
+bool mat_sell_ready(const Mat *A) { return sell_ready(A); }
 
 int spmv_pick_lpr(const Mat *A) {
   double mean = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
@@ -847,8 +855,10 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
 }
 
 int spmv_dot_launch(const Mat *A, const double *p, double *w, double *dot_out, double *partials,
-                    unsigned int *counter, const int *flag, const P2PRed *red) {
+                    unsigned int *counter, const int *flag, const P2PRed *red, const HaloWait *hw) {
+  if (hw && !sell_ready(A)) return set_err(IIFE_ERR_STATE, "the in-kernel halo wait needs the SELL operator copy");
   if (sell_ready(A)) {
+    if (hw) return launch_sell(A, true, p, w, dot_out, partials, counter, flag, red, hw);
     // dot fused into the SpMV (default since the kernel has 64 registers: 407 -> 395 us per CG iteration);
     // IIFE_SELL_FUSED_DOT=0 selects the plain SpMV followed by the dot kernel
     static const bool fused = !(getenv("IIFE_SELL_FUSED_DOT") && atoi(getenv("IIFE_SELL_FUSED_DOT")) == 0);

@@ -23,10 +23,7 @@ CPU tensors with gloo in the tests); the per-call hot work is in the CUDA librar
 from __future__ import annotations
 
 import ctypes
-import json
 import os
-import sys
-import time
 
 import numpy as np
 import torch
@@ -415,170 +412,3 @@ class DistExtraction:
             if err.value:
                 raise RuntimeError("peer-memory exchange timed out (a rank did not arrive)")
         return core.KSPInfo(int(res.iterations), int(res.reason), float(res.rnorm), float(res.rnorm0), np.zeros(0))
-
-
-# --------------------------------------------------------------------------------------------------
-# bench (N > 1): strong scaling of the S1 cube, launched by torchrun
-# --------------------------------------------------------------------------------------------------
-def bench_distributed(args, I, stream, peak, peak_src, metric, unit):
-    from . import synthetic
-    from .core import synth_cube
-
-    rank, world = _world()
-    dev = torch.device("cuda", torch.cuda.current_device())
-    init_comm()
-    N = args.cells
-    sz = synthetic.cube_sizes(N)
-    n_f, n_b = sz["n_f"], sz["n_b"]
-    nnzA, nnzM, nnzC = synthetic.cube_nnz(N)
-    fpart = row_partition(n_f, world)
-    f0, f1 = int(fpart[rank]), int(fpart[rank + 1])
-    b_f = torch.empty(f1 - f0, dtype=torch.float64, device=dev)
-    A, M = synth_cube(N, 1.0, f0, f1, b_f=b_f)
-    I.sync()
-
-    def tensors_of(mat):
-        n_rows, _, nnz = mat.info()
-        rp = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
-        ci = torch.empty(nnz, dtype=torch.int32, device=dev)
-        v = torch.empty(nnz, dtype=torch.float64, device=dev)
-        check(lib.iife_mat_get_csr(mat.handle, ctypes.c_void_p(rp.data_ptr()), ctypes.c_void_p(ci.data_ptr()),
-                                   ctypes.c_void_p(v.data_ptr()), 4, I.MEM_DEVICE))
-        I.sync()
-        return rp, ci, v
-
-    A_t, M_t = tensors_of(A), tensors_of(M)
-    del A, M
-    t0 = time.perf_counter()
-    ex = DistExtraction(n_f, n_b, M_t, A_t)
-    ex.numeric(A_t[2])
-    I.sync()
-    t_setup = time.perf_counter() - t0
-    x = torch.zeros(ex.n_owned, dtype=torch.float64, device=dev)
-    state = {}
-
-    debug = bool(os.environ.get("IIFE_BENCH_DEBUG"))
-
-    def step():
-        if debug:
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            ev[0].record(stream)
-        ex.numeric(A_t[2])
-        if debug:
-            ev[1].record(stream)
-        bb = ex.rhs(b_f)
-        x.zero_()
-        if debug:
-            ev[2].record(stream)
-        state["info"] = ex.solve(bb, x)
-        if debug:
-            ev[3].record(stream)
-            torch.cuda.synchronize()
-            if rank == 0:
-                print(f"[step r0] numeric {ev[0].elapsed_time(ev[1]):.2f} ms, rhs {ev[1].elapsed_time(ev[2]):.2f} ms, "
-                      f"cg {ev[2].elapsed_time(ev[3]):.2f} ms ({state['info'].iterations} its)", file=sys.stderr)
-
-    def barrier():
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    I.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-    from bench import ClockSampler
-
-    with ClockSampler(torch.cuda.current_device()) as clocks:
-        barrier()
-        e0.record(stream)
-        for _ in range(args.steps):
-            step()
-        e1.record(stream)
-        barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    launches = I.launch_count()
-    ms_step = float(ms.item()) / args.steps
-    info = state["info"]
-    # SpMV of the local operator block (roofline of the dominant kernel, per GPU)
-    n_loc = ex.n_owned
-    n_ext = n_loc + int(ex.ghost_ids.numel())
-    xs = torch.ones(n_ext, dtype=torch.float64, device=dev)
-    ys = torch.empty(n_loc, dtype=torch.float64, device=dev)
-    nnz_loc = ex.C_op.nnz
-    ex.C_op.spmv(xs, ys)
-    torch.cuda.synchronize()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record(stream)
-    for _ in range(20):
-        ex.C_op.spmv(xs, ys)
-    s1.record(stream)
-    torch.cuda.synchronize()
-    t_spmv = s0.elapsed_time(s1) / 20
-    B_spmv = 12 * nnz_loc + 4 * (n_loc + 1) + 8 * n_ext + 8 * n_loc
-    # ---- end to end at N GPUs through DistExtraction (its public per-step API takes the VALUES of this rank's rows of
-    # A_f and its block of b_f: the pattern was routed once at setup, as PETSc's MPIAIJ assembly reuses its layout):
-    # every step uploads them from pinned host memory and brings this rank's block of u_b back
-    e2e = None
-    if not getattr(args, "no_e2e", False):
-        try:
-            hv = torch.empty(A_t[2].numel(), dtype=torch.float64).pin_memory()
-            hb = torch.empty(b_f.numel(), dtype=torch.float64).pin_memory()
-            hx = torch.empty(ex.n_owned, dtype=torch.float64).pin_memory()
-            hv.copy_(A_t[2])
-            hb.copy_(b_f)
-            torch.cuda.synchronize()
-
-            def e2e_step():
-                A_t[2].copy_(hv, non_blocking=True)
-                b_f.copy_(hb, non_blocking=True)
-                ex.numeric(A_t[2])
-                bb = ex.rhs(b_f)
-                x.zero_()
-                ex.solve(bb, x)
-                hx.copy_(x, non_blocking=True)
-                torch.cuda.synchronize()
-
-            n_e2e = max(1, min(args.steps, getattr(args, "e2e_steps", 3)))
-            e2e_step()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(n_e2e):
-                e2e_step()
-            barrier()
-            dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            h2d = torch.tensor([float(hv.numel() * 8 + hb.numel() * 8), float(hx.numel() * 8)], dtype=torch.float64, device=dev)
-            dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
-            e2e = {"value": n_f / float(dt.item()) / 1e6, "unit": unit, "h2d_bytes_per_step": int(h2d[0].item()),
-                   "d2h_bytes_per_step": int(h2d[1].item()), "ms_per_step": float(dt.item()) * 1e3, "steps": n_e2e,
-                   "api": "iife_b200.dist.DistExtraction.numeric/rhs/solve: values of A_f and b_f from pinned host memory "
-                          "on every rank (pattern routed once at setup), u_b back to the host"}
-            del hv, hb, hx
-        except Exception as exc:  # the device-resident line must survive
-            e2e = {"error": str(exc)[:200]}
-    if rank == 0:
-        value = n_f / (ms_step * 1e-3) / 1e6
-        achieved = B_spmv / (t_spmv * 1e-3) / 1e9
-        line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"BASELINE config 5: synthetic S1 fitted cube N_b={N}, row-partitioned", "n_f": n_f,
-                       "n_b": n_b, "nnz_A_f": nnzA, "nnz_M": nnzM, "nnz_A_b": nnzC,
-                       "ksp": "cg+jacobi rtol=1e-8 atol=1e-9 zero guess", "cg_iterations": info.iterations,
-                       "cg_reason": info.reason_name, "setup_plus_first_numeric_ms": t_setup * 1e3,
-                       "parallelism": f"row blocks over {world} GPUs: ghost rows (PtAP), halo + allreduce (CG) via NCCL",
-                       "l2": "inputs larger than L2 (no flush)"},
-            "clocks": clocks.summary(),
-            "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_spmv_sell (local block of A_b, per GPU)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": B_spmv, "launch_ms": t_spmv},
-            "cpu_baseline": None,
-        }
-        print(json.dumps(line))
-    dist.barrier()

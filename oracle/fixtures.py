@@ -121,3 +121,37 @@ def seeded_spd_values(rowptr, colind, seed=0, skew=0.0):
 
 def read_cell_nodes(path):
     return np.loadtxt(path, delimiter=",", dtype=np.int64, ndmin=2)
+
+
+def fullsize_case(g, values_seed=0):
+    """(A_f, M, b_f) of a BASELINE config 1-4 at its named size from a tests/golden/full/*_inputs.npz dictionary
+    (tests/golden/make_fullsize_inputs.py): the foreground surrogate SURVEY.md §8d specifies per config, assembled from
+    the stored mesh arrays.  ``values_seed`` reseeds the value generator of the seeded cases (config 4's value updates)."""
+    import scipy.sparse as sp
+
+    from .oracle import CSR
+
+    kind = str(g["kind"])
+    pts, cells, mat = g["points"], g["cells"].astype(np.int64), g["material"].astype(np.float64)
+    if kind == "p1":
+        A, b = p1_operator(pts, cells, mat)
+    elif kind == "elasticity":
+        A, b = p1_elasticity(pts, cells, mat)
+    elif kind == "p1x3":
+        A1, _ = p1_operator(pts, cells, mat)
+        S = A1.to_scipy()
+        S.data[:] = 1.0
+        blk = sp.kron(S, np.ones((3, 3)), format="csr")
+        blk.sort_indices()
+        rp, ci = blk.indptr.astype(np.int64), blk.indices.astype(np.int32)
+        A = CSR(blk.shape[0], blk.shape[1], rp, ci, seeded_spd_values(rp, ci, seed=values_seed, skew=0.1))
+        b = np.cos(np.arange(blk.shape[0]) * 0.37)
+    elif kind == "p2":
+        n_f = int(g["n_f"])
+        rp, ci = p2_pattern(g["cell_nodes"].astype(np.int64), n_f)
+        A = CSR(n_f, n_f, rp, ci, seeded_spd_values(rp, ci, seed=values_seed))
+        b = np.sin(np.arange(n_f) * 0.11) + 0.5
+    else:
+        raise ValueError(kind)
+    M = CSR(int(g["n_f"]), int(g["n_b"]), g["M_rowptr"], g["M_colind"], g["M_val"])
+    return A, M, b

@@ -1,0 +1,105 @@
+"""Wall time per call of the reference-facing API on BASELINE configs 1-4 at their named sizes (tests/golden/full),
+next to the CPU oracle (the restatement of the reference's PETSc path; parity unpinned).  These sizes (n_b <= 52 k) are
+launch-latency bound on a B200: the figure of merit is wall time per call, cold symbolic phase included.
+usage (GPU box): python scripts/configs_1_4.py > gpurun_out/configs_1_4.md"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "interpolation-based-immersed-fea_b200"))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+import iife_b200 as I
+from InterpolationBasedImmersedFEA import common as api
+from oracle import fixtures as fx
+from oracle import oracle as O
+
+O.build()
+threads = max(1, len(os.sched_getaffinity(0)))
+O.set_threads(min(threads, int(os.environ.get("ORACLE_THREADS", "8"))))
+
+
+def best(fn, reps=5):
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return min(ts) * 1e3
+
+
+rows = []
+for name, method in (("cfg1", "gmres"), ("cfg2", "gmres"), ("cfg3", "gmres"), ("cfg4", "gmres")):
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "full", name + "_inputs.npz")))
+    A, M, b = fx.fullsize_case(g)
+    n_f, n_b = A.n_rows, M.n_cols
+    Mh = api.CSRMat((n_f, n_b), M.rowptr.astype(np.int32), M.colind, M.val)
+    Mh.device()  # M is read once per run in the reference (readExOp) and kept
+
+    def extract_fresh():
+        Ah = api.CSRMat((n_f, n_f), A.rowptr.astype(np.int32), A.colind, A.val)  # a fresh assemble(): new host object
+        return api.assembleLinearSystemBackground(Ah, api.Vec(b), Mh)
+
+    I.plan_cache_clear()
+    I.sync()
+    t0 = time.perf_counter()
+    A_b, b_b = extract_fresh()  # cold: symbolic + template plan + numeric
+    _ = A_b.val
+    t_cold = (time.perf_counter() - t0) * 1e3
+    t_warm = best(lambda: extract_fresh()[0].device())  # plan cached: upload + numeric
+    Ah = api.CSRMat((n_f, n_f), A.rowptr.astype(np.int32), A.colind, A.val)
+    Ah.device()
+
+    def extract_values():
+        Ah.set_values(A.val)
+        return api.assembleLinearSystemBackground(Ah, api.Vec(b), Mh)
+
+    t_vals = best(lambda: extract_values()[0].device())
+    mi = 300
+
+    def solve():
+        u = api.Vec(np.zeros(n_b))
+        api.solveKSP(A_b, b_b, u, method=method, PC="jacobi", max_it=mi, monitor=False)
+
+    solve()
+    t_solve = best(solve, 3)
+    its, reason = api.last_ksp_info.iterations, api.last_ksp_info.reason_name
+    Co = O.AT_R_A(M, A)
+    bo = O.AT_x(M, b)
+    t_cpu_e = best(lambda: (O.AT_R_A(M, A), O.AT_x(M, b)), 3)
+    t_cpu_s = best(lambda: O.solve_ksp(Co, bo, method=method, max_it=mi), 2)
+    rows.append((name, str(g["mesh_dir"]), int(g["nfields"]), n_f, n_b, A.nnz, Co.nnz, t_cold, t_warm, t_vals, t_cpu_e, method, its,
+                 reason, t_solve, t_cpu_s))
+    if name == "cfg4":  # 66 value updates on one plan + GMRES each (demos/tg_vortex.py)
+        vals = [fx.seeded_spd_values(A.rowptr, A.colind, seed=s, skew=0.1) for s in range(4)]
+        I.sync()
+        t0 = time.perf_counter()
+        for s in range(66):
+            Ah.set_values(vals[s % 4])
+            Ab, bb = api.assembleLinearSystemBackground(Ah, api.Vec(b), Mh)
+            u = api.Vec(np.zeros(n_b))
+            api.solveKSP(Ab, bb, u, method="gmres", PC="jacobi", max_it=mi, monitor=False)
+        t_loop = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        for s in range(6):
+            As = O.CSR(n_f, n_f, A.rowptr, A.colind, vals[s % 4])
+            Cs = O.AT_R_A(M, As)
+            O.solve_ksp(Cs, O.AT_x(M, b), method="gmres", max_it=mi)
+        t_loop_cpu = (time.perf_counter() - t0) * 1e3 * 11.0
+        loop = (t_loop, t_loop_cpu)
+
+print("# BASELINE configs 1-4 at their named sizes: wall time per call (ms)\n")
+print(f"`python scripts/configs_1_4.py` on 1 x B200; CPU = oracle port with {min(threads, 8)} threads (not PETSc).  extract = "
+      "`assembleLinearSystemBackground` (AT_R_A + AT_x) through the mirror with host CSR arrays: **cold** = first call "
+      "(symbolic phase, template plan, uploads), **warm** = new host matrix object on a cached plan (full upload + numeric), "
+      "**values** = `CSRMat.set_values` on a kept matrix (values-only upload + numeric).  solve = `solveKSP(method, 'jacobi', "
+      "max_it=300)`.\n")
+print("| config | mesh | fields | n_f | n_b | nnz(A_f) | nnz(A_b) | extract cold | warm | values | CPU extract | solve | its | reason | GPU solve | CPU solve |")
+print("|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|---|---:|---:|")
+for r in rows:
+    print(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]} | {r[4]} | {r[5]} | {r[6]} | {r[7]:.2f} | {r[8]:.2f} | {r[9]:.2f} | {r[10]:.2f} | {r[11]} | {r[12]} | "
+          f"{r[13]} | {r[14]:.2f} | {r[15]:.2f} |")
+print(f"\nconfig 4 loop (66 value updates on one plan + GMRES each, demos/tg_vortex.py): GPU {loop[0]:.1f} ms total = "
+      f"{loop[0] / 66:.2f} ms per step; CPU oracle {loop[1]:.0f} ms (6 steps timed, scaled to 66).")

@@ -329,6 +329,26 @@ def test_ksp_matches_oracle(iife, oracle, method):
         assert np.linalg.norm(x - ro.x) <= SOL_TOL * np.linalg.norm(ro.x)
 
 
+@pytest.mark.parametrize("method", ["cg", "gmres"])
+def test_ksp_zero_rhs_nonzero_guess(iife, oracle, method):
+    """Homogeneous system with a nonzero guess: KSPConvergedDefault falls back to the initial residual norm as the
+    reference norm (`if (!snorm) snorm = rnorm`), so the solve iterates to zero instead of stopping at iteration 0
+    with DIVERGED_DTOL."""
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, _ = assemble_cube(4)
+    C = oracle.AT_R_A(M, A)
+    b = np.zeros(C.n_rows)
+    x0 = np.random.default_rng(5).standard_normal(C.n_rows)
+    ro = oracle.solve_ksp(C, b, x0=x0.copy(), method=method, rtol=1e-8, atol=1e-50, hist_len=400)
+    assert ro.reason == 2 and ro.iterations > 3
+    x = x0.copy()
+    kt = iife.KSP_CG if method == "cg" else iife.KSP_FGMRES
+    info = iife.ksp_solve(dmat(iife, C), b, x, kt, iife.PC_JACOBI, rtol=1e-8, atol=1e-50, hist_len=400)
+    assert info.reason == ro.reason and abs(info.iterations - ro.iterations) <= 1
+    assert np.linalg.norm(x) <= 1e-6 * np.linalg.norm(x0)
+
+
 def test_ksp_singular_rows_and_nonzero_guess(iife, oracle):
     """A_b of real data has structurally empty rows (unsupported background functions): Jacobi maps the
     zero diagonal to 1 and those unknowns keep their initial value."""
@@ -577,6 +597,62 @@ def test_trim_nodes_and_newton_through_the_mirror(iife, oracle, capsys):
                                  monitorNewtonConvergence=False, zero_vec=list(ids))
     assert np.linalg.norm(u_p.array + ro.x) <= 1e-6 * np.linalg.norm(ro.x)
     assert np.allclose(u_f.array, oracle.spmv(Mo, u_p.array), rtol=0, atol=1e-10 * np.abs(u_f.array).max())
+
+
+def test_solve_nonlinear_device_loop(iife, oracle, capsys):
+    """solveNonlinear (reference common.py:404-480) with the assembly callback: a mildly nonlinear problem
+    R(u_f) = A_f u_f + c u_f^3 - f on the cube, Newton on the background space.  The iterate stays on the GPU; every
+    iteration hands back the SAME CSRMat after set_values, so the PtAP plan is reused (one symbolic phase in total).
+    Checked against the same loop run with the oracle."""
+    from InterpolationBasedImmersedFEA import common as api
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, f = assemble_cube(4)
+    n_f, n_b = A.n_rows, M.n_cols
+    c = 50.0
+    diag_pos = np.array([A.rowptr[i] + np.searchsorted(A.colind[A.rowptr[i]:A.rowptr[i + 1]], i) for i in range(n_f)])
+
+    def residual_and_jacobian_values(u):
+        R = oracle.spmv(A, u) + c * u ** 3 * np.abs(f) - f
+        Jv = A.val.copy()
+        Jv[diag_pos] += 3.0 * c * u ** 2 * np.abs(f)
+        return R, Jv
+
+    # oracle loop (host)
+    u_b = np.zeros(n_b)
+    for it in range(12):
+        R, Jv = residual_and_jacobian_values(oracle.spmv(M, u_b))
+        J = oracle.CSR(n_f, n_f, A.rowptr, A.colind, Jv)
+        dR = oracle.AT_R_A(M, J)
+        Rb = oracle.AT_x(M, R)
+        du = oracle.solve_ksp(dR, Rb, method="cg", rtol=1e-8, atol=1e-9).x
+        if np.linalg.norm(du) < 1e-9 * max(np.linalg.norm(u_b), 1e-30):
+            break
+        u_b = u_b - du
+    # mirror loop (device)
+    Mh = api.CSRMat((n_f, n_b), M.rowptr, M.colind, M.val)
+    Jh = api.CSRMat((n_f, n_f), A.rowptr, A.colind, A.val.copy())
+    u_f = api.Vec(np.zeros(n_f))
+    u_p = api.Vec(np.zeros(n_b))
+    calls = []
+
+    def assemble_cb(uf):
+        R, Jv = residual_and_jacobian_values(uf.array)
+        Jh.set_values(Jv)
+        calls.append(1)
+        return Jh, api.Vec(R)
+
+    iife.plan_cache_clear()
+    api.solveNonlinear(None, u_f, Mh, u_p, maxIters=20, relativeTolerance=1e-9, linear_method="cg",
+                       linear_preconditioner="jacobi", assemble_cb=assemble_cb)
+    out = capsys.readouterr().out
+    assert "Newton solver iteration: 0" in out and len(calls) >= 3
+    assert np.linalg.norm(u_p.array - u_b) <= 1e-7 * np.linalg.norm(u_b)
+    assert np.allclose(u_f.array, oracle.spmv(M, u_p.array), rtol=0, atol=1e-7 * np.abs(u_f.array).max())
+    # non-convergence ends the run like the reference's exit()
+    with pytest.raises(SystemExit):
+        api.solveNonlinear(None, api.Vec(np.zeros(n_f)), Mh, api.Vec(np.zeros(n_b)), maxIters=1, relativeTolerance=1e-30,
+                           linear_method="cg", assemble_cb=assemble_cb)
 
 
 def test_condition_estimate_matches_oracle(iife, oracle):

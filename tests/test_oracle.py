@@ -112,6 +112,20 @@ def test_ksp_against_dense_solve(oracle, method):
     assert h[-1] <= 1e-12 * h[0] * 1.0000001 or r.reason == 2
 
 
+@pytest.mark.parametrize("method", ["cg", "gmres"])
+def test_zero_rhs_with_nonzero_guess_iterates(oracle, method):
+    """KSPConvergedDefault: with b = 0 the reference norm falls back to the initial residual norm, so the solve
+    reduces the guess by rtol instead of stopping at iteration 0 with DIVERGED_DTOL (any residual >= dtol * 0)."""
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, _ = assemble_cube(3)
+    C = oracle.AT_R_A(M, A)
+    x0 = np.random.default_rng(2).standard_normal(C.n_rows)
+    r = oracle.solve_ksp(C, np.zeros(C.n_rows), x0=x0.copy(), method=method, rtol=1e-8, atol=1e-50)
+    assert r.reason == 2 and r.iterations > 3
+    assert np.linalg.norm(r.x) <= 1e-6 * np.linalg.norm(x0)
+
+
 def test_cg_textbook_iteration_by_iteration(oracle):
     """The C CG equals a line-by-line numpy transcription of SURVEY A.6 (preconditioned norm)."""
     rng = np.random.default_rng(5)
