@@ -266,9 +266,18 @@ def run_ours(args):
     x = torch.zeros(n_b, dtype=torch.float64, device="cuda")
     bb = torch.empty(n_b, dtype=torch.float64, device="cuda")
     t0 = time.perf_counter()
-    C, cached = I.ptap(M, A)  # cold call: builds the symbolic plan
+    C, cached = I.ptap(M, A)  # cold call: builds the symbolic plan and the template plan
     I.sync()
     t_cold = time.perf_counter() - t0
+    # the same cold call again (plan dropped): the first one also pays for first-touch cudaMalloc of the plan's buffers
+    # and lazy kernel loading, which the library's caching allocator / the driver then keep
+    del C
+    I.plan_cache_clear()
+    I.sync()
+    t0 = time.perf_counter()
+    C, cached = I.ptap(M, A)
+    I.sync()
+    t_cold_repeat = time.perf_counter() - t0
     state = {}
 
     debug = bool(os.environ.get("IIFE_BENCH_DEBUG"))
@@ -360,7 +369,8 @@ def run_ours(args):
     except Exception:
         pass
     achieved = B_spmv / (t_spmv * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_spmv_sell<false,4> (SELL-32 SpMV of A_b: the kernel of every CG iteration)",
+    roofline = {"bound": "hbm", "kernel": "k_spmv_sell<false,4> (SELL-32 SpMV of A_b; every CG iteration runs its dot-fused twin "
+                                          "k_spmv_sell<true,4>)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "frac_of_nominal_8000": achieved / 8000.0,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B_spmv, "launch_ms": t_spmv,
@@ -368,7 +378,8 @@ def run_ours(args):
                                  "solve_ms_samples": cg_times,
                                  "gbs": B_cg_it * max(info_cg.iterations, 1) / (t_cg * 1e-3) / 1e9,
                                  "frac": B_cg_it * max(info_cg.iterations, 1) / (t_cg * 1e-3) / 1e9 / peak},
-                "ptap_numeric": {"algorithmic_bytes": B_ptap_numeric, "ms": t_numeric,
+                "ptap_numeric": {"kernel": "k_ptap_numeric_tpl (template gather programs) + per-row kernels for the rest",
+                                 "algorithmic_bytes": B_ptap_numeric, "ms": t_numeric,
                                  "gbs": B_ptap_numeric / (t_numeric * 1e-3) / 1e9,
                                  "frac": B_ptap_numeric / (t_numeric * 1e-3) / 1e9 / peak}}
 
@@ -480,7 +491,8 @@ def run_ours(args):
         "config": {"workload": f"BASELINE config 5: synthetic S1 fitted cube N_b={N}", "n_f": n_f, "n_b": n_b,
                    "nnz_A_f": nnzA, "nnz_M": nnzM, "nnz_A_b": nnzC, "ksp": "cg+jacobi rtol=1e-8 atol=1e-9 zero guess",
                    "cg_iterations": info.iterations, "cg_reason": info.reason_name, "plan_cached": bool(state["cached"]),
-                   "cold_ptap_symbolic_plus_numeric_ms": t_cold * 1e3, "l2": "inputs larger than L2 (no flush)",
+                   "cold_ptap_symbolic_plus_numeric_ms": t_cold * 1e3, "cold_repeat_ms": t_cold_repeat * 1e3,
+                   "l2": "inputs larger than L2 (no flush)",
                    "parallelism": "1 GPU", "single_gpu": parity_scalars},
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }

@@ -22,8 +22,23 @@
 #include <algorithm>
 #include <list>
 #include <stdlib.h>
+#include <chrono>
 
 namespace iife {
+
+// IIFE_PLAN_DEBUG=1: wall time of the stages of the symbolic phase and of the template build (stderr)
+struct PlanTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  PlanTimer() : on(getenv("IIFE_PLAN_DEBUG") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx().stream);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[plan] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 constexpr int EMPTY = 0x7fffffff;
 constexpr unsigned HASH_MUL = 2654435761u;
@@ -89,6 +104,7 @@ struct Plan {
   size_t tp_blob_bytes = 0;
   long long *tp_blob_off = nullptr;
   int *tp_chunks = nullptr, *tp_rows = nullptr, *tp_rest_rows = nullptr;
+  int2 *tp_rowinfo = nullptr;  // per templated row: (start of its row of R, start of its row of A_b)
   int tp_s_cap = 0, tp_o1_cap = 0, tp_o2_cap = 0;
   double tp_use1 = 0.0, tp_use2 = 0.0;  // mean lane use of the two gather stages, weighted by rows
 };
@@ -746,6 +762,8 @@ static void tpl_free(Plan *P) {
   if (P->tp_blob_off) dev_free_t(P->tp_blob_off, (size_t)P->tp_n_tpl);
   if (P->tp_chunks) dev_free_t(P->tp_chunks, (size_t)P->tp_n_chunks * 3);
   if (P->tp_rows) dev_free_t(P->tp_rows, (size_t)P->tp_n_rows);
+  if (P->tp_rowinfo) dev_free_t(P->tp_rowinfo, (size_t)P->tp_n_rows);
+  P->tp_rowinfo = nullptr;
   if (P->tp_rest_rows) dev_free_t(P->tp_rest_rows, (size_t)P->tp_list_n);
   P->tp_blobs = nullptr;
   P->tp_blob_off = nullptr;
@@ -865,13 +883,16 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
   Tmp<int> sym_keys;  // global tables of the last symbolic level
   Tmp<unsigned long long> u64;
   std::vector<int> level_list_n(N_SYM_LEVELS, 0);
+  PlanTimer pt;
   do {
     if ((rc = mat_fingerprint(M, &P->fpM)) != IIFE_OK) break;
     if ((rc = mat_fingerprint(A, &P->fpA)) != IIFE_OK) break;
+    pt.lap("fingerprints");
     if (!R) {
       if ((rc = transpose_build(M, &P->MT, &P->mt_perm)) != IIFE_OK) break;
     } else if ((rc = mat_fingerprint(R, &P->fpR)) != IIFE_OK) break;
     Mat *Rm = R ? R : P->MT;
+    pt.lap("transpose of M");
     if ((rc = mean_nonempty_logG(A, &P->logG1)) != IIFE_OK) break;
     if ((rc = mean_nonempty_logG(M, &P->logG2)) != IIFE_OK) break;
     if ((rc = dev_alloc_t(&P->n1, (size_t)n_b)) != IIFE_OK) break;
@@ -978,6 +999,7 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
       work = h_ovf;
     }
     if (rc != IIFE_OK) break;
+    pt.lap("count pass");
 
     // ---- row pointers of C
     int64_t total = 0;
@@ -1027,6 +1049,7 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
       a.inter_rowptr = P->inter_rowptr;
       a.inter_col = P->inter_col;
     }
+    pt.lap("scans + slot plan sizes");
     // ---- fill pass: same traversal, same level per row, sorted columns written
     a.c_rowptr = P->c_rowptr;
     a.c_col = P->c_colind;
@@ -1054,6 +1077,7 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
     if ((rc = read_int(P->err_flag, &h_err)) != IIFE_OK) break;
     if (h_err) { rc = set_err(IIFE_ERR_STATE, "PtAP symbolic fill pass inconsistent with count pass (code %d)", h_err); break; }
 
+    pt.lap("fill pass");
     // ---- packed operand-row metadata for the slot kernel
     if (P->inter_total > 0 && !getenv("IIFE_PTAP_NOMETA")) {
       Mat *Rm2 = R ? R : P->MT;
@@ -1116,6 +1140,7 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
     }
     cudaError_t e = cudaStreamSynchronize(c.stream);
     if (e != cudaSuccess) rc = set_err(IIFE_ERR_CUDA, "PtAP symbolic: %s", cudaGetErrorString(e));
+    pt.lap("metadata + bins");
   } while (0);
   if (rc != IIFE_OK) {
     cudaStreamSynchronize(c.stream);
@@ -1188,6 +1213,7 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
   IIFE_TRY(spos.alloc((size_t)n));
   IIFE_TRY(head.alloc((size_t)n + 1));
   IIFE_TRY(run_of.alloc((size_t)n + 1));
+  PlanTimer pt;
   const int hgrid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)c.sm_count * 8);
   IIFE_LAUNCH(k_tpl_hash, hgrid, 256, 0, a, h1.p, h2.p);
   IIFE_LAUNCH(k_tpl_iota, grid_for(n), 256, 0, pos.p, (long long)n);
@@ -1200,6 +1226,7 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
     IIFE_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, h1.p, h1s.p, pos.p, spos.p, (int)n, 0, 64, c.stream));
     c.launches += 8;  // the passes of the library sort (plan build only, never in a numeric call)
   }
+  pt.lap("tpl: hash + sort");
   IIFE_LAUNCH(k_tpl_heads, grid_for(n), 256, 0, h1s.p, (long long)n, head.p);
   int64_t n_runs = 0;
   IIFE_TRY(exclusive_scan_i32(head.p, run_of.p, n, &n_runs));
@@ -1249,6 +1276,7 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
     IIFE_CUDA(cudaMemcpyAsync(raw.data(), raw_d.p, raw.size(), cudaMemcpyDeviceToHost, c.stream));
     IIFE_CUDA(cudaStreamSynchronize(c.stream));
   }
+  pt.lap("tpl: runs + extract");
   const size_t warp_budget = (size_t)env_int("IIFE_TPL_WARP_SMEM", 20 * 1024);
   std::vector<tpl::Program> progs((size_t)n_tpl);
   std::vector<int> valid((size_t)n_tpl, 0);
@@ -1260,7 +1288,7 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
     tpl_parse_raw(raw.data() + (size_t)t * TPLR_STRIDE, r);
     tpl::Program &pr = progs[(size_t)t];
     if (!tpl::compile(r, pr)) continue;
-    if (((size_t)pr.s_cap + pr.o1_cap + pr.o2_cap) * 8 + tpl::MAX_N0 * 4 > warp_budget) continue;
+    if (((size_t)pr.s_cap + pr.o1_cap + pr.o2_cap) * 8 + tpl::MAX_N0 * 16 > warp_budget) continue;
     valid[(size_t)t] = 1;
     ++n_valid;
     blob_off[(size_t)t] = (long long)blob_total;
@@ -1269,6 +1297,8 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
     o1_cap = std::max(o1_cap, pr.o1_cap);
     o2_cap = std::max(o2_cap, pr.o2_cap);
   }
+  pt.lap("tpl: host compile");
+  if (pt.on) fprintf(stderr, "[plan] templates: %d candidates, %d compiled\n", n_tpl, n_valid);
   if (n_valid == 0) return IIFE_OK;
   // buffers start on 16-byte boundaries
   s_cap = (s_cap + 1) & ~1;
@@ -1307,6 +1337,8 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
   IIFE_TRY(dev_alloc_t(&P->tp_rows, (size_t)n_t));
   IIFE_TRY(dev_alloc_t(&P->tp_rest_rows, (size_t)n));
   IIFE_LAUNCH(k_tpl_scatter, grid_for(n), 256, 0, list, tpl_of.p, spos.p, off_sorted.p, off_rest.p, (long long)n, P->tp_rows, P->tp_rest_rows);
+  IIFE_TRY(dev_alloc_t(&P->tp_rowinfo, (size_t)n_t));
+  IIFE_LAUNCH(k_tpl_rowinfo, grid_for(n_t), 256, 0, (const int *)P->tp_rows, (long long)n_t, a.mt_rowptr, a.c_rowptr, P->tp_rowinfo);
   IIFE_LAUNCH(k_tpl_ranges, (n_tpl + 255) / 256, 256, 0, sel_d.p, n_tpl, off_sorted.p, ranges_d.p);
   IIFE_CHECK_LAUNCH();
   std::vector<int> ranges((size_t)2 * n_tpl);
@@ -1338,6 +1370,7 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
   IIFE_CUDA(cudaMemcpyAsync(P->tp_blobs, blobs.data(), blob_total, cudaMemcpyHostToDevice, c.stream));
   IIFE_CUDA(cudaMemcpyAsync(P->tp_blob_off, blob_off.data(), (size_t)n_tpl * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
   IIFE_CUDA(cudaStreamSynchronize(c.stream));  // the host vectors above go out of scope
+  pt.lap("tpl: membership + lists");
   P->tp_rest5 = rest5;
   P->tp_rest6 = n_rest - rest5;
   P->tp_s_cap = s_cap;
@@ -1354,10 +1387,11 @@ static int tpl_launch(Plan *P, PtapArgs a) {
   t.chunks = P->tp_chunks;
   t.n_chunks = P->tp_n_chunks;
   t.rows = P->tp_rows;
+  t.rowinfo = P->tp_rowinfo;
   t.s_cap = P->tp_s_cap;
   t.o1_cap = P->tp_o1_cap;
   t.o2_cap = P->tp_o2_cap;
-  const size_t per_warp = (size_t)tpl::MAX_N0 * 4 + ((size_t)t.s_cap + t.o1_cap + t.o2_cap) * 8;
+  const size_t per_warp = (size_t)tpl::MAX_N0 * 16 + ((size_t)t.s_cap + t.o1_cap + t.o2_cap) * 8;
   const size_t smem_max = (size_t)(c.max_smem_optin ? c.max_smem_optin : 227 * 1024);
   int wpc = std::max(1, std::min(env_int("IIFE_TPL_WPC", 8), 32));
   while (wpc > 1 && per_warp * wpc > smem_max) wpc >>= 1;

@@ -250,6 +250,13 @@ __global__ void k_tpl_scatter(const int *__restrict__ rows, const int *__restric
   }
 }
 
+__global__ void k_tpl_rowinfo(const int *__restrict__ rows, long long n, const int *__restrict__ mt_rowptr,
+                              const int *__restrict__ c_rowptr, int2 *__restrict__ out) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; k < n; k += stride) out[k] = make_int2(mt_rowptr[rows[k]], c_rowptr[rows[k]]);
+}
+
 // out[2t], out[2t+1] = range of template t inside tpl_rows
 __global__ void k_tpl_ranges(const int *__restrict__ sel, int n_tpl, const int *__restrict__ off_sorted,
                              int *__restrict__ out) {
@@ -269,6 +276,7 @@ struct TplArgs {
   const int *chunks;          // [3 * n_chunks]: template, first row (index into rows), row count
   int n_chunks;
   const int *rows;            // templated rows, grouped by template, ascending inside a template
+  const int2 *rowinfo;        // per templated row: (start of its row of R, start of its row of A_b)
   int s_cap, o1_cap, o2_cap;  // per-warp buffer sizes (entries)
 };
 
@@ -318,34 +326,46 @@ __device__ __forceinline__ void tpl_gather(int S, const unsigned *__restrict__ p
   }
 }
 
-// pieces of split destinations: O[gd] += its extras, in order
-__device__ __forceinline__ void tpl_combine(int ng, const unsigned short *__restrict__ g, int n_dest, double *O, int lane) {
-  const unsigned short *gd = g, *gp = g + ng;
-  for (int k = lane; k < ng; k += 32) {
-    const int d = (int)gd[k];
-    double v = O[d];
-    for (int x = (int)gp[k]; x < (int)gp[k + 1]; ++x) v += O[1 + n_dest + x];
-    O[d] = v;
+// pieces of split destinations: round j adds the (j+1)-th piece of every split destination into it (distinct
+// destinations within a round: one lane each); g = ptr[nr + 1] then (destination, extra) index pairs
+__device__ __forceinline__ void tpl_combine(int nr, const unsigned short *__restrict__ g, double *O, int lane) {
+  const unsigned short *pairs = g + ((nr + 2) & ~1);  // the pair words are 4-byte aligned
+  for (int rd = 0; rd < nr; ++rd) {
+    const int e = (int)__ldg(g + rd + 1);
+    for (int k = (int)__ldg(g + rd) + lane; k < e; k += 32) {
+      const unsigned pr = __ldg((const unsigned *)pairs + k);  // two 16-bit indices
+      O[pr & 0xFFFFu] += O[pr >> 16];
+    }
+    __syncwarp();
   }
 }
 
-__global__ void __launch_bounds__(256) k_ptap_numeric_tpl(PtapArgs a, TplArgs t) {
+struct TplDesc {  // one operand row of stage 1: its weight R[i, j_q] and where its values start in A_f.val
+  double w;
+  int beg, pad;
+};
+
+#ifndef IIFE_TPL_MINBLOCKS
+#define IIFE_TPL_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, IIFE_TPL_MINBLOCKS) k_ptap_numeric_tpl(PtapArgs a, TplArgs t) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int wpc = blockDim.x >> 5;
-  // per warp: sbeg[MAX_N0] ints, S[s_cap], O1[o1_cap], O2[o2_cap] doubles
-  const size_t per_warp = (size_t)tpl::MAX_N0 * 4 + ((size_t)t.s_cap + t.o1_cap + t.o2_cap) * 8;
+  // per warp: desc[MAX_N0] (16 B each), S[s_cap], O1[o1_cap], O2[o2_cap] doubles
+  const size_t per_warp = (size_t)tpl::MAX_N0 * 16 + ((size_t)t.s_cap + t.o1_cap + t.o2_cap) * 8;
   unsigned char *base = smem + per_warp * wic;
-  int *sbeg = (int *)base;
-  double *S = (double *)(base + tpl::MAX_N0 * 4);
+  TplDesc *desc = (TplDesc *)base;
+  double *S = (double *)(base + tpl::MAX_N0 * 16);
   double *O1 = S + t.s_cap;
   double *O2 = O1 + t.o1_cap;
   const unsigned S_sh = (unsigned)__cvta_generic_to_shared(S);
   const unsigned O1_sh = (unsigned)__cvta_generic_to_shared(O1);
   const unsigned O2_sh = (unsigned)__cvta_generic_to_shared(O2);
-  if (lane == 0) {  // zero slots read by the padding steps
-    S[0] = 0.0;
-    O1[0] = 0.0;
+  const unsigned desc_sh = (unsigned)__cvta_generic_to_shared(desc);
+  if (lane < 16) {  // the dummy rows read by lanes whose program has ended (any finite value would do)
+    S[lane] = 0.0;
+    O1[lane] = 0.0;
   }
   __syncwarp();
   const double *__restrict__ a_val = a.a_val;
@@ -354,68 +374,76 @@ __global__ void __launch_bounds__(256) k_ptap_numeric_tpl(PtapArgs a, TplArgs t)
     const int tp = __ldg(t.chunks + 3 * ch), r0 = __ldg(t.chunks + 3 * ch + 1), cnt = __ldg(t.chunks + 3 * ch + 2);
     const unsigned char *blob = t.blobs + __ldg(t.blob_off + tp);
     const tpl::Header *h = (const tpl::Header *)blob;
-    const int n0 = h->n0, stg_steps = h->stg_steps, n1 = h->n1, n2 = h->n2, S1 = h->S1, S2 = h->S2;
+    const int n0 = h->n0, stg_steps = h->stg_steps, n2 = h->n2, S1 = h->S1, S2 = h->S2;
     const int ng1 = h->ng1, ng2 = h->ng2;
-    const unsigned short *stg = (const unsigned short *)(blob + h->off_stg);
+    const unsigned *stg = (const unsigned *)(blob + h->off_stg);
     const double *wt = (const double *)(blob + h->off_w);
     const unsigned *p1 = (const unsigned *)(blob + h->off_p1);
     const unsigned short *g1 = (const unsigned short *)(blob + h->off_g1);
     const double *c2 = (const double *)(blob + h->off_c2);
     const unsigned *p2 = (const unsigned *)(blob + h->off_p2);
     const unsigned short *g2 = (const unsigned short *)(blob + h->off_g2);
+    // the template's weights and this chunk's row descriptors: a two-deep software pipeline over the rows, so that
+    // the dependent loads (row info -> operand starts) of row r+1 are in flight while row r is computed
+    const bool has0 = lane < n0, has1 = lane + 32 < n0;
+    const double w0 = has0 ? __ldg(wt + lane) : 0.0, w1 = has1 ? __ldg(wt + lane + 32) : 0.0;
+    int2 ri_cur = __ldg(t.rowinfo + r0);
+    int2 ri_nxt = cnt > 1 ? __ldg(t.rowinfo + r0 + 1) : ri_cur;
+    int b0 = has0 ? __ldg(a.mt_abeg + ri_cur.x + lane) : 0, b1 = has1 ? __ldg(a.mt_abeg + ri_cur.x + lane + 32) : 0;
     for (int r = 0; r < cnt; ++r) {
-      const int i = __ldg(t.rows + r0 + r);
-      const int mtb = __ldg(a.mt_rowptr + i);
-      const int cb = __ldg(a.c_rowptr + i);
-      for (int q = lane; q < n0; q += 32) sbeg[q] = __ldg(a.mt_abeg + mtb + q);
+      const int cb = ri_cur.y;
+      if (has0) desc[lane] = TplDesc{w0, b0, 0};
+      if (has1) desc[lane + 32] = TplDesc{w1, b1, 0};
+      ri_cur = ri_nxt;
+      if (r + 2 < cnt) ri_nxt = __ldg(t.rowinfo + r0 + r + 2);
+      if (r + 1 < cnt) {
+        if (has0) b0 = __ldg(a.mt_abeg + ri_cur.x + lane);
+        if (has1) b1 = __ldg(a.mt_abeg + ri_cur.x + lane + 32);
+      }
       __syncwarp();
-      // ---- staging: S[1+p] = w[q] * A.val[beg[q] + e], 4 loads in flight per lane
+      // ---- staging: S[slot] = w[q] * A.val[beg[q] + e], 4 loads in flight per lane; the slots of a phase of 16 lanes lie
+      // in 16 different banks (edge colouring of the template compiler), as do the reads of stage 1.  A staging word is
+      // slot << 16 | q << 8 | e; desc[q] = (weight, start of the operand row) comes with one 16-byte shared load
       {
         int s = 0;
         for (; s + 4 <= stg_steps; s += 4) {
           unsigned m[4];
           double v[4], w[4];
 #pragma unroll
-          for (int b = 0; b < 4; ++b) m[b] = (unsigned)__ldg(stg + (s + b) * 32 + lane);
+          for (int b = 0; b < 4; ++b) m[b] = __ldg(stg + (s + b) * 32 + lane);
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             v[b] = 0.0;
             w[b] = 0.0;
             if (m[b] != tpl::STG_PAD) {
-              const unsigned q = m[b] >> 8;
-              v[b] = __ldg(a_val + sbeg[q] + (int)(m[b] & 255u));
-              w[b] = __ldg(wt + q);
+              double wq;
+              long long bp;  // (beg, pad)
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=d"(wq), "=l"(bp) : "r"(desc_sh + ((m[b] >> 4) & 0xFF0u)));
+              w[b] = wq;
+              v[b] = __ldg(a_val + (int)bp + (int)(m[b] & 255u));
             }
           }
 #pragma unroll
-          for (int b = 0; b < 4; ++b) S[1 + (s + b) * 32 + lane] = w[b] * v[b];
+          for (int b = 0; b < 4; ++b)
+            if (m[b] != tpl::STG_PAD) S[m[b] >> 16] = w[b] * v[b];
         }
         for (; s < stg_steps; ++s) {
-          const unsigned m = (unsigned)__ldg(stg + s * 32 + lane);
-          double v = 0.0, w = 0.0;
+          const unsigned m = __ldg(stg + s * 32 + lane);
           if (m != tpl::STG_PAD) {
-            const unsigned q = m >> 8;
-            v = __ldg(a_val + sbeg[q] + (int)(m & 255u));
-            w = __ldg(wt + q);
+            const TplDesc d = desc[(m >> 8) & 255u];
+            S[m >> 16] = d.w * __ldg(a_val + d.beg + (int)(m & 255u));
           }
-          S[1 + s * 32 + lane] = w * v;
         }
       }
       __syncwarp();
       // ---- stage 1: intermediate row
       tpl_gather<false>(S1, p1, nullptr, S_sh, O1_sh, lane);
       __syncwarp();
-      if (ng1) {
-        tpl_combine(ng1, g1, n1, O1, lane);
-        __syncwarp();
-      }
+      if (ng1) tpl_combine(ng1, g1, O1, lane);
       // ---- stage 2: output row
       tpl_gather<true>(S2, p2, c2, O1_sh, O2_sh, lane);
       __syncwarp();
-      if (ng2) {
-        tpl_combine(ng2, g2, n2, O2, lane);
-        __syncwarp();
-      }
+      if (ng2) tpl_combine(ng2, g2, O2, lane);
       for (int o = lane; o < n2; o += 32) a.c_val[cb + o] = O2[1 + o];
       __syncwarp();
     }

@@ -9,16 +9,29 @@
 // start.  Such rows share one template; everything that does not depend on A_f's values is precomputed once per
 // template on the host, where there is time to pack it well:
 //
-//   staging     S[1+p] = w[q_p] * A_f.val[beg[q_p] + e_p]       p over the T1 stage-1 terms (coalesced by operand row)
-//   stage 1     O1[f] = sum of S[src] over a lane's run of terms  (the intermediate row (R A_f)[i,:], never in HBM)
-//   stage 2     O2[f] = sum of coef * O1[src]                     (coef = the M value of the term)
+//   staging     S[slot_p] = w[q_p] * A_f.val[beg[q_p] + e_p]      p over the T1 stage-1 terms (coalesced by operand row)
+//   stage 1     O1[f] = sum of S[src] over a lane's run of terms    (the intermediate row (R A_f)[i,:], never in HBM)
+//   stage 2     O2[f] = sum of coef * O1[src]                       (coef = the M value of the term)
 //   write       A_b.val[row i] = O2[1..n2]
 //
 // Stages 1 and 2 are GATHERS: the terms of one destination are consecutive in one lane's program, accumulate in a
 // register and are stored once ("flush"); a destination with more terms than the step count S is split into
 // pieces that flush into extra slots and are added in a fixed order afterwards.  No shared-memory read-modify-write,
 // no privatised accumulator copies, no hashing, no column indices, no atomics; the sum order is fixed by the
-// program, so results are bit-reproducible.  Index 0 of S / O1 is a zero slot read by padding steps.
+// program, so results are bit-reproducible.  Words 0..15 of S / O1 are a dummy row read by lanes whose program has ended.
+//
+// Shared-memory banks.  A step reads 32 fp64 words; the hardware serves it in two phases of 16 lanes, each conflict
+// free iff its words lie in 16 distinct 8-byte banks (index mod 16).
+//   * Stage 1 reads every staged value exactly once, and the staging writes it exactly once, 16 consecutive terms
+//     per phase.  A term is therefore an EDGE between its write phase and its read phase; both have at most 16
+//     members, so by Koenig's theorem the edges of this bipartite multigraph can be coloured with 16 colours such
+//     that no phase sees a colour twice: colour = bank.  edge_colour_16 computes it (alternating-path recolouring) and
+//     the staged value of term p lives at S[16 + 16 * rank + colour]: stage-1 reads AND staging writes are conflict
+//     free for any program.
+//   * Stage 2 reads intermediate entries several times each (once per entry of the M row), so no such guarantee
+//     exists; the order of the terms inside a run and the order of a lane's runs are free, and a maximum bipartite
+//     matching (lanes x banks) per phase picks terms in distinct banks where it can, on a layout of the intermediate
+//     row that a few rounds of local search have adapted to the schedule.
 //
 // Plain C++ (no CUDA): included by ptap.cu.
 #pragma once
@@ -31,13 +44,13 @@ namespace iife {
 namespace tpl {
 
 constexpr int MAX_N0 = 64;     // operand rows of stage 1 (entries of R[i,:])
-constexpr int MAX_T1 = 1023;   // stage-1 product terms  (S index fits 13 bits after the byte scaling)
+constexpr int MAX_T1 = 1023;   // stage-1 product terms
 constexpr int MAX_N1 = 256;    // intermediate row entries
 constexpr int MAX_N2 = 256;    // output row entries
 constexpr int MAX_T2 = 4095;   // stage-2 product terms
-constexpr int MAX_OUT = 1023;  // destinations + extra slots of a stage (byte offset must fit 16 bits)
+constexpr int MAX_OUT = 1023;  // entries of an out buffer (byte offsets must fit 16 bits)
 constexpr uint32_t NO_FLUSH = 0xFFFFu;
-constexpr uint16_t STG_PAD = 0xFFFFu;
+constexpr uint32_t STG_PAD = 0xFFFFFFFFu;
 
 // what the device extracts for the representative row of a template
 struct Raw {
@@ -53,33 +66,38 @@ struct Raw {
 // 16-byte aligned sections inside one blob; all offsets in bytes from the start of the blob (= this header)
 struct Header {
   int n0, T1, stg_steps, n1, n2, S1, S2;
-  int ng1, nx1, ng2, nx2;
+  int ng1, nx1, ng2, nx2;  // ng = rounds of the combine pass, nx = extra slots
   int off_stg, off_w, off_p1, off_g1, off_c2, off_p2, off_g2;
-  int blob_bytes, pad;
+  int blob_bytes;
+  int ext1, ext2;  // index of the first extra slot in O1 / O2 (the destinations live below it)
+  int pad;
 };
-static_assert(sizeof(Header) == 80, "Header layout");
+static_assert(sizeof(Header) == 88, "Header layout");
 
 struct Term {
-  int dest;     // destination slot 0..n_dest-1
-  int src;      // index into the source buffer (already +1: 0 is the zero slot)
+  int dest;     // destination 0..n_dest-1
+  int src;      // LOGICAL source 0..n_src-1 (staged term p in stage 1, intermediate entry q in stage 2)
   double coef;  // stage 2 only
 };
 
-struct Packed {
+// a schedule: which term every lane processes at every step, and what it flushes afterwards
+struct Schedule {
   int S = 0, n_extra = 0;
-  std::vector<uint32_t> prog;  // [S*32]  low 16 bits: BYTE offset of the source entry; high 16: BYTE offset of the flush slot or NO_FLUSH
-  std::vector<double> coef;    // [S*32]  (stage 2)
-  std::vector<uint16_t> gd;    // [ng]    index (not bytes) of a split destination in the out buffer
-  std::vector<uint16_t> gptr;  // [ng+1]  its extras are out[1 + n_dest + gptr[g] .. gptr[g+1])
-  double lane_use = 0.0;       // terms / (32 S)
-  double wavefronts = 0.0;     // mean shared-memory phases per half-warp read (1.0 = conflict free)
+  std::vector<int> term;      // [S*32]  term index or -1 (padding)
+  std::vector<int> flush;     // [S*32]  logical out id (destination d, or n_dest + extra) or -1
+  std::vector<int> gd, gptr;  // split destinations: dest gd[g] += extras gptr[g] .. gptr[g+1]
+  double lane_use = 0.0;      // terms / (32 S)
 };
 
-// Bin-pack the destinations' term runs into 32 lane programs of S steps, S as small as possible.
-// Terms of a destination keep their given order (= ascending operand order, the order the reference's
-// row-wise Gustavson product adds them in).  Returns false if a destination has no term or the out buffer
-// would exceed MAX_OUT entries.
-inline bool pack_stage(int n_dest, const std::vector<Term> &terms, bool with_coef, Packed &out) {
+struct Piece {
+  int dest, first, count, index;  // terms by_dest[dest][first .. first+count), index-th piece of dest
+};
+
+// Bin-pack the destinations' term runs into 32 lane programs of S steps, S as small as possible, then order the
+// terms.  bank_of == nullptr: runs and terms in their given order (ascending operand order: the order the reference's
+// row-wise Gustavson product adds them in).  Otherwise bank_of[src] is the shared-memory bank of every logical source
+// and a maximum matching per phase avoids bank conflicts where it can.  Returns false if a destination has no term.
+inline bool build_schedule(int n_dest, const std::vector<Term> &terms, const int *bank_of, Schedule &out) {
   std::vector<std::vector<int>> by_dest((size_t)n_dest);
   for (size_t t = 0; t < terms.size(); ++t) {
     if (terms[t].dest < 0 || terms[t].dest >= n_dest) return false;
@@ -88,9 +106,6 @@ inline bool pack_stage(int n_dest, const std::vector<Term> &terms, bool with_coe
   for (int d = 0; d < n_dest; ++d)
     if (by_dest[(size_t)d].empty()) return false;
   const int N = (int)terms.size();
-  struct Piece {
-    int dest, first, count, index;  // terms by_dest[dest][first .. first+count), index-th piece of dest
-  };
   std::vector<Piece> pieces;
   std::vector<int> lane_of;  // per piece
   int S = std::max(1, (N + 31) / 32);
@@ -134,38 +149,46 @@ inline bool pack_stage(int n_dest, const std::vector<Term> &terms, bool with_coe
       while (k2 < pieces.size() && pieces[k2].dest == pieces[k].dest) ++k2;
       if (k2 - k > 1) {
         for (size_t p = k + 1; p < k2; ++p) extra_id[p] = n_extra++;
-        out.gd.push_back((uint16_t)(1 + pieces[k].dest));
-        out.gptr.push_back((uint16_t)n_extra);
+        out.gd.push_back(pieces[k].dest);
+        out.gptr.push_back(n_extra);
       }
       k = k2;
     }
   }
-  if (1 + n_dest + n_extra > MAX_OUT) return false;
   out.S = S;
   out.n_extra = n_extra;
-  out.prog.assign((size_t)S * 32, (NO_FLUSH << 16));
-  out.coef.assign(with_coef ? (size_t)S * 32 : 0, 0.0);
-  // ---- schedule: which term every lane reads at every step.  The 32 lanes of a step read 32 fp64 words of shared
-  // memory; the access is served in two phases of 16 lanes, each conflict-free iff its words lie in 16 distinct
-  // 8-byte banks (index mod 16) or coincide.  The order of the terms inside a run and the order of a lane's runs are
-  // free (any fixed order is a valid, reproducible sum), so a greedy list scheduler picks, lane by lane (most
-  // constrained first), a term whose bank is still unused in this phase of this step.
+  out.term.assign((size_t)S * 32, -1);
+  out.flush.assign((size_t)S * 32, -1);
+  out.lane_use = (double)N / (32.0 * S);
+  auto flush_id = [&](int pk) { return pieces[(size_t)pk].index == 0 ? pieces[(size_t)pk].dest : n_dest + extra_id[(size_t)pk]; };
   std::vector<std::vector<int>> lane_pieces(32);
   for (size_t k = 0; k < pieces.size(); ++k) lane_pieces[(size_t)lane_of[k]].push_back((int)k);
+  if (!bank_of) {  // given order
+    for (int l = 0; l < 32; ++l) {
+      int s = 0;
+      for (int pk : lane_pieces[(size_t)l]) {
+        const Piece &pc = pieces[(size_t)pk];
+        for (int e = 0; e < pc.count; ++e, ++s) {
+          out.term[(size_t)s * 32 + l] = by_dest[(size_t)pc.dest][(size_t)(pc.first + e)];
+          if (e == pc.count - 1) out.flush[(size_t)s * 32 + l] = flush_id(pk);
+        }
+      }
+    }
+    return true;
+  }
+  // ---- bank-aware order: per phase (16 lanes of one step) a maximum matching between lanes and banks
   std::vector<std::vector<int>> left(pieces.size());  // remaining term indices of every piece
   for (size_t k = 0; k < pieces.size(); ++k)
     for (int e = 0; e < pieces[k].count; ++e) left[k].push_back(by_dest[(size_t)pieces[k].dest][(size_t)(pieces[k].first + e)]);
   int cur[32];
   for (int l = 0; l < 32; ++l) cur[l] = -1;
-  long long wavefronts = 0;
   for (int s = 0; s < S; ++s) {
     for (int half = 0; half < 2; ++half) {
-      int load[16] = {0};  // lanes scheduled per bank
+      int load[16] = {0};
       int order[16], n_opt[16];
       bool idle_any = false;
       for (int k = 0; k < 16; ++k) {
         const int l = half * 16 + k;
-        order[k] = l;
         int opts = 0;
         if (cur[l] >= 0) opts = (int)left[(size_t)cur[l]].size();
         else
@@ -182,7 +205,7 @@ inline bool pack_stage(int n_dest, const std::vector<Term> &terms, bool with_coe
         auto scan = [&](int pk) {
           const std::vector<int> &rem = left[(size_t)pk];
           for (size_t z = 0; z < rem.size(); ++z) {
-            const int b = terms[(size_t)rem[z]].src & 15;
+            const int b = bank_of[terms[(size_t)rem[z]].src] & 15;
             if (cand_piece[k][b] < 0) {
               cand_piece[k][b] = pk;
               cand_pos[k][b] = (int)z;
@@ -194,11 +217,10 @@ inline bool pack_stage(int n_dest, const std::vector<Term> &terms, bool with_coe
           for (int pk : lane_pieces[(size_t)l])
             if (!left[(size_t)pk].empty()) scan(pk);
       }
-      // maximum matching (Kuhn's augmenting paths), most constrained lanes first; bank 0 is taken when a lane idles
       int bank_owner[16], lane_bank[16];
       for (int b = 0; b < 16; ++b) bank_owner[b] = -1;
       for (int k = 0; k < 16; ++k) lane_bank[k] = -1;
-      if (idle_any) bank_owner[0] = 16;  // sentinel: never re-routed
+      (void)idle_any;  // idle lanes read a dummy word in a bank the phase leaves free
       {
         int n_banks[16];
         for (int k = 0; k < 16; ++k) {
@@ -207,26 +229,25 @@ inline bool pack_stage(int n_dest, const std::vector<Term> &terms, bool with_coe
           order[k] = k;
         }
         std::stable_sort(order, order + 16, [&](int x, int y) { return n_banks[x] < n_banks[y]; });
+        struct Aug {
+          static bool go(int k, int (*cp)[16], int *owner, int *lb, bool *vis) {
+            for (int b = 0; b < 16; ++b) {
+              if (cp[k][b] < 0 || vis[b]) continue;
+              vis[b] = true;
+              if (owner[b] == 16) continue;
+              if (owner[b] < 0 || go(owner[b], cp, owner, lb, vis)) {
+                owner[b] = k;
+                lb[k] = b;
+                return true;
+              }
+            }
+            return false;
+          }
+        };
         for (int oi = 0; oi < 16; ++oi) {
           const int k0 = order[oi];
           if (n_opt[k0] == 0) continue;
           bool visited[16] = {false};
-          // iterative DFS would do; recursion depth is at most 16
-          struct Aug {
-            static bool go(int k, int (*cp)[16], int *owner, int *lb, bool *vis) {
-              for (int b = 0; b < 16; ++b) {
-                if (cp[k][b] < 0 || vis[b]) continue;
-                vis[b] = true;
-                if (owner[b] == 16) continue;
-                if (owner[b] < 0 || go(owner[b], cp, owner, lb, vis)) {
-                  owner[b] = k;
-                  lb[k] = b;
-                  return true;
-                }
-              }
-              return false;
-            }
-          };
           Aug::go(k0, cand_piece, bank_owner, lane_bank, visited);
         }
       }
@@ -241,30 +262,63 @@ inline bool pack_stage(int n_dest, const std::vector<Term> &terms, bool with_coe
             if (cand_piece[k][bb] >= 0 && (b < 0 || load[bb] < load[b])) b = bb;
           load[b]++;
         }
-        const int best_piece = cand_piece[k][b], best_pos = cand_pos[k][b];
-        std::vector<int> &rem = left[(size_t)best_piece];
-        const Term &tm = terms[(size_t)rem[(size_t)best_pos]];
-        rem.erase(rem.begin() + best_pos);
-        uint32_t word = (uint32_t)(tm.src * 8) & 0xFFFFu;
-        uint32_t flush = NO_FLUSH;
+        const int pk = cand_piece[k][b], pos = cand_pos[k][b];
+        std::vector<int> &rem = left[(size_t)pk];
+        out.term[(size_t)s * 32 + l] = rem[(size_t)pos];
+        rem.erase(rem.begin() + pos);
         if (rem.empty()) {
-          const Piece &pc = pieces[(size_t)best_piece];
-          flush = (uint32_t)(8 * (pc.index == 0 ? 1 + pc.dest : 1 + n_dest + extra_id[(size_t)best_piece]));
+          out.flush[(size_t)s * 32 + l] = flush_id(pk);
           cur[l] = -1;
         } else {
-          cur[l] = best_piece;
+          cur[l] = pk;
         }
-        const size_t at = (size_t)s * 32 + (size_t)l;
-        out.prog[at] = word | (flush << 16);
-        if (with_coef) out.coef[at] = tm.coef;
       }
-      int mx = 1;
-      for (int b = 0; b < 16; ++b) mx = std::max(mx, load[b]);
-      wavefronts += mx;
     }
   }
-  out.wavefronts = (double)wavefronts / (2.0 * S);  // 1.0 = conflict free
-  out.lane_use = (double)N / (32.0 * S);
+  return true;
+}
+
+// Proper edge colouring with 16 colours of a bipartite multigraph of maximum degree <= 16 (Koenig): edge e joins
+// left vertex lv[e] and right vertex rv[e]; colour[e] in 0..15, no vertex sees a colour twice.
+inline bool edge_colour_16(int n_left, int n_right, const std::vector<int> &lv, const std::vector<int> &rv, std::vector<int> &colour) {
+  const size_t E = lv.size();
+  colour.assign(E, -1);
+  std::vector<int> at_l((size_t)n_left * 16, -1), at_r((size_t)n_right * 16, -1);  // edge of each colour at each vertex
+  for (size_t e = 0; e < E; ++e) {
+    const int u = lv[e], v = rv[e];
+    int a = -1, b = -1;
+    for (int c = 0; c < 16 && a < 0; ++c)
+      if (at_l[(size_t)u * 16 + c] < 0) a = c;
+    for (int c = 0; c < 16 && b < 0; ++c)
+      if (at_r[(size_t)v * 16 + c] < 0) b = c;
+    if (a < 0 || b < 0) return false;  // degree above 16
+    if (a != b) {
+      // a is free at u but used at v: flip the a/b alternating path that starts at v with colour a (it cannot end at u)
+      std::vector<int> path;
+      int x = v, c = a;
+      bool on_right = true;
+      for (;;) {
+        const int f = on_right ? at_r[(size_t)x * 16 + c] : at_l[(size_t)x * 16 + c];
+        if (f < 0) break;
+        path.push_back(f);
+        x = on_right ? lv[(size_t)f] : rv[(size_t)f];
+        on_right = !on_right;
+        c = (c == a) ? b : a;
+      }
+      for (int f : path) {
+        at_l[(size_t)lv[(size_t)f] * 16 + colour[(size_t)f]] = -1;
+        at_r[(size_t)rv[(size_t)f] * 16 + colour[(size_t)f]] = -1;
+      }
+      for (int f : path) {
+        colour[(size_t)f] = (colour[(size_t)f] == a) ? b : a;
+        at_l[(size_t)lv[(size_t)f] * 16 + colour[(size_t)f]] = f;
+        at_r[(size_t)rv[(size_t)f] * 16 + colour[(size_t)f]] = f;
+      }
+    }
+    colour[e] = a;
+    at_l[(size_t)u * 16 + a] = (int)e;
+    at_r[(size_t)v * 16 + a] = (int)e;
+  }
   return true;
 }
 
@@ -277,6 +331,26 @@ struct Program {
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// phases needed by the reads of one stage given the buffer index of every logical source (idle lanes read a dummy
+// word in a free bank)
+inline double stage_conflicts(const Schedule &sc, const std::vector<Term> &terms, const std::vector<int> &index_of) {
+  long long wf = 0;
+  for (int s = 0; s < sc.S; ++s)
+    for (int half = 0; half < 2; ++half) {
+      int word[16], cnt[16] = {0}, mx = 1;
+      for (int k = 0; k < 16; ++k) {
+        const int t = sc.term[(size_t)s * 32 + half * 16 + k];
+        word[k] = t < 0 ? -1 : index_of[(size_t)terms[(size_t)t].src];
+        if (t < 0) continue;
+        bool dup = false;
+        for (int b = 0; b < k; ++b) dup = dup || word[b] == word[k];
+        if (!dup) mx = std::max(mx, ++cnt[word[k] & 15]);
+      }
+      wf += mx;
+    }
+  return (double)wf / (2.0 * std::max(sc.S, 1));
+}
+
 // false: the row does not fit the template kernel's limits (it stays on the per-row kernels)
 inline bool compile(const Raw &r, Program &out) {
   if (r.n0 < 1 || r.n0 > MAX_N0 || r.n1 < 1 || r.n1 > MAX_N1 || r.n2 < 1 || r.n2 > MAX_N2) return false;
@@ -288,24 +362,172 @@ inline bool compile(const Raw &r, Program &out) {
   for (int q = 0; q < r.n1; ++q) T2 += r.len2[(size_t)q];
   if (T1 < 1 || T1 > MAX_T1 || T2 < 1 || T2 > MAX_T2) return false;
   if ((int)r.slot1.size() != T1 || (int)r.slot2.size() != T2 || (int)r.mval.size() != T2) return false;
-  // staging list and stage-1 terms share the term order (operand rows ascending, entries ascending)
   const int stg_steps = (T1 + 31) / 32;
-  std::vector<uint16_t> stg((size_t)stg_steps * 32, STG_PAD);
+  std::vector<int> stg_q((size_t)T1), stg_e((size_t)T1);
   std::vector<Term> t1((size_t)T1), t2((size_t)T2);
   {
     int p = 0;
     for (int q = 0; q < r.n0; ++q)
       for (int e = 0; e < r.len1[(size_t)q]; ++e, ++p) {
-        stg[(size_t)p] = (uint16_t)((q << 8) | e);
-        t1[(size_t)p] = {(int)r.slot1[(size_t)p], 1 + p, 0.0};
+        stg_q[(size_t)p] = q;
+        stg_e[(size_t)p] = e;
+        t1[(size_t)p] = {(int)r.slot1[(size_t)p], p, 0.0};
       }
     p = 0;
     for (int q = 0; q < r.n1; ++q)
-      for (int e = 0; e < r.len2[(size_t)q]; ++e, ++p) t2[(size_t)p] = {(int)r.slot2[(size_t)p], 1 + q, r.mval[(size_t)p]};
+      for (int e = 0; e < r.len2[(size_t)q]; ++e, ++p) t2[(size_t)p] = {(int)r.slot2[(size_t)p], q, r.mval[(size_t)p]};
   }
-  Packed p1, p2;
-  if (!pack_stage(r.n1, t1, false, p1)) return false;
-  if (!pack_stage(r.n2, t2, true, p2)) return false;
+  // ---- stage 1: schedule in Gustavson order, then banks by edge colouring (write phase p / 16  x  read phase)
+  Schedule s1;
+  if (!build_schedule(r.n1, t1, nullptr, s1)) return false;
+  std::vector<int> s_index((size_t)T1, 0);  // index of staged term p inside S
+  {
+    std::vector<int> lv((size_t)T1), rv((size_t)T1), col;
+    for (int p = 0; p < T1; ++p) lv[(size_t)p] = p / 16;
+    for (int s = 0; s < s1.S; ++s)
+      for (int l = 0; l < 32; ++l) {
+        const int t = s1.term[(size_t)s * 32 + l];
+        if (t >= 0) rv[(size_t)t] = 2 * s + (l >> 4);
+      }
+    if (!edge_colour_16((T1 + 15) / 16, 2 * s1.S, lv, rv, col)) return false;
+    int rank[16] = {0};
+    for (int p = 0; p < T1; ++p) {
+      s_index[(size_t)p] = 16 + 16 * rank[col[(size_t)p]] + col[(size_t)p];  // words 0..15 are the dummy row
+      ++rank[col[(size_t)p]];
+    }
+  }
+  int s_words = 1;
+  for (int p = 0; p < T1; ++p) s_words = std::max(s_words, s_index[(size_t)p] + 1);
+  // ---- stage 2: layout of the intermediate row adapted to a bank-aware schedule (a few rounds of local search)
+  std::vector<int> o1_bank((size_t)r.n1), o1_index((size_t)r.n1);
+  auto layout_from_banks = [&](const std::vector<int> &bank, std::vector<int> &index) {
+    int rank[16] = {0};
+    int hi = 0;
+    for (int q = 0; q < r.n1; ++q) {
+      const int b = bank[(size_t)q];
+      index[(size_t)q] = 16 + 16 * rank[b] + b;  // (index & 15) == bank; words 0..15 are the dummy row
+      ++rank[b];
+      hi = std::max(hi, index[(size_t)q]);
+    }
+    return hi + 1;  // first free index
+  };
+  for (int q = 0; q < r.n1; ++q) o1_bank[(size_t)q] = (q + 1) & 15;  // start from (about) the identity layout
+  Schedule s2, best_s2;
+  std::vector<int> best_bank = o1_bank, best_index;
+  double best_conf = 1e30;
+  for (int round = 0; round < 6; ++round) {
+    if (!build_schedule(r.n2, t2, o1_bank.data(), s2)) return false;
+    layout_from_banks(o1_bank, o1_index);
+    const double conf = stage_conflicts(s2, t2, o1_index);
+    if (conf < best_conf) {
+      best_conf = conf;
+      best_s2 = s2;
+      best_bank = o1_bank;
+      best_index = o1_index;
+    }
+    if (conf <= 1.0 + 1e-12) break;
+    // local search on the banks for THIS schedule: move a source to the bank that minimises the phases it is read in
+    std::vector<std::vector<int>> reads((size_t)r.n1);  // phases (2 s + half) every source is read in, ascending
+    for (int s = 0; s < s2.S; ++s)
+      for (int l = 0; l < 32; ++l) {
+        const int t = s2.term[(size_t)s * 32 + l];
+        if (t >= 0) reads[(size_t)t2[(size_t)t].src].push_back(2 * s + (l >> 4));
+      }
+    const int n_ph = 2 * s2.S;
+    std::vector<int> cnt((size_t)n_ph * 16, 0);  // distinct sources per (phase, bank)
+    auto add = [&](int q, int d) {
+      int last = -1;
+      for (int ph : reads[(size_t)q]) {
+        if (ph == last) continue;  // several lanes of one phase reading q: one word
+        cnt[(size_t)ph * 16 + o1_bank[(size_t)q]] += d;
+        last = ph;
+      }
+    };
+    for (int q = 0; q < r.n1; ++q) add(q, +1);
+    bool moved = true;
+    for (int sweep = 0; sweep < 4 && moved; ++sweep) {
+      moved = false;
+      for (int q = 0; q < r.n1; ++q) {
+        add(q, -1);
+        int best_b = o1_bank[(size_t)q], best_cost = 1 << 30;
+        for (int b = 0; b < 16; ++b) {
+          int cost = 0, last = -1;
+          for (int ph : reads[(size_t)q]) {
+            if (ph == last) continue;
+            cost += cnt[(size_t)ph * 16 + b];
+            last = ph;
+          }
+          if (cost < best_cost || (cost == best_cost && b == o1_bank[(size_t)q])) {
+            best_cost = cost;
+            best_b = b;
+          }
+        }
+        if (best_b != o1_bank[(size_t)q]) moved = true;
+        o1_bank[(size_t)q] = best_b;
+        add(q, +1);
+      }
+    }
+  }
+  s2 = best_s2;
+  o1_bank = best_bank;
+  const int ext1 = layout_from_banks(o1_bank, o1_index);  // extras of stage 1 follow the destinations
+  const int ext2 = 1 + r.n2;
+  if (ext1 + s1.n_extra > MAX_OUT || ext2 + s2.n_extra > MAX_OUT || s_words > 8191) return false;
+  // ---- emit
+  auto out1_index = [&](int id) { return id < r.n1 ? o1_index[(size_t)id] : ext1 + (id - r.n1); };
+  auto out2_index = [&](int id) { return id < r.n2 ? 1 + id : ext2 + (id - r.n2); };
+  std::vector<uint32_t> stg((size_t)stg_steps * 32, STG_PAD);
+  for (int p = 0; p < T1; ++p)
+    stg[(size_t)p] = ((uint32_t)s_index[(size_t)p] << 16) | ((uint32_t)stg_q[(size_t)p] << 8) | (uint32_t)stg_e[(size_t)p];
+  std::vector<uint32_t> p1((size_t)s1.S * 32), p2((size_t)s2.S * 32);
+  std::vector<double> c2((size_t)s2.S * 32, 0.0);
+  // a lane whose program has ended keeps stepping: it reads a dummy word (index = a bank none of the phase's active lanes
+  // uses, in the dummy row 0..15), adds it to an accumulator that is never flushed again
+  auto idle_word = [&](const Schedule &sc, size_t k, const std::vector<Term> &terms, const std::vector<int> &index_of) {
+    const size_t base = k & ~(size_t)15;
+    bool used[16] = {false};
+    for (size_t j = base; j < base + 16; ++j)
+      if (sc.term[j] >= 0) used[index_of[(size_t)terms[(size_t)sc.term[j]].src] & 15] = true;
+    for (int b = 0; b < 16; ++b)
+      if (!used[b]) return b;
+    return 0;
+  };
+  for (size_t k = 0; k < p1.size(); ++k) {
+    const int t = s1.term[k], f = s1.flush[k];
+    const int src = t < 0 ? idle_word(s1, k, t1, s_index) : s_index[(size_t)t1[(size_t)t].src];
+    p1[k] = (uint32_t)(8 * src) | ((f < 0 ? NO_FLUSH : (uint32_t)(8 * out1_index(f))) << 16);
+  }
+  for (size_t k = 0; k < p2.size(); ++k) {
+    const int t = s2.term[k], f = s2.flush[k];
+    const int src = t < 0 ? idle_word(s2, k, t2, o1_index) : o1_index[(size_t)t2[(size_t)t].src];
+    p2[k] = (uint32_t)(8 * src) | ((f < 0 ? NO_FLUSH : (uint32_t)(8 * out2_index(f))) << 16);
+    if (t >= 0) c2[k] = t2[(size_t)t].coef;
+  }
+  // pieces of split destinations are added in ROUNDS: round j adds the (j+1)-th piece of every split destination into
+  // it, so the pairs of one round touch distinct destinations (one lane each, no race) and the order is fixed.
+  // Section layout: ptr[nr + 1] (in pairs, padded to an even count), then the pairs (destination index, extra index).
+  auto rounds_of = [&](const Schedule &sc, int ext, const std::vector<int> &dest_index, int *n_rounds) {
+    int nr = 0;
+    for (size_t g = 0; g < sc.gd.size(); ++g) nr = std::max(nr, sc.gptr[g + 1] - sc.gptr[g]);
+    std::vector<uint16_t> ptr, pairs;
+    ptr.push_back(0);
+    for (int j = 0; j < nr; ++j) {
+      for (size_t g = 0; g < sc.gd.size(); ++g)
+        if (sc.gptr[g + 1] - sc.gptr[g] > j) {
+          pairs.push_back((uint16_t)dest_index[(size_t)sc.gd[g]]);
+          pairs.push_back((uint16_t)(ext + sc.gptr[g] + j));
+        }
+      ptr.push_back((uint16_t)(pairs.size() / 2));
+    }
+    *n_rounds = nr;
+    while (ptr.size() < (size_t)((nr + 2) & ~1)) ptr.push_back(ptr.back());  // the pairs start 4-byte aligned
+    ptr.insert(ptr.end(), pairs.begin(), pairs.end());
+    return ptr;
+  };
+  std::vector<int> o2_index((size_t)r.n2);
+  for (int o = 0; o < r.n2; ++o) o2_index[(size_t)o] = 1 + o;
+  int nr1 = 0, nr2 = 0;
+  std::vector<uint16_t> g1 = rounds_of(s1, ext1, o1_index, &nr1), g2 = rounds_of(s2, ext2, o2_index, &nr2);
   Header h;
   memset(&h, 0, sizeof(h));
   h.n0 = r.n0;
@@ -313,45 +535,45 @@ inline bool compile(const Raw &r, Program &out) {
   h.stg_steps = stg_steps;
   h.n1 = r.n1;
   h.n2 = r.n2;
-  h.S1 = p1.S;
-  h.S2 = p2.S;
-  h.ng1 = (int)p1.gd.size();
-  h.nx1 = p1.n_extra;
-  h.ng2 = (int)p2.gd.size();
-  h.nx2 = p2.n_extra;
+  h.S1 = s1.S;
+  h.S2 = s2.S;
+  h.ng1 = nr1;  // rounds of the combine pass
+  h.nx1 = s1.n_extra;
+  h.ng2 = nr2;
+  h.nx2 = s2.n_extra;
+  h.ext1 = ext1;
+  h.ext2 = ext2;
   size_t off = align16(sizeof(Header));
   auto place = [&](size_t bytes) {
     size_t at = off;
     off = align16(off + bytes);
     return (int)at;
   };
-  h.off_stg = place(stg.size() * 2);
+  h.off_stg = place(stg.size() * 4);
   h.off_w = place((size_t)r.n0 * 8);
-  h.off_p1 = place(p1.prog.size() * 4);
-  h.off_g1 = place((p1.gd.size() + p1.gptr.size()) * 2);
-  h.off_c2 = place(p2.coef.size() * 8);
-  h.off_p2 = place(p2.prog.size() * 4);
-  h.off_g2 = place((p2.gd.size() + p2.gptr.size()) * 2);
+  h.off_p1 = place(p1.size() * 4);
+  h.off_g1 = place(g1.size() * 2);
+  h.off_c2 = place(c2.size() * 8);
+  h.off_p2 = place(p2.size() * 4);
+  h.off_g2 = place(g2.size() * 2);
   h.blob_bytes = (int)off;
   out.blob.assign(off, 0);
   unsigned char *b = out.blob.data();
   memcpy(b, &h, sizeof(h));
-  memcpy(b + h.off_stg, stg.data(), stg.size() * 2);
+  memcpy(b + h.off_stg, stg.data(), stg.size() * 4);
   memcpy(b + h.off_w, r.w.data(), (size_t)r.n0 * 8);
-  memcpy(b + h.off_p1, p1.prog.data(), p1.prog.size() * 4);
-  if (!p1.gd.empty()) memcpy(b + h.off_g1, p1.gd.data(), p1.gd.size() * 2);
-  memcpy(b + h.off_g1 + p1.gd.size() * 2, p1.gptr.data(), p1.gptr.size() * 2);
-  memcpy(b + h.off_c2, p2.coef.data(), p2.coef.size() * 8);
-  memcpy(b + h.off_p2, p2.prog.data(), p2.prog.size() * 4);
-  if (!p2.gd.empty()) memcpy(b + h.off_g2, p2.gd.data(), p2.gd.size() * 2);
-  memcpy(b + h.off_g2 + p2.gd.size() * 2, p2.gptr.data(), p2.gptr.size() * 2);
-  out.s_cap = 1 + stg_steps * 32;
-  out.o1_cap = 1 + r.n1 + p1.n_extra;
-  out.o2_cap = 1 + r.n2 + p2.n_extra;
-  out.use1 = p1.lane_use;
-  out.use2 = p2.lane_use;
-  out.conf1 = p1.wavefronts;
-  out.conf2 = p2.wavefronts;
+  memcpy(b + h.off_p1, p1.data(), p1.size() * 4);
+  if (!g1.empty()) memcpy(b + h.off_g1, g1.data(), g1.size() * 2);
+  memcpy(b + h.off_c2, c2.data(), c2.size() * 8);
+  memcpy(b + h.off_p2, p2.data(), p2.size() * 4);
+  if (!g2.empty()) memcpy(b + h.off_g2, g2.data(), g2.size() * 2);
+  out.s_cap = s_words;
+  out.o1_cap = ext1 + s1.n_extra;
+  out.o2_cap = ext2 + s2.n_extra;
+  out.use1 = s1.lane_use;
+  out.use2 = s2.lane_use;
+  out.conf1 = stage_conflicts(s1, t1, s_index);
+  out.conf2 = stage_conflicts(s2, t2, o1_index);
   return true;
 }
 
@@ -360,18 +582,19 @@ inline bool compile(const Raw &r, Program &out) {
 inline void interpret(const unsigned char *blob, const double *const *a_rows, double *c_out) {
   Header h;
   memcpy(&h, blob, sizeof(h));
-  const uint16_t *stg = (const uint16_t *)(blob + h.off_stg);
+  const uint32_t *stg = (const uint32_t *)(blob + h.off_stg);
   const double *w = (const double *)(blob + h.off_w);
   const uint32_t *p1 = (const uint32_t *)(blob + h.off_p1);
-  const uint16_t *gd1 = (const uint16_t *)(blob + h.off_g1), *gp1 = gd1 + h.ng1;
+  const uint16_t *gp1 = (const uint16_t *)(blob + h.off_g1), *pr1 = gp1 + ((h.ng1 + 2) & ~1);
   const double *c2 = (const double *)(blob + h.off_c2);
   const uint32_t *p2 = (const uint32_t *)(blob + h.off_p2);
-  const uint16_t *gd2 = (const uint16_t *)(blob + h.off_g2), *gp2 = gd2 + h.ng2;
-  std::vector<double> S((size_t)1 + (size_t)h.stg_steps * 32, 0.0), O1((size_t)1 + h.n1 + h.nx1, 0.0), O2((size_t)1 + h.n2 + h.nx2, 0.0);
+  const uint16_t *gp2 = (const uint16_t *)(blob + h.off_g2), *pr2 = gp2 + ((h.ng2 + 2) & ~1);
+  std::vector<double> S(8192, 0.0), O1((size_t)h.ext1 + h.nx1 + 1, 0.0), O2((size_t)h.ext2 + h.nx2 + 1, 0.0);
   for (int p = 0; p < h.stg_steps * 32; ++p) {
-    const uint16_t m = stg[p];
+    const uint32_t m = stg[p];
     if (m == STG_PAD) continue;
-    S[(size_t)1 + p] = w[m >> 8] * a_rows[m >> 8][m & 255];
+    const uint32_t q = (m >> 8) & 255u, e = m & 255u;
+    S[m >> 16] = w[q] * a_rows[q][e];
   }
   for (int lane = 0; lane < 32; ++lane) {
     double acc = 0.0;
@@ -385,11 +608,8 @@ inline void interpret(const unsigned char *blob, const double *const *a_rows, do
       }
     }
   }
-  for (int g = 0; g < h.ng1; ++g) {
-    double v = O1[gd1[g]];
-    for (int x = gp1[g]; x < gp1[g + 1]; ++x) v += O1[(size_t)1 + h.n1 + x];
-    O1[gd1[g]] = v;
-  }
+  for (int rd = 0; rd < h.ng1; ++rd)
+    for (int k = gp1[rd]; k < gp1[rd + 1]; ++k) O1[pr1[2 * k]] += O1[pr1[2 * k + 1]];
   for (int lane = 0; lane < 32; ++lane) {
     double acc = 0.0;
     for (int s = 0; s < h.S2; ++s) {
@@ -402,11 +622,8 @@ inline void interpret(const unsigned char *blob, const double *const *a_rows, do
       }
     }
   }
-  for (int g = 0; g < h.ng2; ++g) {
-    double v = O2[gd2[g]];
-    for (int x = gp2[g]; x < gp2[g + 1]; ++x) v += O2[(size_t)1 + h.n2 + x];
-    O2[gd2[g]] = v;
-  }
+  for (int rd = 0; rd < h.ng2; ++rd)
+    for (int k = gp2[rd]; k < gp2[rd + 1]; ++k) O2[pr2[2 * k]] += O2[pr2[2 * k + 1]];
   for (int o = 0; o < h.n2; ++o) c_out[o] = O2[(size_t)1 + o];
 }
 

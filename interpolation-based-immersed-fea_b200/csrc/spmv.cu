@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "p2p_dev.cuh"
 #include <stdlib.h>
+#include <algorithm>
 
 namespace iife {
 
@@ -122,6 +123,140 @@ k_spmv_ilp2(const int *__restrict__ rowptr, const int *__restrict__ colind, cons
       if (i1 < n_rows) y[i1] = s1;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSR-stream SpMV for operators with SHORT, ragged rows (the extraction operator M: 1-8 entries per row, rejected by
+// SELL-32 for its padding): y = A x, transferToForeground (reference common.py:123-140, la_utils.py:129-141).
+// The (colind, val) entries of a tile of consecutive rows are one contiguous range of the CSR arrays, so a tile is
+// staged in shared memory with two bulk async copies (cp.async.bulk = the TMA engine, completion on an mbarrier):
+// no register staging, no dependent pointer chase, STAGES tiles in flight per CTA, and the global reads are perfectly
+// coalesced whatever the row lengths.  One thread then owns one row and walks its entries in shared memory; the only
+// irregular access left is the gather of x (L1/L2 resident: consecutive foreground rows touch neighbouring
+// background columns).  Persistent CTAs, tiles handed out round robin.
+// ------------------------------------------------------------------------------------------------
+constexpr int STREAM_ROWS = 256;   // rows per tile = threads per CTA
+constexpr int STREAM_STAGES = 3;
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(phase)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// max_len: longest row of A (<= cap_entries / STREAM_ROWS).  Shared memory per stage: cap_entries + 4 column words and
+// cap_entries + 2 values (alignment slack: bulk copies start on 16-byte boundaries of the global arrays).
+__global__ void __launch_bounds__(STREAM_ROWS)
+k_spmv_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, const double *__restrict__ val, int64_t n_rows,
+              int64_t nnz, int cap_entries, const double *__restrict__ x, double *__restrict__ y) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bars[STREAM_STAGES];
+  __shared__ int s_base[STREAM_STAGES];  // first entry (rowptr[r0]) of the tile in each stage; -1: tile read from global
+  const int tid = threadIdx.x;
+  const size_t val_bytes = ((size_t)cap_entries + 2) * 8, col_bytes = (((size_t)cap_entries + 4) * 4 + 15) & ~(size_t)15;
+  const size_t stage_bytes = val_bytes + col_bytes;
+  const int64_t n_tiles = (n_rows + STREAM_ROWS - 1) / STREAM_ROWS;
+  if (tid == 0) {
+    for (int s = 0; s < STREAM_STAGES; ++s) mbar_init((unsigned)__cvta_generic_to_shared(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // producer: thread 0 issues the copies of tile `t` into stage `s`
+  auto issue = [&](int64_t t, int s) {
+    const int64_t r0 = t * STREAM_ROWS;
+    const int64_t r1 = r0 + STREAM_ROWS < n_rows ? r0 + STREAM_ROWS : n_rows;
+    const int b = __ldg(rowptr + r0), e = __ldg(rowptr + r1);
+    const int bc = b & ~3, bv = b & ~1;
+    const unsigned cb = (unsigned)(((e - bc) * 4 + 15) & ~15), vb = (unsigned)(((e - bv) * 8 + 15) & ~15);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[s]);
+    // the rounded-up copies may not run past the arrays (last tile): such a tile is read with plain loads instead
+    const bool fits = (int64_t)bc * 4 + cb <= nnz * 4 && (int64_t)bv * 8 + vb <= nnz * 8 && (e - b) <= cap_entries;
+    if (e == b || !fits) {
+      s_base[s] = -1 - b;  // nothing staged (empty tile, or tail / oversized tile)
+      mbar_expect_tx(bar, 0);
+      return;
+    }
+    s_base[s] = b;
+    unsigned char *st = smem + (size_t)s * stage_bytes;
+    mbar_expect_tx(bar, cb + vb);
+    bulk_g2s((unsigned)__cvta_generic_to_shared(st), val + bv, vb, bar);
+    bulk_g2s((unsigned)__cvta_generic_to_shared(st + val_bytes), colind + bc, cb, bar);
+  };
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  if (tid == 0)
+    for (int s = 0; s < STREAM_STAGES; ++s)
+      if (first + (int64_t)s * step < n_tiles) issue(first + (int64_t)s * step, s);
+  int64_t k = 0;
+  for (int64_t t = first; t < n_tiles; t += step, ++k) {
+    const int s = (int)(k % STREAM_STAGES);
+    const unsigned phase = (unsigned)((k / STREAM_STAGES) & 1);
+    mbar_wait((unsigned)__cvta_generic_to_shared(&bars[s]), phase);
+    const int base = s_base[s];
+    const int64_t i = t * STREAM_ROWS + tid;
+    if (i < n_rows) {
+      const int rb = __ldg(rowptr + i), re = __ldg(rowptr + i + 1);
+      double acc = 0.0;
+      if (base >= 0) {
+        const double *sv = (const double *)(smem + (size_t)s * stage_bytes) - (base & ~1);
+        const int *sc = (const int *)(smem + (size_t)s * stage_bytes + val_bytes) - (base & ~3);
+        // four gathers of x in flight per thread (rows are short: a plain loop would leave one)
+        for (int p = rb; p < re; p += 4) {
+          double xv[4], av[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool in = p + u < re;
+            av[u] = in ? sv[p + u] : 0.0;
+            xv[u] = in ? __ldg(x + sc[p + u]) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc = fma(av[u], xv[u], acc);
+        }
+      } else {
+        for (int p = rb; p < re; ++p) acc = fma(ld_stream(val + p), __ldg(x + ld_stream(colind + p)), acc);
+      }
+      y[i] = acc;
+    }
+    __syncthreads();  // every thread is done with stage s: refill it
+    if (tid == 0 && t + (int64_t)STREAM_STAGES * step < n_tiles) issue(t + (int64_t)STREAM_STAGES * step, s);
+  }
+}
+
+int spmv_stream_launch(const Mat *A, int max_len, const double *x, double *y) {
+  Ctx &c = ctx();
+  const int cap = STREAM_ROWS * max_len;
+  const size_t stage = ((size_t)cap + 2) * 8 + ((((size_t)cap + 4) * 4 + 15) & ~(size_t)15);
+  const size_t smem = stage * STREAM_STAGES;
+  if (smem > 48 * 1024) IIFE_CUDA(cudaFuncSetAttribute(k_spmv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_stream, STREAM_ROWS, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  const int64_t n_tiles = (A->n_rows + STREAM_ROWS - 1) / STREAM_ROWS;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)c.sm_count * per_sm));
+  IIFE_LAUNCH(k_spmv_stream, grid, STREAM_ROWS, smem, A->rowptr, A->colind, A->val, A->n_rows, A->nnz, cap, x, y);
+  IIFE_CHECK_LAUNCH();
+  return IIFE_OK;
 }
 
 // w = A p, dot = (p, w).  Rows of A index p as well (A square on the local row block).
@@ -825,6 +960,15 @@ int spmv_launch(const Mat *A, double alpha, const double *x, double beta, double
   int lpr = spmv_pick_lpr(A);
   int g = spmv_grid(A->n_rows, lpr);
   bool plain = (alpha == 1.0 && beta == 0.0);
+  if (plain && lpr <= 8 && A->max_row_len < 0) {  // first product with this operator: one reduction over the row lengths
+    int ml = 0;
+    IIFE_TRY(mat_max_row_len(const_cast<Mat *>(A), &ml));
+  }
+  if (plain && lpr <= 8 && A->max_row_len >= 0 && A->max_row_len <= 16 && A->nnz >= 1024) {
+    // short ragged rows: tiles staged with bulk async copies (k_spmv_stream); IIFE_SPMV_STREAM=0 disables
+    const char *st = getenv("IIFE_SPMV_STREAM");
+    if (!st || atoi(st) != 0) return spmv_stream_launch(A, A->max_row_len < 1 ? 1 : A->max_row_len, x, y);
+  }
   if (plain && lpr <= 8) {
     const char *ilp = getenv("IIFE_SPMV_ILP");  // two-rows-in-flight kernel for short rows (default on)
     if (!ilp || atoi(ilp) != 0) {

@@ -1,0 +1,14 @@
+#!/bin/bash
+# full GPU test suite, configs 1-4 timing table, default bench line
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu --tb=short 2>&1 | tail -40 > gpurun_out/full_tests.log
+tail -5 gpurun_out/full_tests.log
+timeout 300 python scripts/configs_1_4.py > gpurun_out/configs_1_4.md 2> gpurun_out/configs_1_4.err; echo "configs rc=$?"; tail -8 gpurun_out/configs_1_4.md
+timeout 600 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/bench_full.json").read().strip().splitlines()[-1])
+r = d["roofline"]
+print(f"step {d['ms_per_step']:.2f} ms value {d['value']:.1f}  e2e {d['e2e']['ms_per_step']:.1f} ms ({d['e2e']['value']:.1f})  fixed {d['e2e'].get('fixed_pattern')}  cpu {d['cpu_baseline']}")
+print(f"spmv {r['launch_ms']*1e3:.0f} us frac {r['frac']:.3f}  cg/it {r['cg_iteration']['ms']*1e3:.0f} us  ptap {r['ptap_numeric']['ms']:.2f} ms frac {r['ptap_numeric']['frac']:.3f}  cold {d['config']['cold_ptap_symbolic_plus_numeric_ms']:.0f} ms launches {d['gpu_launches']}")
+PY

@@ -148,6 +148,26 @@ def test_spmv_matches_oracle(iife, oracle, mean):
     assert np.all(np.abs(y2 - (-2.0 * yo + 0.5 * y0)) <= 1e-13 * (2 * scale + np.abs(y0)))
 
 
+@pytest.mark.parametrize("n_rows,n_cols,mean,empty", [(1000, 300, 2.0, 0.3), (70001, 9000, 3.4, 0.1), (4097, 4097, 6.0, 0.0)])
+def test_spmv_short_rows_stream_kernel(iife, oracle, monkeypatch, n_rows, n_cols, mean, empty):
+    """Operators with short ragged rows (the extraction operator M: 1-8 entries) take the CSR-stream kernel, whose
+    tiles are staged with bulk async copies (csrc/spmv.cu: k_spmv_stream): tiles that start off 16-byte boundaries,
+    empty rows, a ragged last tile, against the oracle and against the plain CSR kernel."""
+    rng = np.random.default_rng(int(n_rows))
+    A = ocsr(oracle, n_rows, n_cols, rand_csr(rng, n_rows, n_cols, mean, max_len=8, empty_frac=empty))
+    x = rng.standard_normal(n_cols)
+    ref = oracle.spmv(A, x)
+    scale = oracle.spmv(abs_csr(oracle, A), np.abs(x)) + 1e-300
+    dA = dmat(iife, A)
+    n0 = iife.launch_count(reset=True)
+    y = dA.spmv(x)
+    assert np.all(np.abs(y - ref) <= 1e-14 * scale)
+    monkeypatch.setenv("IIFE_SPMV_STREAM", "0")
+    y2 = dmat(iife, A).spmv(x)
+    assert np.all(np.abs(y2 - ref) <= 1e-14 * scale)
+    assert np.all(np.abs(y2 - y) <= 1e-14 * scale)
+
+
 def test_diagonal(iife, oracle):
     rng = np.random.default_rng(5)
     A = ocsr(oracle, 400, 400, rand_csr(rng, 400, 400, 7, empty_frac=0.1))

@@ -78,7 +78,7 @@ def test_cube_rows_compile_and_match():
     _, _, info = _emulate(d)
     assert len(d["len1"]) == 27 and d["n2"] == 27
     assert info[6] >= 800 and info[7] >= 800, info  # lane use x1000
-    assert info[8] <= 2000 and info[9] <= 2000, info  # conflict degree x1000 of the gather reads (2000 = unscheduled)
+    assert info[8] == 1000 and info[9] <= 1500, info  # conflict degree x1000: stage 1 is conflict free by construction
 
 
 @pytest.mark.parametrize("seed", range(4))
