@@ -65,6 +65,7 @@ extern "C" {
 /* KSP types / preconditioners (common.py:554-574: 'cg' -> KSPCG, 'gmres' -> KSPFGMRES; PC 'jacobi') */
 #define IIFE_KSP_CG 0
 #define IIFE_KSP_FGMRES 1
+#define IIFE_KSP_GCR 2 /* common.py:559-560: 'gcr' -> KSPGCR; `restart` <= 0 selects PETSc's default of 30; single GPU */
 #define IIFE_PC_NONE 0
 #define IIFE_PC_JACOBI 1
 

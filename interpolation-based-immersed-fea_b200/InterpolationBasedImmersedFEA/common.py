@@ -3,13 +3,13 @@
 
 On the extraction hot path everything PETSc did runs in libiife.so on the GPU:
 ``assembleLinearSystemBackground`` (:142-163), ``transferToForeground`` (:123-140), ``zeroDofBackground`` (:120-121),
-the Krylov + Jacobi branch of ``solveKSP`` (:554-574, :628-636), ``readExOp`` (:645-712, host side), the
+the Krylov + Jacobi branch of ``solveKSP`` (:554-574, :628-636: FGMRES, CG, GCR), ``readExOp`` (:645-712, host side), the
 basis-function-removal helpers ``createNonzeroDiagonal`` / ``removeZeroDiagonal`` / ``getIdentity`` / ``trimNodes``
 (:207-332), the Newton drivers ``solveNewtonsLinear`` (:335-402) and ``solveNonlinear`` (:404-480), ``L2Project``
 (:172-195) and ``estimateConditionNumber`` (:483-507).  FEniCS assembly stays on the host exactly as in the reference.
 
 Everything else keeps working as an OVERLAY of the reference package:
-  * the MUMPS / GCR / ASM / ICC / HYPRE branches of ``solveKSP`` (:525-551, :576-616) are configured through
+  * the MUMPS / ASM / ICC / HYPRE branches of ``solveKSP`` (:525-551, :576-616) are configured through
     petsc4py exactly as the reference does whenever petsc4py is importable (NotImplementedError otherwise);
   * with dolfin importable, dolfin's names are re-exported (the reference module star-imports dolfin, and the
     demos rely on it: demos/poisson.py:14-16) and ``worldcomm`` / ``mpirank`` / ``mpisize`` exist;
@@ -42,8 +42,9 @@ except Exception:  # pragma: no cover - depends on the environment
 
 DEFAULT_LINEAR_SOLVER = 'gmres'  # reference common.py:36
 
-_KRYLOV = {'gmres': _iife.KSP_FGMRES, 'cg': _iife.KSP_CG}
-_DELEGATED_METHODS = ('mumps', 'gcr')          # direct / GCR: not on the north-star path
+_KRYLOV = {'gmres': _iife.KSP_FGMRES, 'cg': _iife.KSP_CG, 'gcr': _iife.KSP_GCR}
+_RESTART = {'gmres': 300, 'cg': 0, 'gcr': 30}  # FGMRES: common.py:574; GCR: PETSc's default (setGMRESRestart does not reach it)
+_DELEGATED_METHODS = ('mumps',)                 # sparse direct solve: PETSc only
 _DELEGATED_PCS = ('ASM', 'ICC', 'ILU', 'ILUT')  # heavy preconditioners: PETSc only
 
 last_ksp_info = None  # KSPInfo of the most recent solveKSP call (iterations, reason, residual history)
@@ -200,8 +201,8 @@ def solveKSP(A, b, u, method='gmres', PC='jacobi',
     Krylov branch with Jacobi (the reference's default and the north-star path): 'gmres' is PETSc's
     FGMRES with restart 300 (:557, :574), 'cg' is KSPCG (:561), tolerances as given (:555, :631-633),
     the initial guess is whatever ``u`` holds (:634), non-convergence never raises (:635); ``u`` is
-    updated in place and None is returned.  Direct solves (MUMPS), GCR and the heavy preconditioners (ASM / ICC /
-    HYPRE) keep running on PETSc, configured as the reference configures them, whenever petsc4py is importable;
+    updated in place and None is returned.  'gcr' is KSPGCR (:559-560, restart 30).  Direct solves (MUMPS) and the heavy
+    preconditioners (ASM / ICC / HYPRE) keep running on PETSc, configured as the reference configures them, whenever petsc4py is importable;
     without PETSc they raise NotImplementedError."""
     global last_ksp_info
     if method is None:
@@ -213,8 +214,8 @@ def solveKSP(A, b, u, method='gmres', PC='jacobi',
             return _solve_with_petsc(A, b, u, method, PC, remove_zero_diagonal, rtol, atol, max_it, bfr_tol, monitor,
                                      gmr_res, bfr_b)
         raise NotImplementedError(
-            f"solveKSP(method={method!r}, PC={PC!r}) runs on PETSc (MUMPS / GCR / ASM / ICC / HYPRE) in the reference "
-            "and petsc4py is not importable here; the B200 path implements method in ('gmres', 'cg') with PC='jacobi'")
+            f"solveKSP(method={method!r}, PC={PC!r}) runs on PETSc (MUMPS / ASM / ICC / HYPRE) in the reference "
+            "and petsc4py is not importable here; the B200 path implements method in ('gmres', 'cg', 'gcr') with PC='jacobi'")
     if method not in _KRYLOV:
         raise NotImplementedError(f"unknown method {method!r}")
     if PC != 'jacobi':
@@ -223,7 +224,7 @@ def solveKSP(A, b, u, method='gmres', PC='jacobi',
         A, b = trimNodes(A, b=b, bfr_tol=bfr_tol)  # reference common.py:565-566
     dA = _as_device(arg2m(A))
     bv, uv = arg2v(b), arg2v(u)
-    kw = dict(rtol=rtol, atol=atol, max_it=max_it, restart=300, hist_len=(4096 if monitor else 0))
+    kw = dict(rtol=rtol, atol=atol, max_it=max_it, restart=_RESTART[method], hist_len=(4096 if monitor else 0))
     uarr = _vec_array(uv)  # u is updated in place (:634-636)
     direct = isinstance(uarr, np.ndarray) and uarr.dtype == np.float64 and uarr.flags.c_contiguous and uarr.ndim == 1
     if isinstance(bv, Vec) and bv.device_tensor() is not None and direct and uarr.size > 0:
@@ -373,7 +374,7 @@ def solveNewtonsLinear(A, L, u_f, M, u_p,
         du_d.zero_()
         tsync()
         info = _iife.ksp_solve(dA, res_d, du_d, _KRYLOV[method], _iife.PC_JACOBI, rtol=1e-8, atol=1e-9,
-                               max_it=1000000, restart=300)
+                               max_it=1000000, restart=_RESTART[method])
         currentNorm = float(torch.linalg.vector_norm(du_d))
         if i == 0:
             initialNorm, initialNormRes = currentNorm, currentNormRes
@@ -507,7 +508,7 @@ def solveNonlinear(res_f, u_f, M, u_p,
             du_d = torch.zeros(dA.shape[0], dtype=torch.float64, device=Rb_d.device)
             tsync()
             info = _iife.ksp_solve(dA, Rb_d, du_d, _KRYLOV[method], _iife.PC_JACOBI, rtol=1e-8, atol=1e-9,
-                                   max_it=1000000, restart=300)
+                                   max_it=1000000, restart=_RESTART[method])
             if moniterLinearConvergence:
                 print('Converged in', info.iterations, 'iterations.')
                 print('Convergence history:', [])

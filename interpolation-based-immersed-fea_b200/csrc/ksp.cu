@@ -378,7 +378,6 @@ __global__ void k_cg_update_scalars(double *sc, int *fl, double *hist, long long
 }
 
 }  // namespace iife
-#include "ksp_persist.cuh"
 namespace iife {
 
 // ------------------------------------------------------------------------------------------------
@@ -462,8 +461,8 @@ k_gm_scale_pc(double *__restrict__ v, double *__restrict__ z, const double *__re
 constexpr int KT = 8;
 __global__ void __launch_bounds__(VEC_THREADS)
 k_gm_dots(const double *__restrict__ w, double *const *__restrict__ V, int64_t n, int j, GmresSmall gs,
-          const int *__restrict__ fl, double *mpartials, unsigned int *counter) {
-  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != j) return;
+          const int *__restrict__ fl, double *mpartials, unsigned int *counter, int gate) {
+  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != gate) return;
   __shared__ double red[32];
   __shared__ bool last;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -798,7 +797,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   if (chunk < 1) chunk = 1;
   // three-kernel iteration of the peer-memory path (k_cg_p_push / SpMV with halo wait / k_cg_update<3>)
   const bool fused3 = p2p && !fused_halo && mat_sell_ready(A) && H->bmask && env_int("IIFE_CG_FUSED3", 1) != 0 && !dbg_nohalo &&
-                      !dbg_nored && env_int("IIFE_KSP_PERSIST", 0) == 0;
+                      !dbg_nored;
   RowPush rpush{};
   HaloWait hwait{};
   if (fused3) {
@@ -825,68 +824,8 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     hwait.recv_mask = H->recv_mask;
     hwait.err = H->p2p_err;
   }
-  // EXPERIMENTAL (ksp_persist.cuh, off by default): one cooperative kernel per chunk of iterations
-  bool persist = false;
-  CgPersist pa{};
-  int pgrid = 0;
-  Tmp<GridBcast> bcast;
-  if (env_int("IIFE_KSP_PERSIST", 0) != 0 && A->sell_state == 1 && (!dist || p2p) && !dbg_nohalo && !dbg_nored) {
-    int coop = 0, per_sm = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device);
-    if (dist) IIFE_TRY(mat_ensure_sell_order(A, H->n_owned));
-    if (coop && (!dist || A->sell_order) &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persist<4>, VEC_THREADS, 0) == cudaSuccess && per_sm >= 1) {
-      int64_t need = std::max<int64_t>((n + VEC_THREADS - 1) / VEC_THREADS, (A->sell_slices + 7) / 8);
-      int64_t gmax = std::min<int64_t>((int64_t)c.sm_count * per_sm, MAX_PARTIALS);
-      pgrid = (int)std::max<int64_t>(1, std::min<int64_t>(need, gmax));
-      IIFE_TRY(bcast.alloc(1));
-      IIFE_CUDA(cudaMemsetAsync(bcast.p, 0, sizeof(GridBcast), c.stream));
-      pa.sell_ptr = A->sell_ptr;
-      pa.sell_cptr = A->sell_cptr;
-      pa.sell_col = A->sell_col;
-      pa.sell_val = A->sell_val;
-      pa.n_rows = n;
-      pa.n_slices = A->sell_slices;
-      pa.order = dist ? A->sell_order : nullptr;
-      pa.n_interior = dist ? A->sell_n_interior : A->sell_slices;
-      pa.x = x;
-      pa.r = r.p;
-      pa.p = p.p;
-      pa.w = wv.p;
-      pa.dinv = dinv;
-      pa.sc = w.sc;
-      pa.fl = w.fl;
-      pa.hist = w.hist;
-      pa.hist_len = (long long)w.hist_len;
-      pa.partials = w.partials;
-      pa.bc = bcast.p;
-      pa.n_iters = chunk;
-      pa.dist = dist ? 1 : 0;
-      if (dist) {
-        pa.pr = pr;
-        for (int q = 0; q < P2P_MAX_RANKS; ++q) {
-          pa.pt.xbuf[q] = H->peer_xbuf[q];
-          pa.pt.mbox[q] = H->peer_mbox[q];
-          pa.pt.dst_start[q] = H->dst_start[q];
-        }
-        pa.mbox = H->mbox;
-        pa.send_idx = H->send_idx;
-        pa.send_peer = H->send_peer;
-        pa.send_off = H->send_off_dev;
-        pa.total_send = (long long)H->total_send;
-        pa.send_mask = H->send_mask;
-        pa.recv_mask = H->recv_mask;
-        pa.halo_seq = H->dev_seq;
-        pa.iter_ptr = H->dev_seq + 2;
-        pa.push_counter = H->p2p_counter;
-      }
-      persist = true;
-    } else {
-      cudaGetLastError();
-    }
-  }
   // NCCL calls inside the loop: keep to plain stream launches (no graph capture) in that case
-  const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && (!dist || p2p) && !persist;
+  const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && (!dist || p2p);
   auto enqueue_iteration = [&](int k) -> int {
     if (fused3) {
       P2PRed prk = pr;
@@ -990,12 +929,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
   auto enqueue_chunk = [&](int slot) -> int {
-    if (persist) {
-      void *kargs[] = {(void *)&pa};
-      cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_cg_persist<4>, dim3(pgrid), dim3(VEC_THREADS), kargs, 0, c.stream);
-      if (e != cudaSuccess) return set_err(IIFE_ERR_CUDA, "cooperative CG launch: %s", cudaGetErrorString(e));
-      c.launches++;
-    } else if (exec) {
+    if (exec) {
       cudaError_t e = cudaGraphLaunch(exec, c.stream);
       if (e != cudaSuccess) return set_err(IIFE_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
       c.launches += launches_per_chunk;
@@ -1133,7 +1067,7 @@ static int fgmres_solve(Mat *A, Halo *H, const double *dinv, const double *b, do
       if (dist && (rc = halo_exchange(H, Z[j])) != IIFE_OK) break;
       if ((rc = spmv_launch(A, 1.0, Z[j], 0.0, V[j + 1])) != IIFE_OK) break;
       IIFE_LAUNCH(k_gm_dots, g, VEC_THREADS, 0, V[j + 1], (double *const *)vtab.p, n, j, gs, w.fl, mpart.p,
-                  w.counters + 1);
+                  w.counters + 1, j);
       if (dist) {
         if ((rc = allreduce_sum(gs.H + (size_t)j * (gs.m + 1), j + 1)) != IIFE_OK) break;
         IIFE_LAUNCH(k_gm_update<true>, g, VEC_THREADS, (size_t)(j + 1) * sizeof(double), V[j + 1], (double *const *)vtab.p,
@@ -1178,6 +1112,157 @@ static int fgmres_solve(Mat *A, Halo *H, const double *dinv, const double *b, do
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// GCR (PETSc's KSPGCR, restart 30, reference common.py:559-560: method='gcr'), single GPU.  Per step k of a cycle:
+//   s_k = D^-1 r;  v_k = A s_k;  c_i = (v_k, v_i), i < k (classical Gram-Schmidt: all dots first);
+//   v_k -= sum c_i v_i;  s_k -= sum c_i s_i;  nrm = ||v_k||;  v_k /= nrm;  s_k /= nrm;
+//   x += (r, v_k) s_k;  r -= (r, v_k) v_k;  test ||r|| (unpreconditioned norm, reference norm ||b||)
+// The residual is recomputed from x at the start of every cycle.  Same device-side bookkeeping as FGMRES: F_LOC_IT is
+// the step inside the cycle, every kernel is gated by it and by the reason flag, the host polls once per chunk.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gcr_pc(const double *__restrict__ r, const double *__restrict__ dinv, double *__restrict__ s, int64_t n,
+         const int *__restrict__ fl, int k) {
+  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != k) return;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s[i] = (dinv ? dinv[i] : 1.0) * r[i];
+}
+
+// v_k -= sum_{i<k} c_i v_i, s_k -= sum_{i<k} c_i s_i; (r, v_k) and (v_k, v_k); the last CTA turns them into the scale
+// 1/||v_k|| (S_SCALE) and the step length (r, v_k)/||v_k|| (S_TT)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gcr_update(double *__restrict__ v, double *__restrict__ sv, const double *__restrict__ r, double *const *__restrict__ V,
+             double *const *__restrict__ SV, int64_t n, int k, GmresSmall gs, double *sc, const int *__restrict__ fl,
+             double *partials, unsigned int *counter) {
+  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != k) return;
+  extern __shared__ double csh[];  // k coefficients
+  __shared__ double red[32];
+  __shared__ double out[2];
+  __shared__ bool last;
+  const double *ck = k > 0 ? gs.H + (size_t)(k - 1) * (gs.m + 1) : nullptr;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) csh[i] = ck[i];
+  __syncthreads();
+  double acc[2] = {0.0, 0.0};
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double a = v[i], b = sv[i];
+    for (int q = 0; q < k; ++q) {
+      const double c = csh[q];
+      a = fma(-c, V[q][i], a);
+      b = fma(-c, SV[q][i], b);
+    }
+    v[i] = a;
+    sv[i] = b;
+    acc[0] = fma(r[i], a, acc[0]);
+    acc[1] = fma(a, a, acc[1]);
+  }
+  if (grid_reduce<2>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
+    const double nrm = sqrt(out[1]);
+    sc[S_SCALE] = 1.0 / nrm;  // nrm == 0 (breakdown) gives inf/NaN, which the convergence test reports as NANORINF
+    sc[S_TT] = out[0] / nrm;
+  }
+}
+
+// normalise v_k, s_k; x += tt s_k; r -= tt v_k; ||r|| -> iteration count, history, convergence test
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gcr_apply(double *__restrict__ v, double *__restrict__ sv, double *__restrict__ x, double *__restrict__ r, int64_t n, int k,
+            double *sc, int *fl, double *partials, unsigned int *counter, double *hist, long long hist_len) {
+  if (fl[F_REASON] != 0 || fl[F_LOC_IT] != k) return;
+  __shared__ double red[32];
+  __shared__ double out[1];
+  __shared__ bool last;
+  const double scale = sc[S_SCALE], tt = sc[S_TT];
+  double acc[1] = {0.0};
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double vi = v[i] * scale, si = sv[i] * scale;
+    v[i] = vi;
+    sv[i] = si;
+    x[i] = fma(tt, si, x[i]);
+    const double ri = fma(-tt, vi, r[i]);
+    r[i] = ri;
+    acc[0] = fma(ri, ri, acc[0]);
+  }
+  if (grid_reduce<1>(acc, partials, counter, out, red, &last) && threadIdx.x == 0) {
+    const double res = sqrt(out[0]);
+    const int its = fl[F_ITS] + 1;
+    fl[F_ITS] = its;
+    fl[F_LOC_IT] = k + 1;
+    sc[S_RES] = res;
+    log_hist(hist, hist_len, its, res);
+    converged_default(sc, fl, its, res);
+    if (fl[F_REASON] == 0 && its >= fl[F_MAXIT]) fl[F_REASON] = IIFE_KSP_DIVERGED_ITS;
+  }
+}
+
+static int gcr_solve(Mat *A, const double *dinv, const double *b, double *x, int64_t max_it, int restart, KspWork &w,
+                     HostFlags *hf) {
+  Ctx &c = ctx();
+  const int64_t n = A->n_rows;
+  int m = restart > 0 ? restart : 30;
+  if (m > 1000) m = 1000;
+  const int g = vec_grid(n);
+  Tmp<double> small, r, mpart;
+  const size_t hs = (size_t)(m + 1) * m;
+  IIFE_TRY(small.alloc(hs + 4 * (size_t)(m + 1)));
+  IIFE_CUDA(cudaMemsetAsync(small.p, 0, (hs + 4 * (size_t)(m + 1)) * sizeof(double), c.stream));
+  GmresSmall gs;
+  gs.H = small.p;
+  gs.cs = small.p + hs;
+  gs.sn = gs.cs + (m + 1);
+  gs.rs = gs.sn + (m + 1);
+  gs.y = gs.rs + (m + 1);
+  gs.m = m;
+  IIFE_TRY(r.alloc((size_t)n));
+  IIFE_TRY(mpart.alloc((size_t)(m + 1) * g));
+  const size_t n_pad = ((size_t)n + 31) & ~(size_t)31;
+  Tmp<double> slab;  // v_0..v_{m-1}, s_0..s_{m-1}
+  IIFE_TRY(slab.alloc(2 * (size_t)m * n_pad));
+  std::vector<double *> V((size_t)m), SV((size_t)m);
+  for (int k = 0; k < m; ++k) {
+    V[(size_t)k] = slab.p + (size_t)k * n_pad;
+    SV[(size_t)k] = slab.p + (size_t)(m + k) * n_pad;
+  }
+  Tmp<double *> vtab, stab;
+  IIFE_TRY(vtab.alloc((size_t)m));
+  IIFE_TRY(stab.alloc((size_t)m));
+  IIFE_CUDA(cudaMemcpyAsync(vtab.p, V.data(), (size_t)m * sizeof(double *), cudaMemcpyHostToDevice, c.stream));
+  IIFE_CUDA(cudaMemcpyAsync(stab.p, SV.data(), (size_t)m * sizeof(double *), cudaMemcpyHostToDevice, c.stream));
+  IIFE_CUDA(cudaStreamSynchronize(c.stream));  // the host tables go out of use
+  int chunk = env_int("IIFE_KSP_CHUNK", 10);
+  if (chunk < 1) chunk = 1;
+  bool first_cycle = true;
+  int64_t enq_total = 0;
+  for (;;) {
+    // cycle start: r = b - A x, ||r|| (and ||b|| the first time), test
+    IIFE_LAUNCH(k_copy_gated, g, VEC_THREADS, 0, b, r.p, n, (const int *)w.fl);
+    IIFE_TRY(spmv_launch(A, -1.0, x, 1.0, r.p));
+    IIFE_LAUNCH(k_gm_cycle_start<false>, g, VEC_THREADS, 0, r.p, b, n, w.sc, w.fl, gs, w.partials, w.counters, w.hist,
+                (long long)w.hist_len, first_cycle ? 1 : 0);
+    first_cycle = false;
+    IIFE_TRY(poll_flags(w, hf));
+    if (hf->fl[F_REASON] != 0) return IIFE_OK;
+    for (int k = 0; k < m; ++k) {
+      IIFE_LAUNCH(k_gcr_pc, g, VEC_THREADS, 0, r.p, dinv, SV[(size_t)k], n, w.fl, k);
+      IIFE_TRY(spmv_launch(A, 1.0, SV[(size_t)k], 0.0, V[(size_t)k]));  // harmless after convergence: v_k is not read any more
+      if (k > 0)
+        IIFE_LAUNCH(k_gm_dots, g, VEC_THREADS, 0, V[(size_t)k], (double *const *)vtab.p, n, k - 1, gs, w.fl, mpart.p,
+                    w.counters + 1, k);
+      IIFE_LAUNCH(k_gcr_update, g, VEC_THREADS, (size_t)(k + 1) * sizeof(double), V[(size_t)k], SV[(size_t)k], r.p,
+                  (double *const *)vtab.p, (double *const *)stab.p, n, k, gs, w.sc, w.fl, w.partials, w.counters);
+      IIFE_LAUNCH(k_gcr_apply, g, VEC_THREADS, 0, V[(size_t)k], SV[(size_t)k], x, r.p, n, k, w.sc, w.fl, w.partials,
+                  w.counters + 2, w.hist, (long long)w.hist_len);
+      ++enq_total;
+      if ((k + 1) % chunk == 0 || k + 1 == m) {
+        IIFE_CHECK_LAUNCH();
+        IIFE_TRY(poll_flags(w, hf));
+        if (hf->fl[F_REASON] != 0) return IIFE_OK;
+      }
+    }
+    if (enq_total > max_it + m) return set_err(IIFE_ERR_STATE, "GCR driver ran past max_it without a reason");
+  }
+}
+
 __global__ void k_ksp_setup(double *sc, int *fl, double rtol, double atol, double dtol, int maxit) {
   for (int k = 0; k < S_COUNT; ++k) sc[k] = 0.0;
   for (int k = 0; k < F_COUNT; ++k) fl[k] = 0;
@@ -1201,7 +1286,9 @@ static int ksp_solve_common(Mat *A, Halo *H, int ksp_type, int pc_type, double r
     return set_err(IIFE_ERR_ARG, "local operator %lld x %lld does not match the halo (%lld owned + %lld ghost)", (long long)A->n_rows,
                    (long long)A->n_cols, (long long)H->n_owned, (long long)H->n_ghost);
   if (H && mem != IIFE_MEM_DEVICE) return set_err(IIFE_ERR_ARG, "the row-partitioned solver takes device vectors");
-  if (ksp_type != IIFE_KSP_CG && ksp_type != IIFE_KSP_FGMRES) return set_err(IIFE_ERR_ARG, "unknown ksp_type %d", ksp_type);
+  if (ksp_type != IIFE_KSP_CG && ksp_type != IIFE_KSP_FGMRES && ksp_type != IIFE_KSP_GCR)
+    return set_err(IIFE_ERR_ARG, "unknown ksp_type %d", ksp_type);
+  if (ksp_type == IIFE_KSP_GCR && H) return set_err(IIFE_ERR_UNSUPPORTED, "GCR is not available on the row-partitioned path");
   if (pc_type != IIFE_PC_NONE && pc_type != IIFE_PC_JACOBI) return set_err(IIFE_ERR_ARG, "unknown pc_type %d", pc_type);
   if (max_it < 0) max_it = 0;
   if (max_it > 0x7ffffff0LL) max_it = 0x7ffffff0LL;
@@ -1254,6 +1341,8 @@ static int ksp_solve_common(Mat *A, Halo *H, int ksp_type, int pc_type, double r
     hf->fl[F_REASON] = IIFE_KSP_CONVERGED_ATOL;
   } else if (ksp_type == IIFE_KSP_CG) {
     rc = cg_solve(A, H, dinv, bd, xd, max_it, w, hf);
+  } else if (ksp_type == IIFE_KSP_GCR) {
+    rc = gcr_solve(A, dinv, bd, xd, max_it, restart, w, hf);
   } else {
     rc = fgmres_solve(A, H, dinv, bd, xd, max_it, restart, w, hf);
   }

@@ -104,8 +104,7 @@ struct Plan {
   size_t tp_blob_bytes = 0;
   long long *tp_blob_off = nullptr;
   int *tp_chunks = nullptr, *tp_rows = nullptr, *tp_rest_rows = nullptr;
-  int2 *tp_rowinfo = nullptr;  // per templated row: (start of its row of R, start of its row of A_b)
-  int tp_s_cap = 0, tp_o1_cap = 0, tp_o2_cap = 0;
+  int tp_s_cap = 0, tp_o1_cap = 0, tp_o2_cap = 0, tp_n0_cap = 32;
   double tp_use1 = 0.0, tp_use2 = 0.0;  // mean lane use of the two gather stages, weighted by rows
 };
 
@@ -574,7 +573,6 @@ __global__ void k_ptap_numeric(PtapArgs a) {
 }  // namespace iife
 #include "ptap_warp.cuh"
 #include "ptap_slots.cuh"
-#include "ptap_slots2.cuh"
 #include "ptap_prog.cuh"
 #include "ptap_tpl.cuh"
 namespace iife {
@@ -762,8 +760,6 @@ static void tpl_free(Plan *P) {
   if (P->tp_blob_off) dev_free_t(P->tp_blob_off, (size_t)P->tp_n_tpl);
   if (P->tp_chunks) dev_free_t(P->tp_chunks, (size_t)P->tp_n_chunks * 3);
   if (P->tp_rows) dev_free_t(P->tp_rows, (size_t)P->tp_n_rows);
-  if (P->tp_rowinfo) dev_free_t(P->tp_rowinfo, (size_t)P->tp_n_rows);
-  P->tp_rowinfo = nullptr;
   if (P->tp_rest_rows) dev_free_t(P->tp_rest_rows, (size_t)P->tp_list_n);
   P->tp_blobs = nullptr;
   P->tp_blob_off = nullptr;
@@ -1282,17 +1278,18 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
   std::vector<int> valid((size_t)n_tpl, 0);
   std::vector<long long> blob_off((size_t)n_tpl, 0);
   size_t blob_total = 0;
-  int s_cap = 2, o1_cap = 2, o2_cap = 2, n_valid = 0;
+  int s_cap = 2, o1_cap = 2, o2_cap = 2, n0_max = 1, n_valid = 0;
   for (int t = 0; t < n_tpl; ++t) {
     tpl::Raw r;
     tpl_parse_raw(raw.data() + (size_t)t * TPLR_STRIDE, r);
     tpl::Program &pr = progs[(size_t)t];
     if (!tpl::compile(r, pr)) continue;
-    if (((size_t)pr.s_cap + pr.o1_cap + pr.o2_cap) * 8 + tpl::MAX_N0 * 16 > warp_budget) continue;
+    if (((size_t)pr.s_cap + pr.o1_cap + pr.o2_cap) * 8 > warp_budget) continue;  // per row; a warp holds two
     valid[(size_t)t] = 1;
     ++n_valid;
     blob_off[(size_t)t] = (long long)blob_total;
     blob_total += pr.blob.size();
+    n0_max = std::max(n0_max, pr.n0);
     s_cap = std::max(s_cap, pr.s_cap);
     o1_cap = std::max(o1_cap, pr.o1_cap);
     o2_cap = std::max(o2_cap, pr.o2_cap);
@@ -1337,8 +1334,6 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
   IIFE_TRY(dev_alloc_t(&P->tp_rows, (size_t)n_t));
   IIFE_TRY(dev_alloc_t(&P->tp_rest_rows, (size_t)n));
   IIFE_LAUNCH(k_tpl_scatter, grid_for(n), 256, 0, list, tpl_of.p, spos.p, off_sorted.p, off_rest.p, (long long)n, P->tp_rows, P->tp_rest_rows);
-  IIFE_TRY(dev_alloc_t(&P->tp_rowinfo, (size_t)n_t));
-  IIFE_LAUNCH(k_tpl_rowinfo, grid_for(n_t), 256, 0, (const int *)P->tp_rows, (long long)n_t, a.mt_rowptr, a.c_rowptr, P->tp_rowinfo);
   IIFE_LAUNCH(k_tpl_ranges, (n_tpl + 255) / 256, 256, 0, sel_d.p, n_tpl, off_sorted.p, ranges_d.p);
   IIFE_CHECK_LAUNCH();
   std::vector<int> ranges((size_t)2 * n_tpl);
@@ -1373,6 +1368,7 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
   pt.lap("tpl: membership + lists");
   P->tp_rest5 = rest5;
   P->tp_rest6 = n_rest - rest5;
+  P->tp_n0_cap = (n0_max + 31) & ~31;
   P->tp_s_cap = s_cap;
   P->tp_o1_cap = o1_cap;
   P->tp_o2_cap = o2_cap;
@@ -1387,22 +1383,35 @@ static int tpl_launch(Plan *P, PtapArgs a) {
   t.chunks = P->tp_chunks;
   t.n_chunks = P->tp_n_chunks;
   t.rows = P->tp_rows;
-  t.rowinfo = P->tp_rowinfo;
   t.s_cap = P->tp_s_cap;
   t.o1_cap = P->tp_o1_cap;
   t.o2_cap = P->tp_o2_cap;
-  const size_t per_warp = (size_t)tpl::MAX_N0 * 16 + ((size_t)t.s_cap + t.o1_cap + t.o2_cap) * 8;
+  t.n0_cap = P->tp_n0_cap;
+  // two rows per warp: sbegA/B + 2 x (S, O1, O2)
+  const size_t row_bytes = ((size_t)t.s_cap + t.o1_cap + t.o2_cap) * 8;
   const size_t smem_max = (size_t)(c.max_smem_optin ? c.max_smem_optin : 227 * 1024);
-  int wpc = std::max(1, std::min(env_int("IIFE_TPL_WPC", 8), 32));
-  while (wpc > 1 && per_warp * wpc > smem_max) wpc >>= 1;
-  const size_t smem = per_warp * wpc;
-  if (smem > smem_max) return set_err(IIFE_ERR_STATE, "template kernel needs %zu B of shared memory per warp", per_warp);
-  if (smem > 48 * 1024) IIFE_CUDA(cudaFuncSetAttribute(k_ptap_numeric_tpl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ptap_numeric_tpl, wpc * 32, smem) != cudaSuccess || per_sm < 1) {
-    cudaGetLastError();
-    per_sm = 1;
+  const size_t per_warp = (size_t)t.n0_cap * 8 + 2 * row_bytes;
+  // warps per CTA: whatever keeps the most warps resident per SM (shared memory is the limit; the kernel's latency
+  // tolerance is its warp count: 24 resident warps ran 8.2 ms where 16 ran 10.0 ms)
+  if (per_warp > smem_max) return set_err(IIFE_ERR_STATE, "template kernel needs %zu B of shared memory per warp", per_warp);
+  IIFE_CUDA(cudaFuncSetAttribute(k_ptap_numeric_tpl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  int wpc = 1, per_sm = 1, best_warps = 0;
+  const int forced = env_int("IIFE_TPL_WPC", 0);
+  for (int cand = 8; cand >= 1; --cand) {
+    if (forced > 0 && cand != std::min(forced, 8)) continue;
+    if (per_warp * cand > smem_max) continue;
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_ptap_numeric_tpl, cand * 32, per_warp * cand) != cudaSuccess || blocks < 1) {
+      cudaGetLastError();
+      blocks = 1;
+    }
+    if (blocks * cand > best_warps) {
+      best_warps = blocks * cand;
+      wpc = cand;
+      per_sm = blocks;
+    }
   }
+  const size_t smem = per_warp * wpc;
   const int64_t ctas = std::min<int64_t>(((int64_t)t.n_chunks + wpc - 1) / wpc, (int64_t)c.sm_count * per_sm);
   k_ptap_numeric_tpl<<<(int)ctas, wpc * 32, smem, c.stream>>>(a, t);
   c.launches++;
@@ -1420,6 +1429,17 @@ static int prog_ensure(Plan *P, const Mat *M, PtapArgs a) {
   const int64_t n = a.n_rows;
   const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)c.sm_count * 8);
   ProgArgs pg{};
+  if (P->pg_state == 1) pg_free(P);  // values of M changed: rebuild from scratch
+  struct Guard {  // an allocation failure below leaves no half-built program behind
+    Plan *P;
+    bool armed = true;
+    ~Guard() {
+      if (armed) {
+        pg_free(P);
+        P->pg_state = -1;
+      }
+    }
+  } guard{P};
   if (P->pg_state == 0) {
     P->pg_rows = n;
     IIFE_TRY(dev_alloc_t(&P->pg_steps, (size_t)n));
@@ -1431,10 +1451,7 @@ static int prog_ensure(Plan *P, const Mat *M, PtapArgs a) {
     IIFE_TRY(exclusive_scan_i32_i64(P->pg_steps, P->pg_off, n, &total));
     size_t free_b = 0, total_b = 0;
     IIFE_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    if ((size_t)total * 32 * 9 + ((size_t)n * 33) > free_b / 2) {
-      P->pg_state = -1;  // keep the scatter kernels
-      return IIFE_OK;
-    }
+    if ((size_t)total * 32 * 9 + ((size_t)n * 33) > free_b / 2) return IIFE_OK;  // guard: freed, state -1 (slot kernel)
     P->pg_total_steps = total;
     IIFE_TRY(dev_alloc_t(&P->pg_slot, (size_t)total * 32));
     IIFE_TRY(dev_alloc_t(&P->pg_val, (size_t)total * 32));
@@ -1447,12 +1464,13 @@ static int prog_ensure(Plan *P, const Mat *M, PtapArgs a) {
   pg.maxg = P->pg_maxg;
   pg.slot = P->pg_slot;
   pg.val = P->pg_val;
-  IIFE_CUDA(cudaMemsetAsync(P->pg_slot, 0xFF, (size_t)(P->pg_total_steps ? P->pg_total_steps * 32 : 1), c.stream));
+  if (P->pg_total_steps) IIFE_CUDA(cudaMemsetAsync(P->pg_slot, 0xFF, (size_t)P->pg_total_steps * 32, c.stream));
   IIFE_LAUNCH(k_prog_build<true>, grid, 256, 0, a, pg);
   IIFE_CHECK_LAUNCH();
   P->pg_m_uid = M->uid;
   P->pg_m_version = M->val_version;
   P->pg_state = 1;
+  guard.armed = false;
   return IIFE_OK;
 }
 
@@ -1462,6 +1480,15 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
     return set_err(IIFE_ERR_STATE, "PtAP numeric: operands do not match the symbolic plan (shape/nnz)");
   if (P->general_rap != (R != nullptr) || (R && (R->n_rows != P->n_b || R->nnz != P->nnzR)))
     return set_err(IIFE_ERR_STATE, "PtAP numeric: restriction operand does not match the symbolic plan");
+  {  // the slot-plan / template kernels never look at column indices: a different pattern of the same size would give a
+     // silently wrong A_b.  The fingerprints are cached per matrix, so this is three 64-bit compares per call.
+    uint64_t fM = 0, fA = 0, fR = 0;
+    IIFE_TRY(mat_fingerprint(M, &fM));
+    IIFE_TRY(mat_fingerprint(A, &fA));
+    if (R) IIFE_TRY(mat_fingerprint(R, &fR));
+    if (fM != P->fpM || fA != P->fpA || (R && fR != P->fpR))
+      return set_err(IIFE_ERR_STATE, "PtAP numeric: the sparsity pattern of an operand differs from the one the plan was built for");
+  }
   Mat *C = *C_io;
   bool created = false;
   if (!C) {
@@ -1532,13 +1559,9 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
       int lg2 = a.logG2 < 2 ? 2 : (a.logG2 > 5 ? 5 : a.logG2);
       if (const char *e1v = getenv("IIFE_PTAP_LG1")) lg1 = atoi(e1v);
       if (const char *e2v = getenv("IIFE_PTAP_LG2")) lg2 = atoi(e2v);
-      bool ctail = true;  // compacted second pass over long operand rows (ptap_slots.cuh): 24.9 -> 22.3 ms
-      if (const char *et = getenv("IIFE_PTAP_CTAIL")) ctail = atoi(et) != 0;
-      bool v2 = false;  // experimental kernel of ptap_slots2.cuh (not yet validated on a GPU)
-      if (const char *e2k = getenv("IIFE_PTAP_V2")) v2 = atoi(e2k) != 0;
-      if (sb == 0) {  // experimental stage-2 gather program (ptap_prog.cuh): small-row bin only
-        const char *e3 = getenv("IIFE_PTAP_V3");
-        if (e3 && atoi(e3) != 0 && SLOT_CAP2[0] <= 32 && SLOT_CAP1[0] < PROG_IDLE) {
+      if (sb == 0) {  // stage 2 as a per-row gather program (ptap_prog.cuh): small-row bin only, while it fits in memory
+        const char *e3 = getenv("IIFE_PTAP_PROG");
+        if ((!e3 || atoi(e3) != 0) && SLOT_CAP2[0] <= 32 && SLOT_CAP1[0] < PROG_IDLE) {
           if ((rc = prog_ensure(P, M, a)) != IIFE_OK) break;
           prog_kernel_t pk = P->pg_state == 1 ? pick_prog_kernel(lg1) : nullptr;
           if (pk) {
@@ -1570,11 +1593,10 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
           }
         }
       }
-      slot_kernel_t kern = v2 ? pick_slot2_kernel(lg1, lg2) : pick_slot_kernel(lg1, lg2, ctail);
+      slot_kernel_t kern = pick_slot_kernel(lg1, lg2);
       if (!kern) { rc = set_err(IIFE_ERR_ARG, "no slot kernel for group sizes 2^%d / 2^%d", lg1, lg2); break; }
       int cap1 = SLOT_CAP1[sb], cap2 = SLOT_CAP2[sb];
-      size_t per_warp = v2 ? slot2_per_warp_bytes(lg1, lg2, cap1, cap2)
-                           : ((size_t)(32 >> lg1) * cap1 + (size_t)(32 >> lg2) * cap2) * 8 + SLOT_TAIL_BYTES;
+      size_t per_warp = slot_per_warp_bytes(lg1, lg2, cap1, cap2);
       size_t smem_max = (size_t)(c.max_smem_optin ? c.max_smem_optin : 227 * 1024);
       int wpc = 8;
       if (const char *ew = getenv("IIFE_PTAP_WPC")) wpc = atoi(ew);

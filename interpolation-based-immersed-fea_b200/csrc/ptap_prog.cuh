@@ -1,9 +1,10 @@
-// ptap_prog.cuh — EXPERIMENTAL third version of the numeric PtAP for the small-row bin (intermediate row <= 128,
-// output row <= 32 entries: every row of the trilinear cube), selected with IIFE_PTAP_V3=1 and OFF by default:
-// designed from the cost model in ROUND_NOTES.md, validated as an algorithm by a CPU emulation against the oracle,
-// compiled, but not yet run on a GPU.
+// ptap_prog.cuh — numeric PtAP for rows of the small bin (intermediate row <= 128, output row <= 32 entries) that
+// did NOT find a template (ptap_tpl.cuh): stage 2 runs a per-row gather program built once per (plan, values of M).
+// Measured in round 2 at N_b=184 with templates disabled: 11.7 ms against 18.9 ms for the slot kernel alone
+// (ptap_slots.cuh); it costs 9 bytes of program per padded stage-2 term (33 GB for the whole cube), so it is used
+// only while the program fits half the free device memory (IIFE_PTAP_PROG=0 disables it).
 //
-// Stage 1 (H1 = Mt[i,:] * A) is the v2 code (ptap_slots2.cuh).  Stage 2 (A_b[i,:] = H1 * M[K_i,:]) no longer
+// Stage 1 (H1 = Mt[i,:] * A) is the slot-plan code (ptap_slots.cuh).  Stage 2 (A_b[i,:] = H1 * M[K_i,:]) no longer
 // scatters: M does not change between numeric calls in the reference's workflow (only A_f does), so the stage is
 // compiled once per (plan, values of M) into a GATHER PROGRAM per output row:
 //   * the terms of the row are grouped by output entry l; entry l owns g_l = ceil(cnt_l / S) consecutive lanes,

@@ -1,4 +1,5 @@
-// ptap_slots.cuh — hash-free numeric PtAP for ordinary rows, included by ptap.cu.
+// ptap_slots.cuh — hash-free numeric PtAP for ordinary rows (per-row kernel: every row has its own slot plan), included
+// by ptap.cu.  Rows that share their structure with many others take the template kernel of ptap_tpl.cuh instead.
 //
 // The pattern never changes between numeric calls (every Newton iteration / time step of the reference
 // re-runs AT_R_A on the same sparsity, common.py:432-435), so the symbolic phase records once, for every
@@ -15,12 +16,22 @@
 // Layout per warp in shared memory: h1v[NG1][cap1] then h2v[NG2][cap2] (fp64), NG = 32 / lanes-per-row.
 // Rows qualify when both the intermediate and the output row have <= 256 entries (slot bytes);
 // everything else stays on the hashing kernels of ptap.cu / ptap_warp.cuh.
+//
+// Kernel notes (second version, measured in round 2: 24.0 -> 18.9 ms at N_b=184 against the first one, which is gone):
+//   * the 32 item descriptors of a chunk {w, beg, off, len} are staged once in shared memory (16 B each) and
+//     every step reads its item's descriptor with one broadcast LDS.128 instead of 5 shuffles;
+//   * the privatised accumulator copies are padded by one double, so that the same slot in different copies
+//     falls into different banks;
+//   * operand rows longer than the lane group are finished in a compacted second pass;
+//   * accumulators are cleared as one contiguous range.
+// Summation order per output entry: main pass in item order per lane group, then the compacted second pass, then
+// the copies in ascending order — deterministic.
 #pragma once
+
 
 namespace iife {
 
-// Tuning knob (compile time): `make EXTRA_NVCCFLAGS=-DIIFE_SLOT_MINBLOCKS=4` lets ptxas use 64 registers for the
-// slot-plan kernels (its own choice for <4,2> is 48 registers + 24 bytes of spills); unmeasured so far.
+// Tuning knob (compile time): minBlocks of the slot-plan kernels (4 = 64 registers: ptxas' own choice is 48 + spills)
 #ifndef IIFE_SLOT_MINBLOCKS
 #define IIFE_SLOT_MINBLOCKS 0
 #endif
@@ -30,110 +41,111 @@ namespace iife {
 #define IIFE_SLOT_BOUNDS __launch_bounds__(256)
 #endif
 
-constexpr int PS_BATCH = 4;
 constexpr int SLOT_TAIL_BYTES = 32;  // one lane number per long item of a 32-item chunk
+typedef void (*slot_kernel_t)(PtapArgs, int, int);
 
-// items: one per lane (beg/len/w/off in registers); entries e of item `it` add w * x_val[beg+e] into
-// hv[group][slots[off+e]].
-//
-// Operand rows longer than the lane group (M rows of 8 entries with 4 lanes per row: one row in eight of the
-// trilinear operator) need a second pass.  CTAIL = false walks all items again and lets the short ones idle;
-// CTAIL = true first compacts the lane numbers of the long items into `tail_src` (32 bytes of shared memory per
-// warp), so the second pass costs steps only for the items that need it.
-template <int LG, bool CTAIL>
-__device__ __forceinline__ void slot_stage(int cnt, int my_beg, int my_len, double my_w, int my_off,
-                                           const double *__restrict__ x_val, const unsigned char *__restrict__ slots,
-                                           double *hv, int cap, int lane, unsigned char *tail_src) {
+constexpr int PS2_BATCH = 4;
+constexpr int PS2_DESC_BYTES = 32 * 16;
+
+struct __align__(16) SlotDesc {
+  double w;
+  int beg;
+  unsigned offlen;  // off (low 16 bits: <= 32 * 256) | len << 16 (<= 256)
+};
+
+template <int LG>
+__device__ __forceinline__ void slot_stage2(int my_beg, int my_len, double my_w, int my_off,
+                                            const double *__restrict__ x_val, const unsigned char *__restrict__ slots,
+                                            double *hv, int stride, int lane, SlotDesc *desc, unsigned char *tail_src) {
   constexpr int G = 1 << LG, NG = 32 >> LG;
   const int g = lane >> LG, lg = lane & (G - 1);
-  double *hv_g = hv + (size_t)g * cap;
-  const int nsteps = (cnt + NG - 1) / NG;
-  for (int s0 = 0; s0 < nsteps; s0 += PS_BATCH) {
-    int sl[PS_BATCH];
-    double v[PS_BATCH];
+  double *hv_g = hv + (size_t)g * stride;
+  // every lane publishes its item (len == 0 beyond the end of the list)
+  {
+    SlotDesc d;
+    d.w = my_w;
+    d.beg = my_beg;
+    d.offlen = (unsigned)my_off | ((unsigned)my_len << 16);
+    desc[lane] = d;
+  }
+  __syncwarp();  // descriptor stores visible to the whole warp (the vote below is no memory barrier)
+  const unsigned live_mask = __ballot_sync(0xffffffffu, my_len > 0);
+  const unsigned long_mask = __ballot_sync(0xffffffffu, my_len > G);
+  if (live_mask == 0u) return;
+  const int n_items = 32 - __clz(live_mask);  // items are contiguous from lane 0, empty operand rows may sit between
+  const int nsteps = (n_items + NG - 1) / NG;
+  for (int s0 = 0; s0 < nsteps; s0 += PS2_BATCH) {
+    int sl[PS2_BATCH];
+    double v[PS2_BATCH];
 #pragma unroll
-    for (int b = 0; b < PS_BATCH; ++b) {
-      int it = (s0 + b) * NG + g;
-      int src = it & 31;
-      int beg = __shfl_sync(0xffffffffu, my_beg, src);
-      int len = __shfl_sync(0xffffffffu, my_len, src);
-      int off = __shfl_sync(0xffffffffu, my_off, src);
-      double w = __shfl_sync(0xffffffffu, my_w, src);
-      bool ok = (it < cnt) && (lg < len);
+    for (int b = 0; b < PS2_BATCH; ++b) {
+      const int it = (s0 + b) * NG + g;
       sl[b] = -1;
       v[b] = 0.0;
-      if (ok) {
-        sl[b] = (int)__ldg(slots + off + lg);
-        v[b] = w * __ldg(x_val + beg + lg);
+      if (it < 32) {
+        const SlotDesc d = desc[it];
+        const int len = (int)(d.offlen >> 16), off = (int)(d.offlen & 0xffffu);
+        if (lg < len) {
+          sl[b] = (int)__ldg(slots + (unsigned)(off + lg));
+          v[b] = d.w * __ldg(x_val + (unsigned)(d.beg + lg));
+        }
       }
     }
 #pragma unroll
-    for (int b = 0; b < PS_BATCH; ++b) {
+    for (int b = 0; b < PS2_BATCH; ++b) {
       __syncwarp();
       if (sl[b] >= 0) hv_g[sl[b]] += v[b];
     }
   }
-  const unsigned long_mask = __ballot_sync(0xffffffffu, my_len > G);  // my_len is 0 beyond cnt
-  if (CTAIL && long_mask) {
+  if (long_mask) {  // operand rows longer than the lane group: compacted second pass
     const int n_long = __popc(long_mask);
     if (my_len > G) tail_src[__popc(long_mask & ((1u << lane) - 1u))] = (unsigned char)lane;
     __syncwarp();
     for (int t0 = 0; t0 < n_long; t0 += NG) {
       const int idx = t0 + g;
-      const int src = idx < n_long ? (int)tail_src[idx] : 0;
-      int beg = __shfl_sync(0xffffffffu, my_beg, src);
-      int len = __shfl_sync(0xffffffffu, my_len, src);
-      int off = __shfl_sync(0xffffffffu, my_off, src);
-      double w = __shfl_sync(0xffffffffu, my_w, src);
-      if (idx >= n_long) len = 0;
-      for (int e = G + lg; __any_sync(0xffffffffu, e < len); e += G) {
-        int s1 = -1;
-        double v = 0.0;
-        if (e < len) {
-          s1 = (int)__ldg(slots + off + e);
-          v = w * __ldg(x_val + beg + e);
-        }
-        __syncwarp();
-        if (s1 >= 0) hv_g[s1] += v;
+      int len = 0, off = 0, beg = 0;
+      double w = 0.0;
+      if (idx < n_long) {
+        const SlotDesc d = desc[tail_src[idx]];
+        len = (int)(d.offlen >> 16);
+        off = (int)(d.offlen & 0xffffu);
+        beg = d.beg;
+        w = d.w;
       }
-    }
-  } else if (long_mask) {  // operand rows longer than G: remaining entries
-    for (int s = 0; s < nsteps; ++s) {
-      int it = s * NG + g;
-      int src = it & 31;
-      int beg = __shfl_sync(0xffffffffu, my_beg, src);
-      int len = __shfl_sync(0xffffffffu, my_len, src);
-      int off = __shfl_sync(0xffffffffu, my_off, src);
-      double w = __shfl_sync(0xffffffffu, my_w, src);
-      if (it >= cnt) len = 0;
       for (int e = G + lg; __any_sync(0xffffffffu, e < len); e += G) {
         int s1 = -1;
-        double v = 0.0;
+        double vv = 0.0;
         if (e < len) {
-          s1 = (int)__ldg(slots + off + e);
-          v = w * __ldg(x_val + beg + e);
+          s1 = (int)__ldg(slots + (unsigned)(off + e));
+          vv = w * __ldg(x_val + (unsigned)(beg + e));
         }
         __syncwarp();
-        if (s1 >= 0) hv_g[s1] += v;
+        if (s1 >= 0) hv_g[s1] += vv;
       }
     }
   }
-  __syncwarp();
+  __syncwarp();  // descriptors and tail_src are rewritten by the next chunk
 }
 
-template <int LG1, int LG2, bool CTAIL>
+template <int LG1, int LG2>
 __global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots(PtapArgs a, int cap1, int cap2) {
   constexpr int NG1 = 32 >> LG1, NG2 = 32 >> LG2;
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int wpc = blockDim.x >> 5;
-  // per warp: h1v[NG1][cap1], h2v[NG2][cap2] (fp64) and SLOT_TAIL_BYTES for the compacted second pass
-  const size_t per_warp = ((size_t)NG1 * cap1 + (size_t)NG2 * cap2) * 8 + SLOT_TAIL_BYTES;
-  double *h1v = (double *)(smem + per_warp * wic);
-  double *h2v = h1v + (size_t)NG1 * cap1;
-  unsigned char *tail_src = (unsigned char *)(h2v + (size_t)NG2 * cap2);
+  const int st1 = cap1 + 1, st2 = cap2 + 1;  // padded copy strides (doubles)
+  // per warp (16-byte aligned): desc[32], h1v[NG1][st1], h2v[NG2][st2], tail_src[32]
+  const size_t acc_doubles = ((size_t)NG1 * st1 + (size_t)NG2 * st2 + 1) & ~(size_t)1;
+  const size_t per_warp = PS2_DESC_BYTES + acc_doubles * 8 + SLOT_TAIL_BYTES;
+  unsigned char *base = smem + per_warp * wic;
+  SlotDesc *desc = (SlotDesc *)base;
+  double *h1v = (double *)(base + PS2_DESC_BYTES);
+  double *h2v = h1v + (size_t)NG1 * st1;
+  unsigned char *tail_src = base + PS2_DESC_BYTES + acc_doubles * 8;
   const int64_t warp_global = (int64_t)blockIdx.x * wpc + wic;
   const int64_t n_warps = (int64_t)gridDim.x * wpc;
+  const double *__restrict__ a_val = a.a_val;
+  const double *__restrict__ m_val = a.m_val;
 
   for (int64_t wi = warp_global; wi < a.n_rows; wi += n_warps) {
     const int i = a.rows[wi];
@@ -142,40 +154,35 @@ __global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots(PtapArgs a, int cap1, int 
     const int ib = __ldg(a.inter_rowptr + i), n1 = __ldg(a.inter_rowptr + i + 1) - ib;
     const unsigned char *s1 = a.slot1 + a.s1_off[i];
     const unsigned char *s2 = a.slot2 + a.s2_off[i];
-    // ---- clear the accumulators (only the used prefix of every private copy)
+    // ---- clear the accumulators: one contiguous range (h1v and h2v are adjacent), 16-byte stores
     {
-      const int n1r = (n1 + 1) & ~1, n2r = (n2 + 1) & ~1;
-      double2 z2 = make_double2(0.0, 0.0);
-#pragma unroll
-      for (int gg = 0; gg < NG1; ++gg)
-        for (int s = lane * 2; s < n1r; s += 64) *(double2 *)(h1v + (size_t)gg * cap1 + s) = z2;
-#pragma unroll
-      for (int gg = 0; gg < NG2; ++gg)
-        for (int s = lane * 2; s < n2r; s += 64) *(double2 *)(h2v + (size_t)gg * cap2 + s) = z2;
+      double2 *z = (double2 *)h1v;
+      const int n2x = (int)(acc_doubles >> 1);
+      const double2 z2 = make_double2(0.0, 0.0);
+      for (int s = lane; s < n2x; s += 32) z[s] = z2;
     }
     __syncwarp();
     // ---- stage 1: H1[slot] += Mt[i,j] * A[j,e]
     {
       int base_off = 0;
-      for (int base = 0; base < mt_n; base += 32) {
-        int q = base + lane;
+      for (int cbase = 0; cbase < mt_n; cbase += 32) {
+        const int q = cbase + lane;
         int my_beg = 0, my_len = 0;
         double my_w = 0.0;
         if (q < mt_n) {
           my_w = __ldg(a.mt_val + mt_b + q);
-          if (a.mt_abeg) {  // packed metadata: coalesced, no dependent gather
+          if (a.mt_abeg) {
             my_beg = __ldg(a.mt_abeg + mt_b + q);
             my_len = (int)__ldg(a.mt_alen + mt_b + q);
           } else {
-            int j = __ldg(a.mt_col + mt_b + q);
+            const int j = __ldg(a.mt_col + mt_b + q);
             my_beg = __ldg(a.a_rowptr + j);
             my_len = __ldg(a.a_rowptr + j + 1) - my_beg;
           }
         }
         int total;
-        int my_off = warp_excl_scan(my_len, lane, &total);
-        slot_stage<LG1, CTAIL>(min(32, mt_n - base), my_beg, my_len, my_w, my_off, a.a_val, s1 + base_off, h1v, cap1,
-                               lane, tail_src);
+        const int my_off = warp_excl_scan(my_len, lane, &total);
+        slot_stage2<LG1>(my_beg, my_len, my_w, my_off, a_val, s1 + base_off, h1v, st1, lane, desc, tail_src);
         base_off += total;
       }
     }
@@ -183,15 +190,15 @@ __global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots(PtapArgs a, int cap1, int 
     for (int q = lane; q < n1; q += 32) {
       double v = h1v[q];
 #pragma unroll
-      for (int gg = 1; gg < NG1; ++gg) v += h1v[(size_t)gg * cap1 + q];
+      for (int gg = 1; gg < NG1; ++gg) v += h1v[(size_t)gg * st1 + q];
       h1v[q] = v;
     }
     __syncwarp();
     // ---- stage 2: H2[slot] += H1[q] * M[k_q, e]
     {
       int base_off = 0;
-      for (int base = 0; base < n1; base += 32) {
-        int q = base + lane;
+      for (int cbase = 0; cbase < n1; cbase += 32) {
+        const int q = cbase + lane;
         int my_beg = 0, my_len = 0;
         double my_w = 0.0;
         if (q < n1) {
@@ -200,15 +207,14 @@ __global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots(PtapArgs a, int cap1, int 
             my_beg = __ldg(a.inter_mbeg + ib + q);
             my_len = (int)__ldg(a.inter_mlen + ib + q);
           } else {
-            int k = __ldg(a.inter_col + ib + q);
+            const int k = __ldg(a.inter_col + ib + q);
             my_beg = __ldg(a.m_rowptr + k);
             my_len = __ldg(a.m_rowptr + k + 1) - my_beg;
           }
         }
         int total;
-        int my_off = warp_excl_scan(my_len, lane, &total);
-        slot_stage<LG2, CTAIL>(min(32, n1 - base), my_beg, my_len, my_w, my_off, a.m_val, s2 + base_off, h2v, cap2,
-                               lane, tail_src);
+        const int my_off = warp_excl_scan(my_len, lane, &total);
+        slot_stage2<LG2>(my_beg, my_len, my_w, my_off, m_val, s2 + base_off, h2v, st2, lane, desc, tail_src);
         base_off += total;
       }
     }
@@ -216,21 +222,25 @@ __global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots(PtapArgs a, int cap1, int 
     for (int s = lane; s < n2; s += 32) {
       double v = h2v[s];
 #pragma unroll
-      for (int gg = 1; gg < NG2; ++gg) v += h2v[(size_t)gg * cap2 + s];
+      for (int gg = 1; gg < NG2; ++gg) v += h2v[(size_t)gg * st2 + s];
       a.c_val[cb + s] = v;
     }
     __syncwarp();
   }
 }
 
-typedef void (*slot_kernel_t)(PtapArgs, int, int);
-static slot_kernel_t pick_slot_kernel(int lg1, int lg2, bool ctail) {
-#define PSK(a_, b_) \
-  if (lg1 == a_ && lg2 == b_) return ctail ? k_ptap_numeric_slots<a_, b_, true> : k_ptap_numeric_slots<a_, b_, false>;
-  PSK(3, 2) PSK(3, 3) PSK(3, 4) PSK(3, 5)
-  PSK(4, 2) PSK(4, 3) PSK(4, 4) PSK(4, 5)
-  PSK(5, 2) PSK(5, 3) PSK(5, 4) PSK(5, 5)
-#undef PSK
+static size_t slot_per_warp_bytes(int lg1, int lg2, int cap1, int cap2) {
+  size_t acc = ((size_t)(32 >> lg1) * (cap1 + 1) + (size_t)(32 >> lg2) * (cap2 + 1) + 1) & ~(size_t)1;
+  return PS2_DESC_BYTES + acc * 8 + SLOT_TAIL_BYTES;
+}
+
+static slot_kernel_t pick_slot_kernel(int lg1, int lg2) {
+#define PSK2(a_, b_) \
+  if (lg1 == a_ && lg2 == b_) return k_ptap_numeric_slots<a_, b_>;
+  PSK2(3, 2) PSK2(3, 3) PSK2(3, 4) PSK2(3, 5)
+  PSK2(4, 2) PSK2(4, 3) PSK2(4, 4) PSK2(4, 5)
+  PSK2(5, 2) PSK2(5, 3) PSK2(5, 4) PSK2(5, 5)
+#undef PSK2
   return nullptr;
 }
 

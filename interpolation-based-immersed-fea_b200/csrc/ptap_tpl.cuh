@@ -250,13 +250,6 @@ __global__ void k_tpl_scatter(const int *__restrict__ rows, const int *__restric
   }
 }
 
-__global__ void k_tpl_rowinfo(const int *__restrict__ rows, long long n, const int *__restrict__ mt_rowptr,
-                              const int *__restrict__ c_rowptr, int2 *__restrict__ out) {
-  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; k < n; k += stride) out[k] = make_int2(mt_rowptr[rows[k]], c_rowptr[rows[k]]);
-}
-
 // out[2t], out[2t+1] = range of template t inside tpl_rows
 __global__ void k_tpl_ranges(const int *__restrict__ sel, int n_tpl, const int *__restrict__ off_sorted,
                              int *__restrict__ out) {
@@ -276,8 +269,8 @@ struct TplArgs {
   const int *chunks;          // [3 * n_chunks]: template, first row (index into rows), row count
   int n_chunks;
   const int *rows;            // templated rows, grouped by template, ascending inside a template
-  const int2 *rowinfo;        // per templated row: (start of its row of R, start of its row of A_b)
-  int s_cap, o1_cap, o2_cap;  // per-warp buffer sizes (entries)
+  int s_cap, o1_cap, o2_cap;  // per-row buffer sizes (entries)
+  int n0_cap;                 // operand starts per row (multiple of 32)
 };
 
 __device__ __forceinline__ double tpl_lds(unsigned addr) {
@@ -287,49 +280,71 @@ __device__ __forceinline__ double tpl_lds(unsigned addr) {
 }
 __device__ __forceinline__ void tpl_sts(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 
-// one gather stage: O[flush] = sum over the lane's run of  (COEF ? coef * SRC[src] : SRC[src])
+// One gather stage for the warp's TWO rows: O[flush] = sum over the lane's run of (COEF ? coef * SRC[src] : SRC[src]).
+// Every program word and coefficient is loaded and decoded once for both rows; row B's buffers sit at the constant
+// byte offset `delta` from row A's, so both rows use one address register.
 template <bool COEF>
-__device__ __forceinline__ void tpl_gather(int S, const unsigned *__restrict__ prog, const double *__restrict__ coef,
-                                           unsigned src_base, unsigned out_base, int lane) {
-  double acc = 0.0;
+__device__ __forceinline__ void tpl_gather2(int S, const unsigned *__restrict__ prog, const double *__restrict__ coef,
+                                            unsigned src_base, unsigned out_base, unsigned delta, int lane) {
+  double accA = 0.0, accB = 0.0;
+  prog += lane;
+  coef += lane;
   int s = 0;
   for (; s + 4 <= S; s += 4) {
     unsigned u[4];
     double c[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      u[b] = __ldg(prog + (s + b) * 32 + lane);
-      if (COEF) c[b] = __ldg(coef + (s + b) * 32 + lane);
+      u[b] = __ldg(prog + (s + b) * 32);
+      if (COEF) c[b] = __ldg(coef + (s + b) * 32);
     }
-    double v[4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) v[b] = tpl_lds(src_base + (u[b] & 0xFFFFu));
+    double vA[4], vB[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      acc = COEF ? fma(c[b], v[b], acc) : acc + v[b];
+      const unsigned ad = src_base + (u[b] & 0xFFFFu);
+      vA[b] = tpl_lds(ad);
+      vB[b] = tpl_lds(ad + delta);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      accA = COEF ? fma(c[b], vA[b], accA) : accA + vA[b];
+      accB = COEF ? fma(c[b], vB[b], accB) : accB + vB[b];
       const unsigned f = u[b] >> 16;
       if (f != tpl::NO_FLUSH) {
-        tpl_sts(out_base + f, acc);
-        acc = 0.0;
+        tpl_sts(out_base + f, accA);
+        tpl_sts(out_base + f + delta, accB);
+        accA = 0.0;
+        accB = 0.0;
       }
     }
   }
   for (; s < S; ++s) {
-    const unsigned u = __ldg(prog + s * 32 + lane);
-    const double v = tpl_lds(src_base + (u & 0xFFFFu));
-    acc = COEF ? fma(__ldg(coef + s * 32 + lane), v, acc) : acc + v;
+    const unsigned u = __ldg(prog + s * 32);
+    const unsigned ad = src_base + (u & 0xFFFFu);
+    const double vA = tpl_lds(ad), vB = tpl_lds(ad + delta);
+    if (COEF) {
+      const double c = __ldg(coef + s * 32);
+      accA = fma(c, vA, accA);
+      accB = fma(c, vB, accB);
+    } else {
+      accA += vA;
+      accB += vB;
+    }
     const unsigned f = u >> 16;
     if (f != tpl::NO_FLUSH) {
-      tpl_sts(out_base + f, acc);
-      acc = 0.0;
+      tpl_sts(out_base + f, accA);
+      tpl_sts(out_base + f + delta, accB);
+      accA = 0.0;
+      accB = 0.0;
     }
   }
 }
 
 // pieces of split destinations: round j adds the (j+1)-th piece of every split destination into it (distinct
-// destinations within a round: one lane each); g = ptr[nr + 1] then (destination, extra) index pairs
+// destinations within a round: one lane each); g = ptr[nr + 1] (padded to an even count) then (destination, extra)
+// index pairs.  Rare: stage 1 is packed without splits, stage 2 adds its extras while the row is written.
 __device__ __forceinline__ void tpl_combine(int nr, const unsigned short *__restrict__ g, double *O, int lane) {
-  const unsigned short *pairs = g + ((nr + 2) & ~1);  // the pair words are 4-byte aligned
+  const unsigned short *pairs = g + ((nr + 2) & ~1);
   for (int rd = 0; rd < nr; ++rd) {
     const int e = (int)__ldg(g + rd + 1);
     for (int k = (int)__ldg(g + rd) + lane; k < e; k += 32) {
@@ -340,32 +355,33 @@ __device__ __forceinline__ void tpl_combine(int nr, const unsigned short *__rest
   }
 }
 
-struct TplDesc {  // one operand row of stage 1: its weight R[i, j_q] and where its values start in A_f.val
-  double w;
-  int beg, pad;
-};
-
+// Two rows per warp.  A warp runs the SAME program for two rows of its chunk at once: the two rows' independent load ->
+// shared-memory -> accumulate chains interleave (the one-row version of this kernel issued on 55 % of the cycles with
+// long-scoreboard stalls on top: 9.8 ms at N_b=184 against 8.2 ms), and the instruction count per row halves (528
+// against 976 warp instructions per row, ncu).
 #ifndef IIFE_TPL_MINBLOCKS
-#define IIFE_TPL_MINBLOCKS 4
+#define IIFE_TPL_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(256, IIFE_TPL_MINBLOCKS) k_ptap_numeric_tpl(PtapArgs a, TplArgs t) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int wpc = blockDim.x >> 5;
-  // per warp: desc[MAX_N0] (16 B each), S[s_cap], O1[o1_cap], O2[o2_cap] doubles
-  const size_t per_warp = (size_t)tpl::MAX_N0 * 16 + ((size_t)t.s_cap + t.o1_cap + t.o2_cap) * 8;
+  // per warp: sbegA[n0_cap], sbegB[n0_cap] ints, then for row A and again for row B: S[s_cap], O1[o1_cap], O2[o2_cap]
+  const unsigned delta = (unsigned)(((size_t)t.s_cap + t.o1_cap + t.o2_cap) * 8);
+  const size_t per_warp = (size_t)t.n0_cap * 8 + 2 * (size_t)delta;
   unsigned char *base = smem + per_warp * wic;
-  TplDesc *desc = (TplDesc *)base;
-  double *S = (double *)(base + tpl::MAX_N0 * 16);
+  int *sbegA = (int *)base, *sbegB = sbegA + t.n0_cap;
+  double *S = (double *)(base + (size_t)t.n0_cap * 8);
   double *O1 = S + t.s_cap;
   double *O2 = O1 + t.o1_cap;
+  double *SB = (double *)((unsigned char *)S + delta), *O1B = (double *)((unsigned char *)O1 + delta),
+         *O2B = (double *)((unsigned char *)O2 + delta);
   const unsigned S_sh = (unsigned)__cvta_generic_to_shared(S);
   const unsigned O1_sh = (unsigned)__cvta_generic_to_shared(O1);
   const unsigned O2_sh = (unsigned)__cvta_generic_to_shared(O2);
-  const unsigned desc_sh = (unsigned)__cvta_generic_to_shared(desc);
-  if (lane < 16) {  // the dummy rows read by lanes whose program has ended (any finite value would do)
-    S[lane] = 0.0;
-    O1[lane] = 0.0;
+  if (lane == 0) {  // the zero slot of the write-time combine
+    O2[0] = 0.0;
+    O2B[0] = 0.0;
   }
   __syncwarp();
   const double *__restrict__ a_val = a.a_val;
@@ -375,76 +391,91 @@ __global__ void __launch_bounds__(256, IIFE_TPL_MINBLOCKS) k_ptap_numeric_tpl(Pt
     const unsigned char *blob = t.blobs + __ldg(t.blob_off + tp);
     const tpl::Header *h = (const tpl::Header *)blob;
     const int n0 = h->n0, stg_steps = h->stg_steps, n2 = h->n2, S1 = h->S1, S2 = h->S2;
-    const int ng1 = h->ng1, ng2 = h->ng2;
-    const unsigned *stg = (const unsigned *)(blob + h->off_stg);
+    const int ng1 = h->ng1, ng2 = h->ng2, wc2 = h->wc2;
+    const unsigned *stg = (const unsigned *)(blob + h->off_stg) + lane;
     const double *wt = (const double *)(blob + h->off_w);
     const unsigned *p1 = (const unsigned *)(blob + h->off_p1);
     const unsigned short *g1 = (const unsigned short *)(blob + h->off_g1);
     const double *c2 = (const double *)(blob + h->off_c2);
     const unsigned *p2 = (const unsigned *)(blob + h->off_p2);
     const unsigned short *g2 = (const unsigned short *)(blob + h->off_g2);
-    // the template's weights and this chunk's row descriptors: a two-deep software pipeline over the rows, so that
-    // the dependent loads (row info -> operand starts) of row r+1 are in flight while row r is computed
-    const bool has0 = lane < n0, has1 = lane + 32 < n0;
-    const double w0 = has0 ? __ldg(wt + lane) : 0.0, w1 = has1 ? __ldg(wt + lane + 32) : 0.0;
-    int2 ri_cur = __ldg(t.rowinfo + r0);
-    int2 ri_nxt = cnt > 1 ? __ldg(t.rowinfo + r0 + 1) : ri_cur;
-    int b0 = has0 ? __ldg(a.mt_abeg + ri_cur.x + lane) : 0, b1 = has1 ? __ldg(a.mt_abeg + ri_cur.x + lane + 32) : 0;
-    for (int r = 0; r < cnt; ++r) {
-      const int cb = ri_cur.y;
-      if (has0) desc[lane] = TplDesc{w0, b0, 0};
-      if (has1) desc[lane + 32] = TplDesc{w1, b1, 0};
-      ri_cur = ri_nxt;
-      if (r + 2 < cnt) ri_nxt = __ldg(t.rowinfo + r0 + r + 2);
-      if (r + 1 < cnt) {
-        if (has0) b0 = __ldg(a.mt_abeg + ri_cur.x + lane);
-        if (has1) b1 = __ldg(a.mt_abeg + ri_cur.x + lane + 32);
+    const unsigned *xw = (const unsigned *)(blob + h->off_xw);
+    for (int r = 0; r < cnt; r += 2) {
+      const int iA = __ldg(t.rows + r0 + r);
+      const int iB = __ldg(t.rows + r0 + (r + 1 < cnt ? r + 1 : r));  // odd tail: the last row twice (same values twice)
+      const int mtbA = __ldg(a.mt_rowptr + iA), mtbB = __ldg(a.mt_rowptr + iB);
+      const int cbA = __ldg(a.c_rowptr + iA), cbB = __ldg(a.c_rowptr + iB);
+      for (int q = lane; q < n0; q += 32) {
+        sbegA[q] = __ldg(a.mt_abeg + mtbA + q);
+        sbegB[q] = __ldg(a.mt_abeg + mtbB + q);
       }
       __syncwarp();
-      // ---- staging: S[slot] = w[q] * A.val[beg[q] + e], 4 loads in flight per lane; the slots of a phase of 16 lanes lie
-      // in 16 different banks (edge colouring of the template compiler), as do the reads of stage 1.  A staging word is
-      // slot << 16 | q << 8 | e; desc[q] = (weight, start of the operand row) comes with one 16-byte shared load
+      // ---- staging of both rows: S[slot] = w[q] * A.val[beg[q] + e]; a staging word is slot << 16 | q << 8 | e.  The
+      // slots of a phase of 16 lanes lie in 16 different banks, as do the reads of stage 1 (edge colouring of the
+      // template compiler).  4 steps x 2 rows of loads in flight per lane.
       {
         int s = 0;
         for (; s + 4 <= stg_steps; s += 4) {
           unsigned m[4];
-          double v[4], w[4];
+          double vA[4], vB[4], w[4];
 #pragma unroll
-          for (int b = 0; b < 4; ++b) m[b] = __ldg(stg + (s + b) * 32 + lane);
+          for (int b = 0; b < 4; ++b) m[b] = __ldg(stg + (s + b) * 32);
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
-            v[b] = 0.0;
+            vA[b] = 0.0;
+            vB[b] = 0.0;
             w[b] = 0.0;
             if (m[b] != tpl::STG_PAD) {
-              double wq;
-              long long bp;  // (beg, pad)
-              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=d"(wq), "=l"(bp) : "r"(desc_sh + ((m[b] >> 4) & 0xFF0u)));
-              w[b] = wq;
-              v[b] = __ldg(a_val + (int)bp + (int)(m[b] & 255u));
+              const unsigned q = (m[b] >> 8) & 255u;
+              const int e = (int)(m[b] & 255u);
+              vA[b] = __ldg(a_val + sbegA[q] + e);
+              vB[b] = __ldg(a_val + sbegB[q] + e);
+              w[b] = __ldg(wt + q);
             }
           }
 #pragma unroll
           for (int b = 0; b < 4; ++b)
-            if (m[b] != tpl::STG_PAD) S[m[b] >> 16] = w[b] * v[b];
+            if (m[b] != tpl::STG_PAD) {
+              S[m[b] >> 16] = w[b] * vA[b];
+              SB[m[b] >> 16] = w[b] * vB[b];
+            }
         }
         for (; s < stg_steps; ++s) {
-          const unsigned m = __ldg(stg + s * 32 + lane);
+          const unsigned m = __ldg(stg + s * 32);
           if (m != tpl::STG_PAD) {
-            const TplDesc d = desc[(m >> 8) & 255u];
-            S[m >> 16] = d.w * __ldg(a_val + d.beg + (int)(m & 255u));
+            const unsigned q = (m >> 8) & 255u;
+            const int e = (int)(m & 255u);
+            const double w = __ldg(wt + q);
+            S[m >> 16] = w * __ldg(a_val + sbegA[q] + e);
+            SB[m >> 16] = w * __ldg(a_val + sbegB[q] + e);
           }
         }
       }
       __syncwarp();
-      // ---- stage 1: intermediate row
-      tpl_gather<false>(S1, p1, nullptr, S_sh, O1_sh, lane);
+      // ---- stage 1: intermediate rows
+      tpl_gather2<false>(S1, p1, nullptr, S_sh, O1_sh, delta, lane);
       __syncwarp();
-      if (ng1) tpl_combine(ng1, g1, O1, lane);
-      // ---- stage 2: output row
-      tpl_gather<true>(S2, p2, c2, O1_sh, O2_sh, lane);
+      if (ng1) {
+        tpl_combine(ng1, g1, O1, lane);
+        tpl_combine(ng1, g1, O1B, lane);
+      }
+      // ---- stage 2: output rows
+      tpl_gather2<true>(S2, p2, c2, O1_sh, O2_sh, delta, lane);
       __syncwarp();
-      if (ng2) tpl_combine(ng2, g2, O2, lane);
-      for (int o = lane; o < n2; o += 32) a.c_val[cb + o] = O2[1 + o];
+      if (ng2 && !wc2) {
+        tpl_combine(ng2, g2, O2, lane);
+        tpl_combine(ng2, g2, O2B, lane);
+      }
+      for (int o = lane; o < n2; o += 32) {
+        double vA = O2[1 + o], vB = O2B[1 + o];
+        if (wc2) {  // pieces of a split destination: (piece 0 + piece 1) + piece 2; index 0 is the zero slot
+          const unsigned x = __ldg(xw + o);
+          vA = (vA + O2[x & 0xFFFFu]) + O2[x >> 16];
+          vB = (vB + O2B[x & 0xFFFFu]) + O2B[x >> 16];
+        }
+        a.c_val[cbA + o] = vA;
+        a.c_val[cbB + o] = vB;
+      }
       __syncwarp();
     }
   }

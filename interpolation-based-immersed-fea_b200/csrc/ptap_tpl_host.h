@@ -18,7 +18,7 @@
 // register and are stored once ("flush"); a destination with more terms than the step count S is split into
 // pieces that flush into extra slots and are added in a fixed order afterwards.  No shared-memory read-modify-write,
 // no privatised accumulator copies, no hashing, no column indices, no atomics; the sum order is fixed by the
-// program, so results are bit-reproducible.  Words 0..15 of S / O1 are a dummy row read by lanes whose program has ended.
+// program, so results are bit-reproducible.
 //
 // Shared-memory banks.  A step reads 32 fp64 words; the hardware serves it in two phases of 16 lanes, each conflict
 // free iff its words lie in 16 distinct 8-byte banks (index mod 16).
@@ -26,7 +26,7 @@
 //     per phase.  A term is therefore an EDGE between its write phase and its read phase; both have at most 16
 //     members, so by Koenig's theorem the edges of this bipartite multigraph can be coloured with 16 colours such
 //     that no phase sees a colour twice: colour = bank.  edge_colour_16 computes it (alternating-path recolouring) and
-//     the staged value of term p lives at S[16 + 16 * rank + colour]: stage-1 reads AND staging writes are conflict
+//     the staged value of term p lives at S[16 * rank + colour]: stage-1 reads AND staging writes are conflict
 //     free for any program.
 //   * Stage 2 reads intermediate entries several times each (once per entry of the M row), so no such guarantee
 //     exists; the order of the terms inside a run and the order of a lane's runs are free, and a maximum bipartite
@@ -70,9 +70,11 @@ struct Header {
   int off_stg, off_w, off_p1, off_g1, off_c2, off_p2, off_g2;
   int blob_bytes;
   int ext1, ext2;  // index of the first extra slot in O1 / O2 (the destinations live below it)
+  int wc2;         // 1: every split destination of stage 2 has at most 2 extra pieces and off_xw holds, per output
+  int off_xw;      //    entry, the O2 indices of its extras (two 16-bit fields; 0 = the zero slot O2[0])
   int pad;
 };
-static_assert(sizeof(Header) == 88, "Header layout");
+static_assert(sizeof(Header) == 96, "Header layout");
 
 struct Term {
   int dest;     // destination 0..n_dest-1
@@ -97,7 +99,7 @@ struct Piece {
 // terms.  bank_of == nullptr: runs and terms in their given order (ascending operand order: the order the reference's
 // row-wise Gustavson product adds them in).  Otherwise bank_of[src] is the shared-memory bank of every logical source
 // and a maximum matching per phase avoids bank conflicts where it can.  Returns false if a destination has no term.
-inline bool build_schedule(int n_dest, const std::vector<Term> &terms, const int *bank_of, Schedule &out) {
+inline bool build_schedule(int n_dest, const std::vector<Term> &terms, const int *bank_of, Schedule &out, bool avoid_splits = false) {
   std::vector<std::vector<int>> by_dest((size_t)n_dest);
   for (size_t t = 0; t < terms.size(); ++t) {
     if (terms[t].dest < 0 || terms[t].dest >= n_dest) return false;
@@ -109,6 +111,11 @@ inline bool build_schedule(int n_dest, const std::vector<Term> &terms, const int
   std::vector<Piece> pieces;
   std::vector<int> lane_of;  // per piece
   int S = std::max(1, (N + 31) / 32);
+  if (avoid_splits) {  // a destination is only split when it has more than twice the mean lane load
+    int mx = 0;
+    for (int d = 0; d < n_dest; ++d) mx = std::max(mx, (int)by_dest[(size_t)d].size());
+    if (mx <= 2 * S) S = std::max(S, mx);
+  }
   for (;; ++S) {
     pieces.clear();
     for (int d = 0; d < n_dest; ++d) {
@@ -325,6 +332,7 @@ inline bool edge_colour_16(int n_left, int n_right, const std::vector<int> &lv, 
 struct Program {
   std::vector<unsigned char> blob;  // Header + sections
   int s_cap = 0, o1_cap = 0, o2_cap = 0;  // entries of S / O1 / O2 this template needs
+  int n0 = 0;                              // operand rows of stage 1
   double use1 = 0.0, use2 = 0.0;
   double conf1 = 0.0, conf2 = 0.0;  // mean conflict degree of the gather reads of the two stages (1.0 = none)
 };
@@ -379,7 +387,7 @@ inline bool compile(const Raw &r, Program &out) {
   }
   // ---- stage 1: schedule in Gustavson order, then banks by edge colouring (write phase p / 16  x  read phase)
   Schedule s1;
-  if (!build_schedule(r.n1, t1, nullptr, s1)) return false;
+  if (!build_schedule(r.n1, t1, nullptr, s1, true)) return false;  // stage 1: no combine pass in the common case
   std::vector<int> s_index((size_t)T1, 0);  // index of staged term p inside S
   {
     std::vector<int> lv((size_t)T1), rv((size_t)T1), col;
@@ -392,11 +400,11 @@ inline bool compile(const Raw &r, Program &out) {
     if (!edge_colour_16((T1 + 15) / 16, 2 * s1.S, lv, rv, col)) return false;
     int rank[16] = {0};
     for (int p = 0; p < T1; ++p) {
-      s_index[(size_t)p] = 16 + 16 * rank[col[(size_t)p]] + col[(size_t)p];  // words 0..15 are the dummy row
+      s_index[(size_t)p] = 16 * rank[col[(size_t)p]] + col[(size_t)p];
       ++rank[col[(size_t)p]];
     }
   }
-  int s_words = 1;
+  int s_words = 1;  // entries of S
   for (int p = 0; p < T1; ++p) s_words = std::max(s_words, s_index[(size_t)p] + 1);
   // ---- stage 2: layout of the intermediate row adapted to a bank-aware schedule (a few rounds of local search)
   std::vector<int> o1_bank((size_t)r.n1), o1_index((size_t)r.n1);
@@ -405,7 +413,7 @@ inline bool compile(const Raw &r, Program &out) {
     int hi = 0;
     for (int q = 0; q < r.n1; ++q) {
       const int b = bank[(size_t)q];
-      index[(size_t)q] = 16 + 16 * rank[b] + b;  // (index & 15) == bank; words 0..15 are the dummy row
+      index[(size_t)q] = 16 * rank[b] + b;  // (index & 15) == bank
       ++rank[b];
       hi = std::max(hi, index[(size_t)q]);
     }
@@ -444,13 +452,19 @@ inline bool compile(const Raw &r, Program &out) {
       }
     };
     for (int q = 0; q < r.n1; ++q) add(q, +1);
+    // banks stay balanced (the buffer holds 16 x the fullest bank): at most ceil(n1 / 16) + 1 sources per bank
+    const int bank_cap = (r.n1 + 15) / 16 + 1;
+    int pop[16] = {0};
+    for (int q = 0; q < r.n1; ++q) pop[o1_bank[(size_t)q]]++;
     bool moved = true;
     for (int sweep = 0; sweep < 4 && moved; ++sweep) {
       moved = false;
       for (int q = 0; q < r.n1; ++q) {
         add(q, -1);
+        pop[o1_bank[(size_t)q]]--;
         int best_b = o1_bank[(size_t)q], best_cost = 1 << 30;
         for (int b = 0; b < 16; ++b) {
+          if (pop[b] >= bank_cap) continue;
           int cost = 0, last = -1;
           for (int ph : reads[(size_t)q]) {
             if (ph == last) continue;
@@ -464,6 +478,7 @@ inline bool compile(const Raw &r, Program &out) {
         }
         if (best_b != o1_bank[(size_t)q]) moved = true;
         o1_bank[(size_t)q] = best_b;
+        pop[best_b]++;
         add(q, +1);
       }
     }
@@ -481,16 +496,16 @@ inline bool compile(const Raw &r, Program &out) {
     stg[(size_t)p] = ((uint32_t)s_index[(size_t)p] << 16) | ((uint32_t)stg_q[(size_t)p] << 8) | (uint32_t)stg_e[(size_t)p];
   std::vector<uint32_t> p1((size_t)s1.S * 32), p2((size_t)s2.S * 32);
   std::vector<double> c2((size_t)s2.S * 32, 0.0);
-  // a lane whose program has ended keeps stepping: it reads a dummy word (index = a bank none of the phase's active lanes
-  // uses, in the dummy row 0..15), adds it to an accumulator that is never flushed again
+  // a lane whose program has ended keeps stepping: it reads some DATA word of a bank that none of the phase's active
+  // lanes uses (no conflict, the value is added to an accumulator that is never flushed again)
   auto idle_word = [&](const Schedule &sc, size_t k, const std::vector<Term> &terms, const std::vector<int> &index_of) {
     const size_t base = k & ~(size_t)15;
     bool used[16] = {false};
     for (size_t j = base; j < base + 16; ++j)
       if (sc.term[j] >= 0) used[index_of[(size_t)terms[(size_t)sc.term[j]].src] & 15] = true;
-    for (int b = 0; b < 16; ++b)
-      if (!used[b]) return b;
-    return 0;
+    for (int idx : index_of)
+      if (!used[idx & 15]) return idx;
+    return index_of[0];
   };
   for (size_t k = 0; k < p1.size(); ++k) {
     const int t = s1.term[k], f = s1.flush[k];
@@ -528,8 +543,21 @@ inline bool compile(const Raw &r, Program &out) {
   for (int o = 0; o < r.n2; ++o) o2_index[(size_t)o] = 1 + o;
   int nr1 = 0, nr2 = 0;
   std::vector<uint16_t> g1 = rounds_of(s1, ext1, o1_index, &nr1), g2 = rounds_of(s2, ext2, o2_index, &nr2);
+  // stage-2 destinations with one or two extra pieces: added while the row is written (no combine pass)
+  std::vector<uint32_t> xw((size_t)((r.n2 + 31) / 32) * 32, 0u);
+  int wc2 = 1;
+  for (size_t g = 0; g < s2.gd.size(); ++g) {
+    const int cnt = s2.gptr[g + 1] - s2.gptr[g];
+    if (cnt > 2) {
+      wc2 = 0;
+      break;
+    }
+    const uint32_t x1 = (uint32_t)(ext2 + s2.gptr[g]), x2 = cnt > 1 ? x1 + 1 : 0u;
+    xw[(size_t)s2.gd[g]] = x1 | (x2 << 16);
+  }
   Header h;
   memset(&h, 0, sizeof(h));
+  h.wc2 = wc2;
   h.n0 = r.n0;
   h.T1 = T1;
   h.stg_steps = stg_steps;
@@ -556,6 +584,7 @@ inline bool compile(const Raw &r, Program &out) {
   h.off_c2 = place(c2.size() * 8);
   h.off_p2 = place(p2.size() * 4);
   h.off_g2 = place(g2.size() * 2);
+  h.off_xw = place(xw.size() * 4);
   h.blob_bytes = (int)off;
   out.blob.assign(off, 0);
   unsigned char *b = out.blob.data();
@@ -567,6 +596,8 @@ inline bool compile(const Raw &r, Program &out) {
   memcpy(b + h.off_c2, c2.data(), c2.size() * 8);
   memcpy(b + h.off_p2, p2.data(), p2.size() * 4);
   if (!g2.empty()) memcpy(b + h.off_g2, g2.data(), g2.size() * 2);
+  memcpy(b + h.off_xw, xw.data(), xw.size() * 4);
+  out.n0 = r.n0;
   out.s_cap = s_words;
   out.o1_cap = ext1 + s1.n_extra;
   out.o2_cap = ext2 + s2.n_extra;
@@ -621,6 +652,12 @@ inline void interpret(const unsigned char *blob, const double *const *a_rows, do
         acc = 0.0;
       }
     }
+  }
+  if (h.wc2) {  // the kernel adds the extras while it writes the row: (piece 0 + piece 1) + piece 2, O2[0] = 0
+    const uint32_t *xw = (const uint32_t *)(blob + h.off_xw);
+    O2[0] = 0.0;
+    for (int o = 0; o < h.n2; ++o) c_out[o] = (O2[(size_t)1 + o] + O2[xw[o] & 0xFFFFu]) + O2[xw[o] >> 16];
+    return;
   }
   for (int rd = 0; rd < h.ng2; ++rd)
     for (int k = gp2[rd]; k < gp2[rd + 1]; ++k) O2[pr2[2 * k]] += O2[pr2[2 * k + 1]];

@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import check, lib
 
 MEM_HOST, MEM_DEVICE = 0, 1
-KSP_CG, KSP_FGMRES = 0, 1
+KSP_CG, KSP_FGMRES, KSP_GCR = 0, 1, 2
 PC_NONE, PC_JACOBI = 0, 1
 
 REASONS = {

@@ -475,3 +475,81 @@ void oracle_synth_cube_fill(i64 n_bg_cells, const double *coef /* 8 x 27 */, con
         }
   }
 }
+
+/* ---- KSPGCR + PCJACOBI (reference common.py:559-560: method='gcr'; PETSc's default restart of 30).  Restated from
+ * the published algorithm (src/ksp/ksp/impls/gcr/gcr.c): per step  s = B r;  v = A s;  classical Gram-Schmidt of v
+ * (and the same combination of s) against the stored v_i;  normalise;  x += (r, v) s;  r -= (r, v) v;  test the
+ * unpreconditioned ||r|| with KSPConvergedDefault against ||b||.  The residual is recomputed from x at the start of
+ * every cycle (and tested there).  dinv == NULL means PCNONE. */
+int oracle_gcr_jacobi(i64 n, const i64 *rp, const i32 *ci, const double *v, const double *dinv_in, const double *b,
+                      double *x, double rtol, double atol, double dtol, i64 max_it, int m, i64 *its_out,
+                      double *rnorm_out, double *hist, i64 hist_len) {
+  if (m < 1) m = 30;
+  double **V = (double **)calloc((size_t)m, sizeof(double *));
+  double **S = (double **)calloc((size_t)m, sizeof(double *));
+  double *r = (double *)malloc((size_t)(n + 1) * sizeof(double));
+  double *coef = (double *)calloc((size_t)m + 1, sizeof(double));
+  int reason = 0, first = 1;
+  i64 its = 0;
+  double rho0 = sqrt(dot(n, b, b)), ttol = fmax(rtol * rho0, atol), res = 0.0;
+  while (!reason) {
+    oracle_spmv(n, rp, ci, v, x, r);
+#pragma omp parallel for schedule(static)
+    for (i64 k = 0; k < n; ++k) r[k] = b[k] - r[k];
+    res = sqrt(dot(n, r, r));
+    if (first) {
+      if (hist && hist_len > 0) hist[0] = res;
+      if (rho0 == 0.0) {
+        rho0 = res;
+        ttol = fmax(rtol * rho0, atol);
+      }
+      first = 0;
+    }
+    reason = converged_default(res, ttol, atol, dtol, rho0);
+    if (!reason && its >= max_it) reason = -3;
+    for (int k = 0; k < m && !reason; ++k) {
+      if (!V[k]) V[k] = (double *)malloc((size_t)(n + 1) * sizeof(double));
+      if (!S[k]) S[k] = (double *)malloc((size_t)(n + 1) * sizeof(double));
+      double *vk = V[k], *sk = S[k];
+#pragma omp parallel for schedule(static)
+      for (i64 t = 0; t < n; ++t) sk[t] = (dinv_in ? dinv_in[t] : 1.0) * r[t];
+      oracle_spmv(n, rp, ci, v, sk, vk);
+      for (int i = 0; i < k; ++i) coef[i] = dot(n, vk, V[i]);
+#pragma omp parallel for schedule(static)
+      for (i64 t = 0; t < n; ++t) {
+        double a = vk[t], c = sk[t];
+        for (int i = 0; i < k; ++i) {
+          a -= coef[i] * V[i][t];
+          c -= coef[i] * S[i][t];
+        }
+        vk[t] = a;
+        sk[t] = c;
+      }
+      double rv = dot(n, r, vk), nrm = sqrt(dot(n, vk, vk));
+      double scale = 1.0 / nrm, tt = rv / nrm;
+#pragma omp parallel for schedule(static)
+      for (i64 t = 0; t < n; ++t) {
+        vk[t] *= scale;
+        sk[t] *= scale;
+        x[t] += tt * sk[t];
+        r[t] -= tt * vk[t];
+      }
+      res = sqrt(dot(n, r, r));
+      ++its;
+      if (hist && its < hist_len) hist[its] = res;
+      reason = converged_default(res, ttol, atol, dtol, rho0);
+      if (!reason && its >= max_it) reason = -3;
+    }
+  }
+  for (int k = 0; k < m; ++k) {
+    free(V[k]);
+    free(S[k]);
+  }
+  free(V);
+  free(S);
+  free(r);
+  free(coef);
+  if (its_out) *its_out = its;
+  if (rnorm_out) *rnorm_out = res;
+  return reason;
+}

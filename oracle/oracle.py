@@ -58,6 +58,7 @@ def lib():
         _lib.oracle_max_threads.restype = ctypes.c_int
         _lib.oracle_cg_jacobi.restype = ctypes.c_int
         _lib.oracle_fgmres_jacobi.restype = ctypes.c_int
+        _lib.oracle_gcr_jacobi.restype = ctypes.c_int
         _lib.oracle_fgmres_hessenberg.restype = ctypes.c_int
     return _lib
 
@@ -284,7 +285,8 @@ class KSPResult:
 def solve_ksp(A: CSR, b: np.ndarray, x0: np.ndarray | None = None, method: str = "gmres", PC: str = "jacobi",
               rtol: float = 1e-8, atol: float = 1e-9, max_it: int = 1000000, restart: int = 300, dtol: float = 1e4,
               hist_len: int = 0) -> KSPResult:
-    """Krylov branch of reference common.py:509-641: 'gmres' -> FGMRES(300), 'cg' -> CG, PC jacobi."""
+    """Krylov branch of reference common.py:509-641: 'gmres' -> FGMRES(300), 'cg' -> CG, 'gcr' -> GCR (PETSc's default
+    restart of 30: pass restart=30; the reference's setGMRESRestart does not reach KSPGCR), PC jacobi."""
     assert A.n_rows == A.n_cols
     n = A.n_rows
     b = np.ascontiguousarray(b, dtype=np.float64)
@@ -307,6 +309,9 @@ def solve_ksp(A: CSR, b: np.ndarray, x0: np.ndarray | None = None, method: str =
     elif method in ("gmres", None):
         reason = lib().oracle_fgmres_jacobi(*common, ctypes.c_int(restart), ctypes.byref(its), ctypes.byref(rn),
                                             _p(hist, _c_f64p), ctypes.c_int64(hist_len))
+    elif method == "gcr":
+        reason = lib().oracle_gcr_jacobi(*common, ctypes.c_int(30 if restart in (None, 300) else restart), ctypes.byref(its),
+                                         ctypes.byref(rn), _p(hist, _c_f64p), ctypes.c_int64(hist_len))
     else:
         raise NotImplementedError(method)
     return KSPResult(x, int(its.value), int(reason), float(rn.value), hist[:hist_len])

@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 os.makedirs(P, exist_ok=True)
 
 
@@ -25,6 +25,7 @@ def launch_list():
             pass
     tot = sum(sum(v) for v in agg.values())
     out = [f"# ncu launch list — `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu` ({tag})", "",
+           "(the command makes two cold PtAP calls, 5 steps of numeric PtAP + M^T b + CG, and the per-phase timing loops)", "",
            "`ncu --metrics gpu__time_duration.sum --clock-control none -c 4000`; per-launch times are cold-cache and",
            "serialised: read the SHARES.  N_b = 184 (50.2 M foreground dofs), 1 x B200.", "",
            f"total kernel time in the capture: {tot / 1e6:.1f} ms over {sum(len(v) for v in agg.values())} launches", "",
@@ -104,7 +105,9 @@ def kernel_report(rep_name, title, fname, note=""):
 
 launch_list()
 sell = kernel_report("prof_spmv_sell.ncu-rep", "SELL-32 SpMV of the CG iteration (k_spmv_sell)", f"{tag}_spmv_sell.md")
-kernel_report("prof_ptap_numeric.ncu-rep", "Numeric PtAP (slot-plan kernel)", f"{tag}_ptap_numeric.md")
+kernel_report("prof_ptap_numeric.ncu-rep", "Numeric PtAP (template kernel k_ptap_numeric_tpl, two rows per warp)", f"{tag}_ptap_numeric.md",
+              note="Per output row (6 331 625 rows): divide smsp__inst_executed.sum and the byte counts by the row count.")
+kernel_report("prof_ptap_symbolic.ncu-rep", "Symbolic PtAP (count and fill pass of k_ptap_symbolic, cold path)", f"{tag}_ptap_symbolic.md")
 kernel_report("prof_cg_vec.ncu-rep", "CG vector kernels", f"{tag}_cg_vector_kernels.md")
 if sell:
     # the DOT variant is the kernel inside the iteration
@@ -113,4 +116,7 @@ if sell:
     wr = float(d["dram__bytes_write.sum"][0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[d["dram__bytes_write.sum"][1]]
     json.dump({"n_bg_cells": 184, "kernel": d["Kernel Name"].split("(")[0], "spmv_dot_dram_bytes_per_launch": rd + wr,
                "source": f"profiles/{tag}_spmv_sell.md"}, open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
+for src, dst in (("configs_1_4.md", f"{tag}_configs_1_4.md"), ("robustness.md", f"{tag}_robustness.md"), ("phase184.log", f"{tag}_phase184.log")):
+    if os.path.exists(os.path.join(G, src)):
+        open(os.path.join(P, dst), "w").write(open(os.path.join(G, src)).read())
 print(open(os.path.join(P, f"{tag}_launch_list.md")).read()[:1800])

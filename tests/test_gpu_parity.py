@@ -369,6 +369,33 @@ def test_ksp_zero_rhs_nonzero_guess(iife, oracle, method):
     assert np.linalg.norm(x) <= 1e-6 * np.linalg.norm(x0)
 
 
+@pytest.mark.parametrize("restart", [30, 7])
+def test_gcr_matches_oracle(iife, oracle, restart):
+    """Device GCR (IIFE_KSP_GCR, reference common.py:559-560: method='gcr' -> KSPGCR) against the oracle's restatement:
+    reason, iteration count, residual history and solution; also through solveKSP(method='gcr')."""
+    from InterpolationBasedImmersedFEA import common as api
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, b = assemble_cube(6)
+    C = oracle.AT_R_A(M, A)
+    bb = oracle.AT_x(M, b)
+    ro = oracle.solve_ksp(C, bb, method="gcr", rtol=1e-8, atol=1e-9, restart=restart, hist_len=600)
+    x = np.zeros(C.n_rows)
+    info = iife.ksp_solve(dmat(iife, C), bb, x, iife.KSP_GCR, iife.PC_JACOBI, rtol=1e-8, atol=1e-9, restart=restart, hist_len=600)
+    assert info.reason == ro.reason and abs(info.iterations - ro.iterations) <= 1, (info.reason_name, info.iterations, ro.iterations)
+    k = min(info.iterations, ro.iterations) + 1
+    assert np.allclose(info.history[:k], ro.history[:k], rtol=1e-4, atol=1e-9 * ro.history[0])
+    assert np.linalg.norm(x - ro.x) <= SOL_TOL * np.linalg.norm(ro.x)
+    if restart == 30:
+        u = api.Vec(np.zeros(C.n_rows))
+        api.solveKSP(api.CSRMat((C.n_rows, C.n_cols), C.rowptr, C.colind, C.val), api.Vec(bb), u, method="gcr", monitor=False)
+        assert api.last_ksp_info.reason == ro.reason and np.linalg.norm(u.array - ro.x) <= SOL_TOL * np.linalg.norm(ro.x)
+        # max_it is honoured inside a cycle
+        x2 = np.zeros(C.n_rows)
+        i2 = iife.ksp_solve(dmat(iife, C), bb, x2, iife.KSP_GCR, iife.PC_JACOBI, rtol=1e-30, atol=1e-300, max_it=13)
+        assert i2.reason == -3 and i2.iterations == 13
+
+
 def test_ksp_singular_rows_and_nonzero_guess(iife, oracle):
     """A_b of real data has structurally empty rows (unsupported background functions): Jacobi maps the
     zero diagonal to 1 and those unknowns keep their initial value."""

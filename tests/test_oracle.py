@@ -126,6 +126,34 @@ def test_zero_rhs_with_nonzero_guess_iterates(oracle, method):
     assert np.linalg.norm(r.x) <= 1e-6 * np.linalg.norm(x0)
 
 
+def test_gcr_against_dense_solve_and_restart(oracle):
+    """KSPGCR restatement (reference common.py:559-560): converges to the dense solution, the residual history is
+    the true residual norm and decreases monotonically (GCR minimises it over the current space), a restart shorter
+    than the iteration count still converges."""
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, b = assemble_cube(3)
+    C = oracle.AT_R_A(M, A)
+    bb = oracle.AT_x(M, b)
+    x_ref = np.linalg.solve(C.todense(), bb)
+    for restart in (30, 5):
+        r = oracle.solve_ksp(C, bb, method="gcr", rtol=1e-10, atol=1e-50, restart=restart, hist_len=400)
+        assert r.reason == 2 and (restart == 30 or r.iterations > 5)
+        assert np.linalg.norm(r.x - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
+        h = r.history[: r.iterations + 1]
+        assert np.all(np.diff(h) <= 1e-12 * h[0])
+        assert abs(h[-1] - np.linalg.norm(bb - oracle.spmv(C, r.x))) <= 1e-8 * h[0]
+    # unsymmetric operator: GCR does not need symmetry
+    rng = np.random.default_rng(0)
+    S = C.to_scipy().tolil()
+    S[0, 5] += 0.3
+    S[7, 2] -= 0.2
+    Cu = oracle.CSR.from_scipy(S.tocsr())
+    xr = np.linalg.solve(Cu.todense(), bb)
+    r = oracle.solve_ksp(Cu, bb, method="gcr", rtol=1e-10, atol=1e-50)
+    assert r.reason == 2 and np.linalg.norm(r.x - xr) <= 1e-8 * np.linalg.norm(xr)
+
+
 def test_cg_textbook_iteration_by_iteration(oracle):
     """The C CG equals a line-by-line numpy transcription of SURVEY A.6 (preconditioned norm)."""
     rng = np.random.default_rng(5)

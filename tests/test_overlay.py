@@ -34,7 +34,7 @@ def test_without_petsc_the_delegated_branches_raise():
         from InterpolationBasedImmersedFEA.profile_utils import profile_separate
         assert not HAVE_PETSC and not HAVE_DOLFIN and mpirank == 0 and mpisize == 1 and worldcomm is None
         A = CSRMat((2, 2), np.array([0, 1, 2]), np.array([0, 1]), np.array([2.0, 4.0]))
-        for kw in (dict(method='mumps'), dict(method='gcr'), dict(PC='ASM'), dict(PC='ICC'), dict(PC='ILU'), dict(PC='ILUT')):
+        for kw in (dict(method='mumps'), dict(PC='ASM'), dict(PC='ICC'), dict(PC='ILU'), dict(PC='ILUT')):
             try:
                 solveKSP(A, Vec(np.ones(2)), Vec(np.zeros(2)), monitor=False, **kw)
             except NotImplementedError as e:
@@ -65,7 +65,7 @@ def test_delegated_branches_run_on_petsc_when_it_imports():
         S = S.tocsr(); S.sort_indices()
         x_ref = rng.standard_normal(n)
         b = S @ x_ref
-        for kw in (dict(method='mumps'), dict(method='gcr'), dict(method='gmres', PC='ASM'), dict(method='cg', PC='ICC'),
+        for kw in (dict(method='mumps'), dict(method='gcr', PC='ASM'), dict(method='gmres', PC='ASM'), dict(method='cg', PC='ICC'),
                    dict(PC='ILU'), dict(PC='ILUT')):
             A = PETSc.Mat().createAIJ(size=S.shape, csr=(S.indptr, S.indices, S.data))
             bv = PETSc.Vec().createWithArray(b.copy())
