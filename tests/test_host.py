@@ -47,7 +47,7 @@ def test_delegated_branches_raise():
 
     A = common.CSRMat((1, 1), np.array([0, 1]), np.array([0]), np.array([1.0]))
     b, u = common.Vec(np.ones(1)), common.Vec(np.zeros(1))
-    for kw in (dict(method="mumps"), dict(PC="ASM"), dict(PC="ILU"), dict(method="gcr")):
+    for kw in (dict(method="mumps"), dict(PC="ASM"), dict(PC="ILU"), dict(method="gcr", PC="ICC"), dict(method="bicg")):
         with pytest.raises(NotImplementedError):
             common.solveKSP(A, b, u, **kw)
 
