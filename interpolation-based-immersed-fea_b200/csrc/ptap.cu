@@ -1195,8 +1195,13 @@ static int tpl_ensure(Plan *P, const Mat *Rm, const Mat *M, PtapArgs a, bool *re
   const int64_t n5 = P->bin_off[N_NUM_LEVELS + 1] - P->bin_off[N_NUM_LEVELS];
   const int64_t n = P->bin_off[N_NUM_LEVELS + 2] - P->bin_off[N_NUM_LEVELS];
   int min_rows = env_int("IIFE_TPL_MIN_ROWS", 32);
-  const int max_tpl = std::max(1, std::min(env_int("IIFE_TPL_MAX", 1024), 4096));
-  if (n < min_rows || !P->packed_meta || n > 0x7fffffff) return IIFE_OK;
+  // Small problems are launch-latency bound either way, and compiling programs costs ~0.1 ms of host time each (config 2,
+  // 33 k rows of an unstructured mesh: 1 000 groups = 150 ms of cold time for nothing): no templates below
+  // IIFE_TPL_MIN_PROBLEM rows, and at most one template per 4 096 rows (at least 32) above it.
+  const int64_t min_problem = env_int("IIFE_TPL_MIN_PROBLEM", 32768);
+  const int max_tpl = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(env_int("IIFE_TPL_MAX", 1024), 4096),
+                                                                std::max<int64_t>(32, n / 4096)));
+  if (n < min_rows || n < min_problem || !P->packed_meta || n > 0x7fffffff) return IIFE_OK;
   const int *list = P->bin_rows + P->bin_off[N_NUM_LEVELS];
   a.rows = list;
   a.n_rows = n;

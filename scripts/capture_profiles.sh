@@ -19,5 +19,5 @@ tail -1 gpurun_out/prof_ncu_cgvec.log
 timeout 600 ncu --set full --clock-control none -k regex:"k_ptap_symbolic" -c 2 -f -o gpurun_out/prof_ptap_symbolic $CMD > gpurun_out/prof_ncu_sym.log 2>&1
 tail -1 gpurun_out/prof_ncu_sym.log
 timeout 300 python scripts/configs_1_4.py > gpurun_out/configs_1_4.md 2> gpurun_out/configs_1_4.err; echo "configs rc=$?"
-SKIP_FGMRES=0 timeout 300 python scripts/phase_bench.py 184 > gpurun_out/phase184.log 2>&1; echo "phase rc=$?"
+timeout 300 python scripts/phase_bench.py 184 > gpurun_out/phase184.log 2>&1; echo "phase rc=$?"
 timeout 900 python scripts/robustness.py > gpurun_out/robustness.md 2> gpurun_out/robustness.err; echo "robustness rc=$?"

@@ -13,6 +13,10 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    # the template numeric PtAP is switched off below 32 768 rows by default (small problems are launch bound and the
+    # host-side program compilation would dominate their cold time); the parity tests are small, so they lower the bar
+    # to keep that kernel on the tested path (tests/test_gpu_parity.py::test_ptap_template_kernel checks the default too)
+    os.environ.setdefault("IIFE_TPL_MIN_PROBLEM", "0")
 
 
 @pytest.fixture(scope="session")

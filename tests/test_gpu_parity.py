@@ -256,6 +256,13 @@ def test_ptap_template_kernel(iife, oracle, monkeypatch, min_rows):
     if min_rows:
         monkeypatch.setenv("IIFE_TPL_MIN_ROWS", min_rows)
     A, M, _ = assemble_cube(6)
+    if not min_rows:  # the library's default: no templates for a problem this small (343 rows)
+        monkeypatch.setenv("IIFE_TPL_MIN_PROBLEM", "32768")
+        dM0, dA0 = dmat(iife, M), dmat(iife, A)
+        p0 = iife.PtapPlan(dM0, dA0)
+        p0.numeric(dM0, dA0, check_errors=True)
+        assert p0.tpl_info()["rows"] == 0
+        monkeypatch.setenv("IIFE_TPL_MIN_PROBLEM", "0")
     dM, dA, dC, C, plan = check_ptap(iife, oracle, M, A)
     ti = plan.tpl_info()
     n_b = M.n_cols
