@@ -405,15 +405,39 @@ def run_ours(args):
         # b_b stays on the device between AT_x and solveKSP; u crosses twice (initial guess in, solution out)
         h2d = sum(t.numel() * t.element_size() for t in hA) + hb.numel() * 8 + n_b * 8
         d2h = n_b * 8
-        u_host = np.zeros(n_b)
+        # the solution vector is a pinned host buffer like the other operands (a pageable one costs 6 ms of D2H per step);
+        # the zero initial guess is written with torch's threaded fill (numpy's takes 5 ms for 50 MB)
+        u_pin = pinned(n_b, torch.float64)
+        u_host = u_pin.numpy()
         Mh = ref_api.CSRMat((n_f, n_b), *(t.numpy() for t in hM))
 
+        def lap(marks, what):  # IIFE_BENCH_DEBUG: wall clock per call of the mirror, device drained after each
+            if debug:
+                torch.cuda.synchronize()
+                marks.append((what, time.perf_counter()))
+
+        def lap_print(tag, marks):
+            if debug:
+                print(f"[{tag}] " + ", ".join(f"{w} {(t - marks[i][1]) * 1e3:.2f} ms" for i, (w, t) in enumerate(marks[1:])),
+                      file=sys.stderr)
+
         def e2e_step():
+            marks = []
+            lap(marks, "start")
             Ah = ref_api.CSRMat((n_f, n_f), *(t.numpy() for t in hA))
+            if debug:
+                Ah.device()
+                lap(marks, "upload A_f")
+                ref_api.AT_R_A(Mh, Ah)
+                lap(marks, "AT_R_A alone")
             A_b, b_b = ref_api.assembleLinearSystemBackground(Ah, hb.numpy(), Mh)
-            u_host[:] = 0.0
+            lap(marks, "assembleLinearSystemBackground")
+            u_pin.zero_()
             u = ref_api.Vec(u_host)
+            lap(marks, "u")
             ref_api.solveKSP(A_b, b_b, u, method="cg", PC="jacobi", monitor=False)
+            lap(marks, "solveKSP")
+            lap_print("e2e", marks)
             return u
 
         n_e2e = max(1, min(args.steps, args.e2e_steps))
@@ -443,11 +467,17 @@ def run_ours(args):
             Ah = ref_api.CSRMat((n_f, n_f), *(t.numpy() for t in hA))
 
             def e2e_values_step():
+                marks = []
+                lap(marks, "start")
                 Ah.set_values(hA[2].numpy())
+                lap(marks, "set_values")
                 A_b, b_b = ref_api.assembleLinearSystemBackground(Ah, hb.numpy(), Mh)
-                u_host[:] = 0.0
+                lap(marks, "assembleLinearSystemBackground")
+                u_pin.zero_()
                 u = ref_api.Vec(u_host)
                 ref_api.solveKSP(A_b, b_b, u, method="cg", PC="jacobi", monitor=False)
+                lap(marks, "solveKSP")
+                lap_print("e2e values", marks)
 
             Ah.device()
             e2e_values_step()

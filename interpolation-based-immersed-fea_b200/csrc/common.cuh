@@ -59,6 +59,30 @@ const char *get_err();
 
 #define IIFE_CHECK_LAUNCH() IIFE_CUDA(cudaGetLastError())
 
+// Launch with programmatic stream serialisation (PDL) when `pdl` is set: the kernel may be scheduled while the previous
+// kernel of the stream is still draining; it MUST call pdl_wait() before it reads anything an earlier kernel wrote (all
+// CTAs, before any early exit), and the previous kernel releases it with pdl_launch() (or by finishing).  Only for
+// kernels written for it (the CG iteration: ksp.cu, k_spmv_sell).
+#define IIFE_LAUNCH_PDL(pdl, kernel, grid, block, smem, ...)                                             \
+  do {                                                                                                   \
+    if (pdl) {                                                                                           \
+      cudaLaunchConfig_t _cfg = {};                                                                      \
+      _cfg.gridDim = dim3((unsigned)(grid));                                                             \
+      _cfg.blockDim = dim3((unsigned)(block));                                                           \
+      _cfg.dynamicSmemBytes = (smem);                                                                    \
+      _cfg.stream = ::iife::ctx().stream;                                                                \
+      cudaLaunchAttribute _attr[1];                                                                      \
+      _attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                  \
+      _attr[0].val.programmaticStreamSerializationAllowed = 1;                                           \
+      _cfg.attrs = _attr;                                                                                \
+      _cfg.numAttrs = 1;                                                                                 \
+      cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                                                    \
+    } else {                                                                                             \
+      kernel<<<(grid), (block), (smem), ::iife::ctx().stream>>>(__VA_ARGS__);                            \
+    }                                                                                                    \
+    ::iife::ctx().launches++;                                                                            \
+  } while (0)
+
 // device allocation with accounting
 int dev_alloc(void **p, size_t bytes);
 int dev_free(void *p, size_t bytes);
@@ -103,7 +127,8 @@ struct Mat {
   bool dinv_valid = false;
   uint64_t fp = 0;
   bool fp_valid = false;
-  int max_row_len = -1;  // lazily computed
+  int max_row_len = -1;  // lazily computed (mat_max_row_len)
+  int max_tile_entries = -1;  // with it: most entries in any 128 consecutive rows starting at a multiple of 128 (k_spmv_stream)
   // identity of the VALUES: uid is unique per matrix object, val_version counts iife_mat_update_values calls
   // (plans that precompute from an operand's values — ptap_prog.cuh — key on the pair)
   uint64_t uid = 0, val_version = 0;
@@ -117,8 +142,7 @@ struct Mat {
   double *sell_val = nullptr;
   bool sell_vals_valid = false;
   // row-partitioned solver: slice order "interior first" for the halo-fused SpMV
-  int *sell_order = nullptr;
-  int64_t sell_n_interior = 0, sell_order_owned = -1;
+  int64_t sell_n_interior = 0, sell_int_lo = -1, sell_order_owned = -1;  // mat_ensure_sell_order
 };
 
 int mat_alloc(Mat **out, int64_t n_rows, int64_t n_cols, int64_t nnz);
@@ -146,8 +170,7 @@ int spmv_pick_lpr(const Mat *A);
 // padding would exceed 1.25x nnz, in which case callers stay on CSR) and refreshes values.
 int mat_ensure_sell(Mat *A);
 int mat_ensure_sell_order(Mat *A, int64_t n_owned);
-int spmv_dot_halo_launch(const Mat *A, struct Halo *H, double *p, double *w, double *dot_out, double *partials,
-                         unsigned int *counter, const int *flag, const struct P2PRed *red);
+void spmv_set_pdl(bool on);  // the SpMV + dot launches that follow are part of a PDL chain (CG iteration)
 void mat_free_sell(Mat *A);
 
 // ghost-entry exchange plan of a row-partitioned operator (comm.cu)
@@ -191,6 +214,9 @@ struct Mailbox {
   // reductions fused into the CG kernels (two per iteration, slot = sequence parity)
   double it_vals[2][P2P_MAX_RANKS][4];
   unsigned long long it_flag[2][P2P_MAX_RANKS];
+  // the same reductions in "low latency" form: every double travels as two 8-byte words (half of the value | low 32
+  // bits of the sequence number), each store atomic and self-validating: no fence and no separate flag
+  unsigned long long it_ll[2][P2P_MAX_RANKS][8];
 };
 // enqueue on the library stream: push ghost entries of H->xbuf to the peers and wait for mine
 int p2p_halo_exchange(Halo *H, const int *reason_flag);
@@ -204,6 +230,8 @@ static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); 
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

@@ -168,6 +168,7 @@ __global__ void k_cg_init_scalars(double *sc, int *fl, double *hist, long long h
 __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_p(const double *__restrict__ r, const double *__restrict__ dinv, double *__restrict__ p, int64_t n,
        const double *__restrict__ sc, const int *__restrict__ fl) {
+  pdl_wait();
   if (fl[F_REASON] != 0) return;
   bool first = (fl[F_ITS] == 0);
   double bb = first ? 0.0 : sc[S_BETA] / sc[S_BETA_OLD];
@@ -176,6 +177,7 @@ k_cg_p(const double *__restrict__ r, const double *__restrict__ dinv, double *__
     double z = (dinv ? dinv[i] : 1.0) * r[i];
     p[i] = first ? z : fma(bb, p[i], z);
   }
+  pdl_launch();
 }
 
 // alpha = beta/delta; x += alpha p; r -= alpha w; z = D^-1 r; (z,r), (z,z) -> beta, dp, test(i+1)
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
             const double *__restrict__ w, const double *__restrict__ dinv, int64_t n, double *sc, int *fl,
             double *partials, unsigned int *counter, double *hist, long long hist_len, P2PRed pr) {
+  pdl_wait();
   if (fl[F_REASON] != 0) return;
   __shared__ double red[32];
   __shared__ double out[2];
@@ -236,6 +239,7 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
     acc[0] = fma(z, ri, acc[0]);
     acc[1] = fma(z, z, acc[1]);
   }
+  pdl_launch();
   if (grid_reduce<2>(acc, partials, counter, out, red, &last)) {
     if (MODE == 2 || MODE == 3) {
       p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 2ull, out, 2, threadIdx.x);
@@ -278,6 +282,7 @@ __global__ void k_cg_scalars_p2p(double *sc, int *fl, double *hist, long long hi
 __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_p_push(const double *__restrict__ r, const double *__restrict__ dinv, double *__restrict__ p, int64_t n, double *sc,
             int *fl, double *hist, long long hist_len, P2PRed pr, RowPush rp) {
+  pdl_wait();
   if (fl[F_REASON] != 0) return;  // set by an earlier kernel (CTA 0 of THIS kernel can only reach the same verdict)
   __shared__ double s_bb;
   __shared__ int s_stop;
@@ -339,6 +344,7 @@ k_cg_p_push(const double *__restrict__ r, const double *__restrict__ dinv, doubl
       stored = true;
     }
   }
+  pdl_launch();
   if (stored) __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -355,6 +361,7 @@ k_cg_p_push(const double *__restrict__ r, const double *__restrict__ dinv, doubl
 
 // end of a captured chunk of `chunk` iterations: the counters the kernels above offset with k
 __global__ void k_cg_chunk_end(unsigned long long *dev_seq, int chunk) {
+  pdl_wait();
   dev_seq[0] += (unsigned long long)chunk;
   dev_seq[2] += (unsigned long long)chunk;
 }
@@ -759,6 +766,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     for (int q = 0; q < P2P_MAX_RANKS; ++q) pr.peer[q] = H->peer_mbox[q];
     pr.iter = H->dev_seq + 2;
     pr.err = H->p2p_err;
+    pr.ll = env_int("IIFE_P2P_LL", 1) != 0 ? 1 : 0;  // packed 8-byte words instead of values + fence + flag
     IIFE_LAUNCH(k_bump_seq, 1, 1, 0, H->dev_seq + 2);
   }
   // r = b - A x0   (row-partitioned: x0 is staged in p to receive its ghost entries)
@@ -785,18 +793,10 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   KSP_DBG("init poll");
   if (hf->fl[F_REASON] != 0) return IIFE_OK;
 
-  // peer-memory path with a SELL operator: optionally the ghost exchange rides inside the SpMV kernel
-  // (IIFE_P2P_FUSED_HALO=1).  Measured at 2 GPUs / 0.8 M rows per GPU it is ~8 % SLOWER than the separate
-  // exchange kernel (three-phase tails outweigh the hidden latency), so it is off by default.
-  bool fused_halo = false;
-  if (p2p && A->sell_state == 1 && env_int("IIFE_P2P_FUSED_HALO", 0) != 0 && !dbg_nohalo) {
-    IIFE_TRY(mat_ensure_sell_order(A, H->n_owned));
-    fused_halo = (A->sell_order != nullptr);
-  }
   int chunk = env_int("IIFE_KSP_CHUNK", 32);
   if (chunk < 1) chunk = 1;
   // three-kernel iteration of the peer-memory path (k_cg_p_push / SpMV with halo wait / k_cg_update<3>)
-  const bool fused3 = p2p && !fused_halo && mat_sell_ready(A) && H->bmask && env_int("IIFE_CG_FUSED3", 1) != 0 && !dbg_nohalo &&
+  const bool fused3 = p2p && mat_sell_ready(A) && H->bmask && env_int("IIFE_CG_FUSED3", 1) != 0 && !dbg_nohalo &&
                       !dbg_nored;
   RowPush rpush{};
   HaloWait hwait{};
@@ -823,30 +823,37 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     hwait.nranks = H->nranks;
     hwait.recv_mask = H->recv_mask;
     hwait.err = H->p2p_err;
+    // interior slices before the ghost wait when they form one run (IIFE_CG_INTERIOR_FIRST=0: wait in the prologue)
+    if (env_int("IIFE_CG_INTERIOR_FIRST", 1) != 0) {
+      IIFE_TRY(mat_ensure_sell_order(A, H->n_owned));
+      if (A->sell_int_lo >= 0) {
+        hwait.interior_first = 1;
+        hwait.int_lo = A->sell_int_lo;
+        hwait.n_int = A->sell_n_interior;
+      }
+    }
   }
   // NCCL calls inside the loop: keep to plain stream launches (no graph capture) in that case
   const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && (!dist || p2p);
+  // programmatic dependent launch between the kernels of the iteration (single GPU and three-kernel peer path)
+  const bool pdl = env_int("IIFE_CG_PDL", 0) != 0 && (!dist || fused3);
+  spmv_set_pdl(pdl);
   auto enqueue_iteration = [&](int k) -> int {
     if (fused3) {
       P2PRed prk = pr;
       prk.k_off = k;
       HaloWait hwk = hwait;
       hwk.k_off = k;
-      IIFE_LAUNCH(k_cg_p_push, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl, w.hist, (long long)w.hist_len, prk, rpush);
+      IIFE_LAUNCH_PDL(pdl, k_cg_p_push, g, VEC_THREADS, 0, (const double *)r.p, dinv, p.p, n, w.sc, w.fl, w.hist, (long long)w.hist_len, prk, rpush);
       IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl, &prk, &hwk));
-      IIFE_LAUNCH(k_cg_update<3>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
-                  w.hist, (long long)w.hist_len, prk);
+      IIFE_LAUNCH_PDL(pdl, k_cg_update<3>, g, VEC_THREADS, 0, x, r.p, (const double *)p.p, (const double *)wv.p, dinv, n, w.sc, w.fl,
+                      w.partials, w.counters, w.hist, (long long)w.hist_len, prk);
       return IIFE_OK;
     }
-    IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, r.p, dinv, p.p, n, w.sc, w.fl);
-    if (fused_halo) {
-      IIFE_TRY(spmv_dot_halo_launch(A, H, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl,
-                                    dbg_nored ? nullptr : &pr));
-    } else {
-      if (dist && !dbg_nohalo) IIFE_TRY(xchg(w.fl));
-      IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl,
-                               (p2p && !dbg_nored) ? &pr : nullptr));
-    }
+    IIFE_LAUNCH_PDL(pdl && !dist, k_cg_p, g, VEC_THREADS, 0, (const double *)r.p, dinv, p.p, n, (const double *)w.sc, (const int *)w.fl);
+    if (dist && !dbg_nohalo) IIFE_TRY(xchg(w.fl));
+    IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl,
+                             (p2p && !dbg_nored) ? &pr : nullptr));
     if (dbg_nored) {
       IIFE_LAUNCH(k_cg_update<0>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
                   w.hist, (long long)w.hist_len, pr);
@@ -863,8 +870,8 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
       IIFE_TRY(ar(w.sc + S_RAW, 2, w.fl));
       IIFE_LAUNCH(k_cg_update_scalars, 1, 1, 0, w.sc, w.fl, w.hist, (long long)w.hist_len);
     } else {
-      IIFE_LAUNCH(k_cg_update<0>, g, VEC_THREADS, 0, x, r.p, p.p, wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
-                  w.hist, (long long)w.hist_len, pr);
+      IIFE_LAUNCH_PDL(pdl, k_cg_update<0>, g, VEC_THREADS, 0, x, r.p, (const double *)p.p, (const double *)wv.p, dinv, n, w.sc, w.fl,
+                      w.partials, w.counters, w.hist, (long long)w.hist_len, pr);
     }
     return IIFE_OK;
   };
@@ -904,7 +911,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     if (e == cudaSuccess) {
       int rc = IIFE_OK;
       for (int k = 0; k < chunk && rc == IIFE_OK; ++k) rc = enqueue_iteration(k);
-      if (fused3 && rc == IIFE_OK) IIFE_LAUNCH(k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
+      if (fused3 && rc == IIFE_OK) IIFE_LAUNCH_PDL(pdl, k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
       e = cudaStreamEndCapture(c.stream, &graph);
       if (rc == IIFE_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
       if (rc != IIFE_OK || e != cudaSuccess || !exec) {
@@ -935,7 +942,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
       c.launches += launches_per_chunk;
     } else {
       for (int k = 0; k < chunk; ++k) IIFE_TRY(enqueue_iteration(k));
-      if (fused3) IIFE_LAUNCH(k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
+      if (fused3) IIFE_LAUNCH_PDL(pdl, k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
       IIFE_CUDA(cudaGetLastError());
     }
     IIFE_CUDA(cudaMemcpyAsync(hf[slot].fl, w.fl, sizeof(int) * F_COUNT, cudaMemcpyDeviceToHost, c.stream));
@@ -955,6 +962,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     rc = enqueue_chunk(slot);
   }
   cudaStreamSynchronize(c.stream);
+  spmv_set_pdl(false);
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
   if (exec) cudaGraphExecDestroy(exec);

@@ -306,13 +306,22 @@ __global__ void k_diag(const int *__restrict__ rowptr, const int *__restrict__ c
 }
 
 __global__ void k_max_row_len(const int *__restrict__ rowptr, int64_t n_rows, int *__restrict__ out) {
-  int m = 0;
+  int m = 0, mt = 0;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n_rows; i += stride) m = max(m, rowptr[i + 1] - rowptr[i]);
+  for (; i < n_rows; i += stride) {
+    m = max(m, rowptr[i + 1] - rowptr[i]);
+    if ((i & 127) == 0) mt = max(mt, rowptr[i + 128 < n_rows ? i + 128 : n_rows] - rowptr[i]);
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+  for (int o = 16; o > 0; o >>= 1) {
+    m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    mt = max(mt, __shfl_down_sync(0xffffffffu, mt, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, m);
+    if (mt > 0) atomicMax(out + 1, mt);
+  }
 }
 
 static int grid_for(int64_t n, int threads = 256) {
@@ -326,14 +335,15 @@ static int grid_for(int64_t n, int threads = 256) {
 int mat_max_row_len(Mat *A, int *out) {
   if (A->max_row_len < 0) {
     Tmp<int> d;
-    IIFE_TRY(d.alloc(1));
-    IIFE_CUDA(cudaMemsetAsync(d.p, 0, sizeof(int), ctx().stream));
+    IIFE_TRY(d.alloc(2));
+    IIFE_CUDA(cudaMemsetAsync(d.p, 0, 2 * sizeof(int), ctx().stream));
     if (A->n_rows > 0) IIFE_LAUNCH(k_max_row_len, grid_for(A->n_rows), 256, 0, A->rowptr, A->n_rows, d.p);
     IIFE_CHECK_LAUNCH();
-    int h = 0;
-    IIFE_CUDA(cudaMemcpyAsync(&h, d.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    int h[2] = {0, 0};
+    IIFE_CUDA(cudaMemcpyAsync(h, d.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
     IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
-    A->max_row_len = h;
+    A->max_row_len = h[0];
+    A->max_tile_entries = h[1];
   }
   *out = A->max_row_len;
   return IIFE_OK;

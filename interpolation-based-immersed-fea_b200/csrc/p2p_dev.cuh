@@ -21,6 +21,7 @@ struct P2PRed {
   const unsigned long long *iter;  // device iteration counter: reductions 2*it+1 (delta) and 2*it+2 (z.r, z.z), it = *iter + k_off
   int *err;
   int k_off;                     // iteration index inside a graph-captured chunk (the counter moves once per chunk)
+  int ll;                        // 1: low-latency packed words (Mailbox::it_ll) instead of values + fence + flag
 };
 
 // SpMV prologue of the three-kernel CG iteration: wait until the ghost entries of exchange *seq_base + k_off + 1 arrived
@@ -30,6 +31,10 @@ struct HaloWait {
   int k_off, nranks;
   unsigned int recv_mask;
   int *err;
+  // interior first: slices [int_lo, int_lo + n_int) reference no ghost column and are multiplied before the wait, the
+  // others after it, so the NVLink latency of the exchange and the skew between the ranks hide behind the bulk
+  int interior_first;
+  long long int_lo, n_int;
 };
 
 // boundary rows of p and where they go (Halo::brow...)
@@ -69,6 +74,16 @@ __device__ __forceinline__ bool spin_until(const unsigned long long *p, unsigned
 __device__ __forceinline__ void p2p_push(const P2PRed &r, unsigned long long seq, const double *vals, int n, int tid) {
   if (tid < r.nranks) {
     const int par = (int)(seq & 1ull);
+    if (r.ll) {
+      const unsigned long long tag = (seq & 0xffffffffull) << 32;
+      unsigned long long *dst = r.peer[tid]->it_ll[par][r.me];
+      for (int i = 0; i < n; ++i) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong(vals[i]);
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2 * i), "l"((u & 0xffffffffull) | tag), "l"((u >> 32) | tag)
+                     : "memory");
+      }
+      return;
+    }
     for (int i = 0; i < n; ++i) r.peer[tid]->it_vals[par][r.me][i] = vals[i];
     __threadfence_system();
     st_flag(&r.peer[tid]->it_flag[par][r.me], seq);
@@ -83,8 +98,26 @@ __device__ __forceinline__ void p2p_wait_sum(const P2PRed &r, unsigned long long
   const int par = (int)(seq & 1ull);
   double v[4] = {0.0, 0.0, 0.0, 0.0};
   if (lane < r.nranks) {
-    spin_until(&r.mbox->it_flag[par][lane], seq, r.err);
-    for (int i = 0; i < n; ++i) v[i] = ((volatile double *)r.mbox->it_vals[par][lane])[i];
+    if (r.ll) {
+      const unsigned long long tag = seq & 0xffffffffull;
+      const unsigned long long *src = r.mbox->it_ll[par][lane];
+      const long long t0 = clock64();
+      for (int i = 0; i < n; ++i) {
+        unsigned long long w0, w1;
+        for (;;) {
+          asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src + 2 * i) : "memory");
+          if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+          if (clock64() - t0 > P2P_SPIN_LIMIT) {
+            atomicExch(r.err, 1);
+            break;
+          }
+        }
+        v[i] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+      }
+    } else {
+      spin_until(&r.mbox->it_flag[par][lane], seq, r.err);
+      for (int i = 0; i < n; ++i) v[i] = ((volatile double *)r.mbox->it_vals[par][lane])[i];
+    }
   }
   for (int i = 0; i < n; ++i) {
     double s = 0.0;

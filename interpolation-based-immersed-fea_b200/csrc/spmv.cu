@@ -135,8 +135,8 @@ k_spmv_ilp2(const int *__restrict__ rowptr, const int *__restrict__ colind, cons
 // irregular access left is the gather of x (L1/L2 resident: consecutive foreground rows touch neighbouring
 // background columns).  Persistent CTAs, tiles handed out round robin.
 // ------------------------------------------------------------------------------------------------
-constexpr int STREAM_ROWS = 256;   // rows per tile = threads per CTA
-constexpr int STREAM_STAGES = 3;
+constexpr int STREAM_ROWS = 128;  // rows per tile = threads per CTA
+constexpr int STREAM_MAX_STAGES = 4;
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -164,33 +164,39 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                : "memory");
 }
 
-// max_len: longest row of A (<= cap_entries / STREAM_ROWS).  Shared memory per stage: cap_entries + 4 column words and
-// cap_entries + 2 values (alignment slack: bulk copies start on 16-byte boundaries of the global arrays).
-__global__ void __launch_bounds__(STREAM_ROWS)
+// Shared memory per stage: the tile's row pointers (STREAM_ROWS + 4 words), cap_entries + 4 column words and
+// cap_entries + 2 values (alignment slack: bulk copies start on 16-byte boundaries of the global arrays).  cap_entries =
+// the largest number of entries any tile of STREAM_ROWS consecutive rows holds (Mat::max_tile_entries), so the stages
+// are sized by what the operator needs, not by rows x longest row: more CTAs per SM.  U = gathers of x in flight per
+// thread and round.
+template <int U, int R>
+__global__ void __launch_bounds__(R)
 k_spmv_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, const double *__restrict__ val, int64_t n_rows,
-              int64_t nnz, int cap_entries, const double *__restrict__ x, double *__restrict__ y) {
+              int64_t nnz, int cap_entries, int stages, const double *__restrict__ x, double *__restrict__ y) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bars[STREAM_STAGES];
-  __shared__ int s_base[STREAM_STAGES];  // first entry (rowptr[r0]) of the tile in each stage; -1: tile read from global
+  __shared__ __align__(8) unsigned long long bars[STREAM_MAX_STAGES];
+  __shared__ int s_base[STREAM_MAX_STAGES];  // first entry (rowptr[r0]) of the tile in each stage; < 0: tile read from global
+  constexpr size_t STREAM_RP_BYTES = (R + 4) * 4;
   const int tid = threadIdx.x;
   const size_t val_bytes = ((size_t)cap_entries + 2) * 8, col_bytes = (((size_t)cap_entries + 4) * 4 + 15) & ~(size_t)15;
-  const size_t stage_bytes = val_bytes + col_bytes;
-  const int64_t n_tiles = (n_rows + STREAM_ROWS - 1) / STREAM_ROWS;
+  const size_t stage_bytes = val_bytes + col_bytes + STREAM_RP_BYTES;
+  const int64_t n_tiles = (n_rows + R - 1) / R;
   if (tid == 0) {
-    for (int s = 0; s < STREAM_STAGES; ++s) mbar_init((unsigned)__cvta_generic_to_shared(&bars[s]), 1);
+    for (int s = 0; s < stages; ++s) mbar_init((unsigned)__cvta_generic_to_shared(&bars[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   // producer: thread 0 issues the copies of tile `t` into stage `s`
   auto issue = [&](int64_t t, int s) {
-    const int64_t r0 = t * STREAM_ROWS;
-    const int64_t r1 = r0 + STREAM_ROWS < n_rows ? r0 + STREAM_ROWS : n_rows;
+    const int64_t r0 = t * R;
+    const int64_t r1 = r0 + R < n_rows ? r0 + R : n_rows;
     const int b = __ldg(rowptr + r0), e = __ldg(rowptr + r1);
     const int bc = b & ~3, bv = b & ~1;
     const unsigned cb = (unsigned)(((e - bc) * 4 + 15) & ~15), vb = (unsigned)(((e - bv) * 8 + 15) & ~15);
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[s]);
     // the rounded-up copies may not run past the arrays (last tile): such a tile is read with plain loads instead
-    const bool fits = (int64_t)bc * 4 + cb <= nnz * 4 && (int64_t)bv * 8 + vb <= nnz * 8 && (e - b) <= cap_entries;
+    const bool fits = (int64_t)bc * 4 + cb <= nnz * 4 && (int64_t)bv * 8 + vb <= nnz * 8 && (e - b) <= cap_entries &&
+                      r0 + R + 4 <= n_rows + 1;
     if (e == b || !fits) {
       s_base[s] = -1 - b;  // nothing staged (empty tile, or tail / oversized tile)
       mbar_expect_tx(bar, 0);
@@ -198,65 +204,85 @@ k_spmv_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, co
     }
     s_base[s] = b;
     unsigned char *st = smem + (size_t)s * stage_bytes;
-    mbar_expect_tx(bar, cb + vb);
+    mbar_expect_tx(bar, cb + vb + (unsigned)STREAM_RP_BYTES);
     bulk_g2s((unsigned)__cvta_generic_to_shared(st), val + bv, vb, bar);
     bulk_g2s((unsigned)__cvta_generic_to_shared(st + val_bytes), colind + bc, cb, bar);
+    bulk_g2s((unsigned)__cvta_generic_to_shared(st + val_bytes + col_bytes), rowptr + r0, (unsigned)STREAM_RP_BYTES, bar);
   };
   const int64_t first = blockIdx.x, step = gridDim.x;
   if (tid == 0)
-    for (int s = 0; s < STREAM_STAGES; ++s)
+    for (int s = 0; s < stages; ++s)
       if (first + (int64_t)s * step < n_tiles) issue(first + (int64_t)s * step, s);
-  int64_t k = 0;
-  for (int64_t t = first; t < n_tiles; t += step, ++k) {
-    const int s = (int)(k % STREAM_STAGES);
-    const unsigned phase = (unsigned)((k / STREAM_STAGES) & 1);
+  int s = 0;
+  unsigned phase = 0;
+  for (int64_t t = first; t < n_tiles; t += step) {
     mbar_wait((unsigned)__cvta_generic_to_shared(&bars[s]), phase);
     const int base = s_base[s];
-    const int64_t i = t * STREAM_ROWS + tid;
+    const int64_t i = t * R + tid;
     if (i < n_rows) {
-      const int rb = __ldg(rowptr + i), re = __ldg(rowptr + i + 1);
       double acc = 0.0;
       if (base >= 0) {
-        const double *sv = (const double *)(smem + (size_t)s * stage_bytes) - (base & ~1);
-        const int *sc = (const int *)(smem + (size_t)s * stage_bytes + val_bytes) - (base & ~3);
-        // four gathers of x in flight per thread (rows are short: a plain loop would leave one)
-        for (int p = rb; p < re; p += 4) {
-          double xv[4], av[4];
+        const unsigned char *st = smem + (size_t)s * stage_bytes;
+        const double *sv = (const double *)st - (base & ~1);
+        const int *sc = (const int *)(st + val_bytes) - (base & ~3);
+        const int *srp = (const int *)(st + val_bytes + col_bytes);
+        const int rb = srp[tid], re = srp[tid + 1];
+        // U gathers of x in flight per thread (rows are short: a plain loop would leave one)
+        for (int p = rb; p < re; p += U) {
+          double xv[U], av[U];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < U; ++u) {
             const bool in = p + u < re;
             av[u] = in ? sv[p + u] : 0.0;
             xv[u] = in ? __ldg(x + sc[p + u]) : 0.0;
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) acc = fma(av[u], xv[u], acc);
+          for (int u = 0; u < U; ++u) acc = fma(av[u], xv[u], acc);
         }
       } else {
+        const int rb = __ldg(rowptr + i), re = __ldg(rowptr + i + 1);
         for (int p = rb; p < re; ++p) acc = fma(ld_stream(val + p), __ldg(x + ld_stream(colind + p)), acc);
       }
       y[i] = acc;
     }
     __syncthreads();  // every thread is done with stage s: refill it
-    if (tid == 0 && t + (int64_t)STREAM_STAGES * step < n_tiles) issue(t + (int64_t)STREAM_STAGES * step, s);
+    if (tid == 0 && t + (int64_t)stages * step < n_tiles) issue(t + (int64_t)stages * step, s);
+    if (++s == stages) {
+      s = 0;
+      phase ^= 1u;
+    }
   }
 }
 
-int spmv_stream_launch(const Mat *A, int max_len, const double *x, double *y) {
+template <int U, int R>
+static int spmv_stream_go(const Mat *A, int cap, int stages, const double *x, double *y) {
   Ctx &c = ctx();
-  const int cap = STREAM_ROWS * max_len;
-  const size_t stage = ((size_t)cap + 2) * 8 + ((((size_t)cap + 4) * 4 + 15) & ~(size_t)15);
-  const size_t smem = stage * STREAM_STAGES;
-  if (smem > 48 * 1024) IIFE_CUDA(cudaFuncSetAttribute(k_spmv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t stage = ((size_t)cap + 2) * 8 + ((((size_t)cap + 4) * 4 + 15) & ~(size_t)15) + (R + 4) * 4;
+  const size_t smem = stage * stages;
+  auto kern = &k_spmv_stream<U, R>;
+  if (smem > 48 * 1024) IIFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_stream, STREAM_ROWS, smem) != cudaSuccess || per_sm < 1) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, R, smem) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     per_sm = 1;
   }
-  const int64_t n_tiles = (A->n_rows + STREAM_ROWS - 1) / STREAM_ROWS;
+  const int64_t n_tiles = (A->n_rows + R - 1) / R;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)c.sm_count * per_sm));
-  IIFE_LAUNCH(k_spmv_stream, grid, STREAM_ROWS, smem, A->rowptr, A->colind, A->val, A->n_rows, A->nnz, cap, x, y);
+  IIFE_LAUNCH(kern, grid, R, smem, A->rowptr, A->colind, A->val, A->n_rows, A->nnz, cap, stages, x, y);
   IIFE_CHECK_LAUNCH();
   return IIFE_OK;
+}
+
+// Measured on M of the N_b = 184 cube (50 M rows, 1-8 entries): what matters is the number of resident threads (every
+// thread has one row's gathers in flight), not the depth of the copy pipeline: 256-row tiles x 3 stages sized by rows x
+// longest row 0.655 ms; sized by the real tile maximum 0.612; 2 stages 0.462; 128-row tiles x 2 stages 0.433 ms
+// (0.95 of the measured copy peak); 3 / 4 stages 0.55 / 0.73; 8 gathers per round 0.47.
+int spmv_stream_launch(const Mat *A, int max_len, const double *x, double *y) {
+  static const int stages_env = getenv("IIFE_STREAM_STAGES") ? atoi(getenv("IIFE_STREAM_STAGES")) : 2;
+  const int stages = std::max(1, std::min(stages_env, STREAM_MAX_STAGES));
+  int cap = STREAM_ROWS * max_len;
+  if (A->max_tile_entries > 0 && A->max_tile_entries < cap) cap = (A->max_tile_entries + 3) & ~3;
+  return spmv_stream_go<4, STREAM_ROWS>(A, cap, stages, x, y);
 }
 
 // w = A p, dot = (p, w).  Rows of A index p as well (A square on the local row block).
@@ -467,16 +493,17 @@ __global__ void k_sell_compact(const int *__restrict__ sell_ptr, const int *__re
   }
 }
 
-template <bool DOT, int U>
+template <bool DOT, int U, bool IFIRST>
 __global__ void IIFE_SELL_BOUNDS
 k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr, const int *__restrict__ sell_col,
             const double *__restrict__ sell_val, int64_t n_rows, int64_t n_slices, const double *__restrict__ x, double *__restrict__ y,
             double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *__restrict__ counter,
             const int *__restrict__ flag, P2PRed pr, HaloWait hw) {
+  pdl_wait();
   if (flag && *flag != 0) return;  // converged: the rest of the enqueued chunk is a row of no-ops
   __shared__ double red[32];
   __shared__ bool is_last;
-  if (hw.flags) {  // three-kernel CG iteration: the neighbours' k_cg_p_push stores the ghost entries of x
+  if (!IFIRST && hw.flags) {  // three-kernel CG iteration: the neighbours' k_cg_p_push stores the ghost entries of x
     const int q = threadIdx.x;
     if (q < hw.nranks && ((hw.recv_mask >> q) & 1u)) spin_until(hw.flags + q, *hw.seq_base + (unsigned long long)hw.k_off + 1ull, hw.err);
     __syncthreads();
@@ -485,14 +512,47 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr,
   const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   double dsum = 0.0;
-  for (int64_t s = w0; s < n_slices; s += nw) {
-    const double acc = sell_slice<U>(sell_ptr, sell_cptr, sell_col, sell_val, x, s, lane, n_rows);
-    const int64_t i = s * 32 + lane;
-    if (i < n_rows) {
-      y[i] = acc;
-      if (DOT) dsum = fma(acc, __ldg(x + i), dsum);
+  if (!IFIRST) {
+    for (int64_t s = w0; s < n_slices; s += nw) {
+      const double acc = sell_slice<U>(sell_ptr, sell_cptr, sell_col, sell_val, x, s, lane, n_rows);
+      const int64_t i = s * 32 + lane;
+      if (i < n_rows) {
+        y[i] = acc;
+        if (DOT) dsum = fma(acc, __ldg(x + i), dsum);
+      }
+    }
+  } else {
+    // interior slices (no ghost column): the ghost entries may still be in flight
+    for (int64_t v = w0; v < hw.n_int; v += nw) {
+      const int64_t s = hw.int_lo + v;
+      const double acc = sell_slice<U>(sell_ptr, sell_cptr, sell_col, sell_val, x, s, lane, n_rows);
+      const int64_t i = s * 32 + lane;
+      if (i < n_rows) {
+        y[i] = acc;
+        if (DOT) dsum = fma(acc, __ldg(x + i), dsum);
+      }
+    }
+    // boundary slices [0, int_lo) and [int_lo + n_int, n_slices), handed out from the far end of the warp list (the
+    // warps with one interior slice fewer); each warp waits for the flags itself; x is read past L1 (the ghost
+    // entries landed during this kernel, and a line holding the last owned entries may sit in L1 with stale ghosts)
+    const int64_t n_bnd = n_slices - hw.n_int;
+    const int64_t b0 = nw - 1 - w0;
+    if (b0 < n_bnd) {
+      if (lane < hw.nranks && ((hw.recv_mask >> lane) & 1u))
+        spin_until(hw.flags + lane, *hw.seq_base + (unsigned long long)hw.k_off + 1ull, hw.err);
+      __syncwarp();
+      for (int64_t b = b0; b < n_bnd; b += nw) {
+        const int64_t s = b < hw.int_lo ? b : b + hw.n_int;
+        const double acc = sell_slice<U, true>(sell_ptr, sell_cptr, sell_col, sell_val, x, s, lane, n_rows);
+        const int64_t i = s * 32 + lane;
+        if (i < n_rows) {
+          y[i] = acc;
+          if (DOT) dsum = fma(acc, __ldcg(x + i), dsum);
+        }
+      }
     }
   }
+  pdl_launch();
   if (DOT) {
     double bs = block_sum(dsum, red);
     if (threadIdx.x == 0) {
@@ -517,122 +577,6 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr,
         __syncthreads();
         p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 1ull, &s_sum, 1, threadIdx.x);
       }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Row-partitioned solver, peer-memory path: SpMV + (p, Ap) with the ghost exchange INSIDE the kernel.
-//   phase 0  all CTAs store this rank's boundary entries of x into the neighbours' vectors; the last
-//            CTA to finish raises the sequence flags in their mailboxes
-//   phase 1  slices whose rows touch no ghost column (the bulk) are multiplied
-//   phase 2  every CTA waits for the flags of the ranks it receives from
-//   phase 3  the remaining (boundary) slices
-// so the NVLink latency of the exchange hides behind the interior rows.  `order` lists the interior
-// slices first (n_interior of them), then the boundary slices.
-// ------------------------------------------------------------------------------------------------
-struct HaloFused {
-  const int *send_idx;
-  const unsigned char *send_peer;
-  const int *send_off;
-  long long total_send;
-  PeerTable pt;
-  Mailbox *mbox;
-  int me, nranks;
-  unsigned int send_mask, recv_mask;
-  unsigned long long *seq_ptr;
-  unsigned int *push_counter;
-  int *err;
-};
-
-template <int U>
-__global__ void __launch_bounds__(SPMV_THREADS)
-k_spmv_sell_halo(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr, const int *__restrict__ sell_col,
-                 const double *__restrict__ sell_val, int64_t n_rows, int64_t n_slices, const int *__restrict__ order, int64_t n_interior, double *x,
-                 double *__restrict__ y, double *__restrict__ dot_out, double *__restrict__ partials,
-                 unsigned int *__restrict__ counter, const int *__restrict__ flag, P2PRed pr, HaloFused hf) {
-  if (flag && *flag != 0) return;
-  __shared__ double red[32];
-  __shared__ bool is_last;
-  __shared__ bool last_pusher;
-  const int lane = threadIdx.x & 31;
-  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const unsigned long long seq = *hf.seq_ptr + 1ull;
-  // ---- phase 0: push
-  {
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
-    bool stored = false;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < hf.total_send; k += nthreads) {
-      int q = hf.send_peer[k];
-      hf.pt.xbuf[q][hf.pt.dst_start[q] + (k - hf.send_off[q])] = x[hf.send_idx[k]];
-      stored = true;
-    }
-    // only threads that stored need the system-scope fence (a fence invalidates the SM's L1, which the
-    // x gathers of the co-resident CTAs live on)
-    if (stored) __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int t = atomicAdd(hf.push_counter, 1u);
-      last_pusher = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (last_pusher) {
-      int q = threadIdx.x;
-      if (q < hf.nranks && ((hf.send_mask >> q) & 1u)) st_flag(&hf.pt.mbox[q]->halo_flag[hf.me], seq);
-    }
-  }
-  double dsum = 0.0;
-  // ---- phase 1: interior slices
-  for (int64_t idx = w0; idx < n_interior; idx += nw) {
-    const int64_t s = order[idx];
-    const double acc = sell_slice<U>(sell_ptr, sell_cptr, sell_col, sell_val, x, s, lane, n_rows);
-    const int64_t i = s * 32 + lane;
-    if (i < n_rows) {
-      y[i] = acc;
-      dsum = fma(acc, x[i], dsum);
-    }
-  }
-  // ---- phase 2: ghosts must have arrived
-  {
-    int q = threadIdx.x;
-    if (q < hf.nranks && ((hf.recv_mask >> q) & 1u)) spin_until(&hf.mbox->halo_flag[q], seq, hf.err);  // ld.acquire.sys
-    __syncthreads();  // ghost entries are then read with volatile (L1-bypassing) loads: no fence needed
-  }
-  // ---- phase 3: boundary slices (ghost entries are read with plain loads: written by peers during this kernel)
-  for (int64_t idx = n_interior + w0; idx < n_slices; idx += nw) {
-    const int64_t s = order[idx];
-    const double acc = sell_slice<U, true>(sell_ptr, sell_cptr, sell_col, sell_val, x, s, lane, n_rows);
-    const int64_t i = s * 32 + lane;
-    if (i < n_rows) {
-      y[i] = acc;
-      dsum = fma(acc, x[i], dsum);
-    }
-  }
-  double bs = block_sum(dsum, red);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = bs;
-    __threadfence();
-    unsigned int t = atomicAdd(counter, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    double sacc = 0.0;
-    for (int kk = threadIdx.x; kk < (int)gridDim.x; kk += blockDim.x) sacc += __ldcg(partials + kk);
-    sacc = block_sum(sacc, red);
-    __shared__ double s_sum;
-    if (threadIdx.x == 0) {
-      *dot_out = sacc;
-      *counter = 0u;
-      *hf.push_counter = 0u;
-      *hf.seq_ptr = seq;
-      s_sum = sacc;
-    }
-    if (pr.enabled) {
-      __syncthreads();
-      p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 1ull, &s_sum, 1, threadIdx.x);
     }
   }
 }
@@ -745,6 +689,9 @@ static int sell_unroll() {
   return u;
 }
 
+static bool g_sell_pdl = false;  // set by the CG driver around its iteration launches (spmv_set_pdl)
+void spmv_set_pdl(bool on) { g_sell_pdl = on; }
+
 static int launch_sell(const Mat *A, bool dot, const double *x, double *y, double *dot_out, double *partials,
                        unsigned int *counter, const int *flag, const P2PRed *red_in = nullptr, const HaloWait *hw_in = nullptr) {
   P2PRed pr{};
@@ -752,17 +699,20 @@ static int launch_sell(const Mat *A, bool dot, const double *x, double *y, doubl
   HaloWait hw{};
   if (hw_in) hw = *hw_in;
   int64_t need = (A->sell_slices + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
-#define SELL_GO(D, UU)                                                                                              \
+#define SELL_GO(D, UU, IF)                                                                                          \
   {                                                                                                                 \
-    int g = resident_grid(k_spmv_sell<D, UU>, need);                                                                \
-    IIFE_LAUNCH((k_spmv_sell<D, UU>), g, SPMV_THREADS, 0, A->sell_ptr, A->sell_cptr, A->sell_col, A->sell_val, A->n_rows, \
-                A->sell_slices, x, y, dot_out, partials, counter, flag, pr, hw);                                    \
+    int g = resident_grid(k_spmv_sell<D, UU, IF>, need);                                                            \
+    IIFE_LAUNCH_PDL(g_sell_pdl && dot, (k_spmv_sell<D, UU, IF>), g, SPMV_THREADS, 0, (const int *)A->sell_ptr, (const int *)A->sell_cptr, \
+                    (const int *)A->sell_col, (const double *)A->sell_val, A->n_rows, A->sell_slices, x, y, dot_out, partials, counter, flag, pr, \
+                    hw);                                                                                            \
   }
   int u = sell_unroll();
-  if (dot) {
-    if (u == 2) SELL_GO(true, 2) else if (u == 8) SELL_GO(true, 8) else SELL_GO(true, 4)
+  if (dot && hw.flags && hw.interior_first) {
+    SELL_GO(true, 4, true)
+  } else if (dot) {
+    if (u == 2) SELL_GO(true, 2, false) else if (u == 8) SELL_GO(true, 8, false) else SELL_GO(true, 4, false)
   } else {
-    if (u == 2) SELL_GO(false, 2) else if (u == 8) SELL_GO(false, 8) else SELL_GO(false, 4)
+    if (u == 2) SELL_GO(false, 2, false) else if (u == 8) SELL_GO(false, 8, false) else SELL_GO(false, 4, false)
   }
 #undef SELL_GO
   IIFE_CHECK_LAUNCH();
@@ -772,68 +722,41 @@ static int launch_sell(const Mat *A, bool dot, const double *x, double *y, doubl
 static int sell_grid(int64_t n_slices);
 static bool sell_ready(const Mat *A);
 
+// Interior slices of a row-partitioned operator block (columns >= n_owned are ghosts): when they form ONE run
+// [sell_int_lo, sell_int_lo + sell_n_interior) — row blocks of a banded operator: the boundary rows sit at the two ends —
+// the three-kernel CG iteration multiplies them before it waits for the ghost entries (k_spmv_sell<.,.,true>).
+// sell_int_lo = -1 otherwise (the wait then stays in the prologue).
 int mat_ensure_sell_order(Mat *A, int64_t n_owned) {
   if (A->sell_state != 1) return IIFE_OK;
-  if (A->sell_order && A->sell_order_owned == n_owned) return IIFE_OK;
-  if (A->sell_order) {
-    dev_free_t(A->sell_order, (size_t)A->sell_slices);
-    A->sell_order = nullptr;
-  }
+  if (A->sell_order_owned == n_owned) return IIFE_OK;
   const int64_t ns = A->sell_slices;
-  Tmp<int> fi, fb, oi, ob;
+  Tmp<int> fi, fb, oi, ob, order;
   IIFE_TRY(fi.alloc((size_t)ns + 1));
   IIFE_TRY(fb.alloc((size_t)ns + 1));
   IIFE_TRY(oi.alloc((size_t)ns + 1));
   IIFE_TRY(ob.alloc((size_t)ns + 1));
+  IIFE_TRY(order.alloc((size_t)ns));
   IIFE_LAUNCH(k_sell_ghost_flag, sell_grid(ns), SPMV_THREADS, 0, A->sell_ptr, A->sell_cptr, A->sell_col, A->n_rows, ns, (int)n_owned, fi.p, fb.p);
   IIFE_CHECK_LAUNCH();
   int64_t n_int = 0, n_bnd = 0;
   IIFE_TRY(exclusive_scan_i32(fi.p, oi.p, ns, &n_int));
   IIFE_TRY(exclusive_scan_i32(fb.p, ob.p, ns, &n_bnd));
-  IIFE_TRY(dev_alloc_t(&A->sell_order, (size_t)ns));
-  IIFE_LAUNCH(k_sell_order, sell_grid(ns), SPMV_THREADS, 0, fi.p, oi.p, ob.p, ns, (int)n_int, A->sell_order);
+  IIFE_LAUNCH(k_sell_order, sell_grid(ns), SPMV_THREADS, 0, fi.p, oi.p, ob.p, ns, (int)n_int, order.p);
   IIFE_CHECK_LAUNCH();
+  int ends[2] = {0, 0};  // first and last interior slice (k_sell_order keeps the slices in order inside each class)
+  if (n_int > 0) {
+    IIFE_CUDA(cudaMemcpyAsync(&ends[0], order.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    IIFE_CUDA(cudaMemcpyAsync(&ends[1], order.p + (n_int - 1), sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+  }
   IIFE_CUDA(cudaStreamSynchronize(ctx().stream));
   A->sell_n_interior = n_int;
+  A->sell_int_lo = (n_int > 0 && (int64_t)ends[1] - ends[0] + 1 == n_int) ? ends[0] : -1;
   A->sell_order_owned = n_owned;
   return IIFE_OK;
 }
 
-// SpMV + dot with the ghost exchange fused (peer-memory path of the row-partitioned CG)
-int spmv_dot_halo_launch(const Mat *A, Halo *H, double *p, double *w, double *dot_out, double *partials,
-                         unsigned int *counter, const int *flag, const P2PRed *red) {
-  if (!sell_ready(A) || !A->sell_order || !H->p2p) return set_err(IIFE_ERR_STATE, "fused halo SpMV needs SELL + order + p2p");
-  HaloFused hf;
-  hf.send_idx = H->send_idx;
-  hf.send_peer = H->send_peer;
-  hf.send_off = H->send_off_dev;
-  hf.total_send = H->total_send;
-  for (int q = 0; q < P2P_MAX_RANKS; ++q) {
-    hf.pt.xbuf[q] = H->peer_xbuf[q];
-    hf.pt.mbox[q] = H->peer_mbox[q];
-    hf.pt.dst_start[q] = H->dst_start[q];
-  }
-  hf.mbox = H->mbox;
-  hf.me = H->me;
-  hf.nranks = H->nranks;
-  hf.send_mask = H->send_mask;
-  hf.recv_mask = H->recv_mask;
-  hf.seq_ptr = H->dev_seq;
-  hf.push_counter = H->p2p_counter;
-  hf.err = H->p2p_err;
-  P2PRed pr{};
-  if (red) pr = *red;
-  int64_t need = (A->sell_slices + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
-  int g = resident_grid(k_spmv_sell_halo<4>, need);
-  IIFE_LAUNCH(k_spmv_sell_halo<4>, g, SPMV_THREADS, 0, A->sell_ptr, A->sell_cptr, A->sell_col, A->sell_val, A->n_rows, A->sell_slices,
-              A->sell_order, A->sell_n_interior, p, w, dot_out, partials, counter, flag, pr, hf);
-  IIFE_CHECK_LAUNCH();
-  return IIFE_OK;
-}
-
 void mat_free_sell(Mat *A) {
-  if (A->sell_order) dev_free_t(A->sell_order, (size_t)A->sell_slices);
-  A->sell_order = nullptr;
+  A->sell_order_owned = -1;
   if (A->sell_ptr) dev_free_t(A->sell_ptr, (size_t)A->sell_slices + 1);
   if (A->sell_col) dev_free_t(A->sell_col, (size_t)A->sell_cwords);
   if (A->sell_cptr) dev_free_t(A->sell_cptr, (size_t)A->sell_slices + 1);
