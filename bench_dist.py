@@ -167,23 +167,31 @@ def run(args, I, stream, peak, peak_src, metric, unit, ClockSampler):
             parity = {"parity_check": f"not run: {str(exc)[:160]}", "partitioned": got}
     barrier()
 
-    # ---- end to end at N GPUs through DistExtraction (its public per-step API takes the VALUES of this rank's rows of
-    # A_f and its block of b_f: the pattern was routed once at setup, as PETSc's MPIAIJ assembly reuses its layout):
-    # every step uploads them from pinned host memory and brings this rank's block of u_b back
+    # ---- end to end at N GPUs through DistExtraction: every step uploads the CSR arrays of this rank's rows of A_f (a
+    # freshly assembled matrix, as in the single-GPU figure) and its block of b_f from pinned host memory, and brings this
+    # rank's block of u_b back.  The pattern was routed once at setup; numeric_csr checks the new one against it.
     e2e = None
     if not getattr(args, "no_e2e", False):
         try:
+            hrp = torch.empty(A_t[0].numel(), dtype=torch.int32).pin_memory()
+            hci = torch.empty(A_t[1].numel(), dtype=torch.int32).pin_memory()
             hv = torch.empty(A_t[2].numel(), dtype=torch.float64).pin_memory()
             hb = torch.empty(b_f.numel(), dtype=torch.float64).pin_memory()
             hx = torch.empty(ex.n_owned, dtype=torch.float64).pin_memory()
+            hrp.copy_(A_t[0])
+            hci.copy_(A_t[1])
             hv.copy_(A_t[2])
             hb.copy_(b_f)
+            drp, dci = torch.empty_like(A_t[0]), torch.empty_like(A_t[1])
             torch.cuda.synchronize()
 
             def e2e_step():
+                # a freshly assembled block of A_f: all three CSR arrays cross PCIe, as in the single-GPU figure
+                drp.copy_(hrp, non_blocking=True)
+                dci.copy_(hci, non_blocking=True)
                 A_t[2].copy_(hv, non_blocking=True)
                 b_f.copy_(hb, non_blocking=True)
-                ex.numeric(A_t[2])
+                ex.numeric_csr(drp, dci, A_t[2])
                 bbe = ex.rhs(b_f)
                 x.zero_()
                 ex.solve(bbe, x)
@@ -198,12 +206,13 @@ def run(args, I, stream, peak, peak_src, metric, unit, ClockSampler):
                 e2e_step()
             barrier()
             dt = _max_over_ranks((time.perf_counter() - t0) / n_e2e, dev)
-            h2d = _sum_over_ranks([hv.numel() * 8 + hb.numel() * 8, hx.numel() * 8], dev)
+            h2d = _sum_over_ranks([hrp.numel() * 4 + hci.numel() * 4 + hv.numel() * 8 + hb.numel() * 8, hx.numel() * 8], dev)
             e2e = {"value": n_f / dt / 1e6, "unit": unit, "h2d_bytes_per_step": int(h2d[0]),
                    "d2h_bytes_per_step": int(h2d[1]), "ms_per_step": dt * 1e3, "steps": n_e2e,
-                   "api": "iife_b200.dist.DistExtraction.numeric/rhs/solve: values of A_f and b_f from pinned host memory "
-                          "on every rank (pattern routed once at setup), u_b back to the host"}
-            del hv, hb, hx
+                   "api": "iife_b200.dist.DistExtraction.numeric_csr/rhs/solve: every rank uploads the full CSR arrays of its "
+                          "rows of A_f and its block of b_f from pinned host memory (same accounting as the single-GPU "
+                          "figure; the pattern is checked on the device against the one routed at setup), u_b back"}
+            del hrp, hci, hv, hb, hx, drp, dci
         except Exception as exc:  # the device-resident line must survive
             e2e = {"error": str(exc)[:200]}
     if rank == 0:

@@ -151,6 +151,9 @@ int iife_plan_get_info(iife_plan P, int64_t *n_b, int64_t *nnz_c, int64_t *nnz_i
  * 8K/4K, [4] CTA hashing with global-memory tables, [5] slot plan 128/32, [6] slot plan 256/256 (tests use it to
  * prove that every kernel of the ladder is exercised) */
 int iife_plan_bin_counts(iife_plan P, int64_t *counts7);
+/* the same for the first n bins; [7] = slot plan for wide rows (intermediate row <= 2040, output row <= 512 entries, two
+ * bytes per product term: quadratic / 3-D unfitted backgrounds) */
+int iife_plan_bin_counts_n(iife_plan P, int64_t *counts, int n);
 /* template plan of the numeric phase (built on the first numeric call, rebuilt when the values of M change):
  * rows of the slot-plan bins that share structure and M values with at least IIFE_TPL_MIN_ROWS (32) others run one
  * precompiled gather program per group.  n_templates groups cover n_rows rows in n_chunks work items;

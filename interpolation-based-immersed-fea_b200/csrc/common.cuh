@@ -198,7 +198,7 @@ struct Halo {
   unsigned int send_mask = 0, recv_mask = 0;
   // push plan by OWNED ROW (three-kernel CG iteration, ksp.cu): the thread that updates p[i] also stores it into the
   // neighbours' ghost slots.  brow: sorted owned rows that are sent anywhere; entries bptr[k]..bptr[k+1] of
-  // (bpeer, bdst) say where; bmask: one bit per owned row (is it in brow?)
+  // (bpeer, bdst) say where; bmask: per 32 owned rows the pair (bits of the rows in brow, number of brow entries before)
   int n_brow = 0;
   int *brow = nullptr, *bptr = nullptr;
   unsigned char *bpeer = nullptr;

@@ -33,6 +33,10 @@ enum {
 enum { F_REASON = 0, F_ITS, F_LOC_IT, F_MAXIT, F_HAPEND, F_COUNT = 8 };
 
 constexpr int VEC_THREADS = 256;
+#ifndef IIFE_VEC_ILP
+#define IIFE_VEC_ILP 4
+#endif
+constexpr int VEC_ILP = IIFE_VEC_ILP;  // elements per thread and round in the CG vector kernels
 constexpr int MAX_PARTIALS = 2048;
 
 struct KspWork {
@@ -173,9 +177,24 @@ k_cg_p(const double *__restrict__ r, const double *__restrict__ dinv, double *__
   bool first = (fl[F_ITS] == 0);
   double bb = first ? 0.0 : sc[S_BETA] / sc[S_BETA_OLD];
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    double z = (dinv ? dinv[i] : 1.0) * r[i];
-    p[i] = first ? z : fma(bb, p[i], z);
+  // VEC_ILP elements per thread and round, all loads issued before the first use (a thread owns ~10 elements: one
+  // element per round leaves one batch of loads in flight and the kernel on the latency, not the bandwidth)
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += VEC_ILP * stride) {
+    double rv[VEC_ILP], dv[VEC_ILP], pv[VEC_ILP];
+#pragma unroll
+    for (int u = 0; u < VEC_ILP; ++u) {
+      const int64_t i = i0 + u * stride;
+      const bool in = i < n;
+      rv[u] = in ? r[i] : 0.0;
+      dv[u] = (in && dinv) ? dinv[i] : 1.0;
+      pv[u] = (in && !first) ? p[i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < VEC_ILP; ++u) {
+      const int64_t i = i0 + u * stride;
+      const double z = dv[u] * rv[u];
+      if (i < n) p[i] = first ? z : fma(bb, pv[u], z);
+    }
   }
   pdl_launch();
 }
@@ -199,12 +218,14 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
   double delta;
   if (MODE == 2 || MODE == 3) {
     __shared__ double s_delta;
+    if (MODE == 3 && blockIdx.x == 0 && threadIdx.x == 0) cg_trace(pr, TR_U_IN);
     if (threadIdx.x < 32) {
       double d;
       p2p_wait_sum(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 1ull, &d, 1);
       if (threadIdx.x == 0) {
         s_delta = d;
         if (blockIdx.x == 0) sc[S_DELTA] = d;
+        if (MODE == 3 && blockIdx.x == 0) cg_trace(pr, TR_U_WAITED);
       }
     }
     __syncthreads();
@@ -230,19 +251,36 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
   double alpha = beta_now / delta;
   double acc[2] = {0.0, 0.0};
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    double pi = p[i], wi = __ldcs(w + i);
-    x[i] = fma(alpha, pi, x[i]);
-    double ri = fma(-alpha, wi, r[i]);
-    r[i] = ri;
-    double z = (dinv ? dinv[i] : 1.0) * ri;
-    acc[0] = fma(z, ri, acc[0]);
-    acc[1] = fma(z, z, acc[1]);
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += VEC_ILP * stride) {
+    double pv[VEC_ILP], wv[VEC_ILP], xv[VEC_ILP], rv[VEC_ILP], dv[VEC_ILP];
+#pragma unroll
+    for (int u = 0; u < VEC_ILP; ++u) {  // all loads of the round first (see k_cg_p)
+      const int64_t i = i0 + u * stride;
+      const bool in = i < n;
+      pv[u] = in ? p[i] : 0.0;
+      wv[u] = in ? __ldcs(w + i) : 0.0;
+      xv[u] = in ? x[i] : 0.0;
+      rv[u] = in ? r[i] : 0.0;
+      dv[u] = (in && dinv) ? dinv[i] : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < VEC_ILP; ++u) {  // same order of the sums as one element per round
+      const int64_t i = i0 + u * stride;
+      if (i < n) {
+        x[i] = fma(alpha, pv[u], xv[u]);
+        const double ri = fma(-alpha, wv[u], rv[u]);
+        r[i] = ri;
+        const double z = dv[u] * ri;
+        acc[0] = fma(z, ri, acc[0]);
+        acc[1] = fma(z, z, acc[1]);
+      }
+    }
   }
   pdl_launch();
   if (grid_reduce<2>(acc, partials, counter, out, red, &last)) {
     if (MODE == 2 || MODE == 3) {
       p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 2ull, out, 2, threadIdx.x);
+      if (MODE == 3 && threadIdx.x == 0) cg_trace(pr, TR_U_OUT);
     } else if (threadIdx.x == 0) {
       if (MODE == 1) {
         sc[S_RAW + 0] = out[0];
@@ -290,11 +328,13 @@ k_cg_p_push(const double *__restrict__ r, const double *__restrict__ dinv, doubl
   const unsigned long long git = *pr.iter + (unsigned long long)pr.k_off;
   const unsigned long long it_rel = git - pr.iter[1];
   const bool first = (it_rel == 0ull);
+  if (blockIdx.x == 0 && threadIdx.x == 0) cg_trace(pr, TR_P_IN);
   if (!first) {
     if (threadIdx.x < 32) {
       double v[2];
       p2p_wait_sum(pr, 2ull * (git - 1ull) + 2ull, v, 2);
       if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) cg_trace(pr, TR_P_WAITED);
         // KSPSolve_CG after the update of iteration it_rel-1: beta_old <- beta, beta = (z, r), dp = ||z||, its, test
         const double beta_old = sc[S_BETA2 + (int)((it_rel - 1ull) & 1ull)];
         const double beta = v[0], dp = sqrt(v[1]);
@@ -329,19 +369,31 @@ k_cg_p_push(const double *__restrict__ r, const double *__restrict__ dinv, doubl
   const double bb = first ? 0.0 : s_bb;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   bool stored = false;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double z = (dinv ? dinv[i] : 1.0) * r[i];
-    const double pn = first ? z : fma(bb, p[i], z);
-    p[i] = pn;
-    if ((__ldg(rp.bmask + (i >> 5)) >> (i & 31)) & 1u) {  // a boundary row: its neighbours' ghost copies
-      int lo = 0, hi = rp.n_brow;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(rp.brow + mid) < (int)i) lo = mid + 1;
-        else hi = mid;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += VEC_ILP * stride) {
+    double rv[VEC_ILP], dv[VEC_ILP], pv[VEC_ILP];
+    uint2 mv[VEC_ILP];  // (boundary-row bits of the 32-row word, boundary rows before it)
+#pragma unroll
+    for (int u = 0; u < VEC_ILP; ++u) {  // all loads of the round first (see k_cg_p)
+      const int64_t i = i0 + u * stride;
+      const bool in = i < n;
+      rv[u] = in ? r[i] : 0.0;
+      dv[u] = (in && dinv) ? dinv[i] : 1.0;
+      pv[u] = (in && !first) ? p[i] : 0.0;
+      mv[u] = in ? __ldg((const uint2 *)rp.bmask + (i >> 5)) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < VEC_ILP; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n) continue;
+      const double z = dv[u] * rv[u];
+      const double pn = first ? z : fma(bb, pv[u], z);
+      p[i] = pn;
+      const unsigned bit = 1u << (i & 31);
+      if (mv[u].x & bit) {  // a boundary row: its neighbours' ghost copies
+        const int k = (int)mv[u].y + __popc(mv[u].x & (bit - 1u));
+        for (int e = __ldg(rp.bptr + k); e < __ldg(rp.bptr + k + 1); ++e) rp.pt.xbuf[rp.bpeer[e]][rp.bdst[e]] = pn;
+        stored = true;
       }
-      for (int e = __ldg(rp.bptr + lo); e < __ldg(rp.bptr + lo + 1); ++e) rp.pt.xbuf[rp.bpeer[e]][rp.bdst[e]] = pn;
-      stored = true;
     }
   }
   pdl_launch();
@@ -356,7 +408,10 @@ k_cg_p_push(const double *__restrict__ r, const double *__restrict__ dinv, doubl
   __threadfence_system();
   const int q = threadIdx.x;
   if (q < rp.nranks && ((rp.send_mask >> q) & 1u)) st_flag(&rp.pt.mbox[q]->halo_flag[rp.me], *rp.seq_base + (unsigned long long)pr.k_off + 1ull);
-  if (threadIdx.x == 0) *rp.counter = 0u;
+  if (threadIdx.x == 0) {
+    *rp.counter = 0u;
+    cg_trace(pr, TR_P_OUT);
+  }
 }
 
 // end of a captured chunk of `chunk` iterations: the counters the kernels above offset with k
@@ -747,6 +802,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   static const bool dbg_nohalo = getenv("IIFE_DBG_NOHALO") != nullptr, dbg_nored = getenv("IIFE_DBG_NORED") != nullptr;
   struct PBuf { double *p = nullptr; } p;
   Tmp<double> r, p_own, wv;
+  Tmp<unsigned long long> trace;
   IIFE_TRY(r.alloc((size_t)n));
   if (p2p) p.p = H->xbuf;
   else {
@@ -767,6 +823,11 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     pr.iter = H->dev_seq + 2;
     pr.err = H->p2p_err;
     pr.ll = env_int("IIFE_P2P_LL", 1) != 0 ? 1 : 0;  // packed 8-byte words instead of values + fence + flag
+    if (env_int("IIFE_CG_TRACE", 0) != 0) {
+      IIFE_TRY(trace.alloc((size_t)CG_TRACE_ITERS * CG_TRACE_SLOTS));
+      IIFE_CUDA(cudaMemsetAsync(trace.p, 0, sizeof(unsigned long long) * CG_TRACE_ITERS * CG_TRACE_SLOTS, c.stream));
+      pr.trace = trace.p;
+    }
     IIFE_LAUNCH(k_bump_seq, 1, 1, 0, H->dev_seq + 2);
   }
   // r = b - A x0   (row-partitioned: x0 is staged in p to receive its ghost entries)
@@ -963,6 +1024,35 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   }
   cudaStreamSynchronize(c.stream);
   spmv_set_pdl(false);
+  if (trace.p && rc == IIFE_OK) {
+    // averages over iterations 20 .. its-5 of this solve (nanoseconds between the stamps; see p2p_dev.cuh)
+    std::vector<unsigned long long> t((size_t)CG_TRACE_ITERS * CG_TRACE_SLOTS);
+    cudaMemcpy(t.data(), trace.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    const int its = hf[0].fl[F_ITS] > hf[1].fl[F_ITS] ? hf[0].fl[F_ITS] : hf[1].fl[F_ITS];
+    const int lo = 20, hi = std::min(its - 5, CG_TRACE_ITERS - 2);
+    if (hi > lo) {
+      auto at = [&](int it, int slot) { return (double)t[(size_t)it * CG_TRACE_SLOTS + slot]; };
+      const char *names[9] = {"p: wait (z,r)", "p: update + push", "gap p -> spmv", "spmv: to ghost wait done", "spmv: rest + dot push",
+                              "gap spmv -> update", "update: wait delta", "update: x, r + push", "gap update -> p"};
+      double sum[9] = {0};
+      for (int it = lo; it < hi; ++it) {
+        sum[0] += at(it, TR_P_WAITED) - at(it, TR_P_IN);
+        sum[1] += at(it, TR_P_OUT) - at(it, TR_P_WAITED);
+        sum[2] += at(it, TR_S_IN) - at(it, TR_P_OUT);
+        sum[3] += at(it, TR_S_WAITED) - at(it, TR_S_IN);
+        sum[4] += at(it, TR_S_OUT) - at(it, TR_S_WAITED);
+        sum[5] += at(it, TR_U_IN) - at(it, TR_S_OUT);
+        sum[6] += at(it, TR_U_WAITED) - at(it, TR_U_IN);
+        sum[7] += at(it, TR_U_OUT) - at(it, TR_U_WAITED);
+        sum[8] += at(it + 1, TR_P_IN) - at(it, TR_U_OUT);
+      }
+      double tot = 0;
+      for (double v : sum) tot += v;
+      fprintf(stderr, "[cg trace rank %d] %.1f us/iteration over iterations %d..%d:", H ? H->me : 0, tot / (hi - lo) * 1e-3, lo, hi);
+      for (int k = 0; k < 9; ++k) fprintf(stderr, " %s %.1f;", names[k], sum[k] / (hi - lo) * 1e-3);
+      fprintf(stderr, "\n");
+    }
+  }
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
   if (exec) cudaGraphExecDestroy(exec);

@@ -199,17 +199,23 @@ int iife_halo_p2p_attach(iife_halo H_, const void *all_handles, const int64_t *d
     std::vector<int> brow, bptr;
     std::vector<unsigned char> bpeer(ent.size());
     std::vector<long long> bdst(ent.size());
-    std::vector<unsigned int> bmask((size_t)(H->n_owned + 31) / 32 + 1, 0u);
+    // per 32 owned rows: (bit mask of the boundary rows, number of boundary rows before the word) -> index into bptr by
+    // one popcount, no search
+    std::vector<unsigned int> bmask(2 * ((size_t)(H->n_owned + 31) / 32 + 1), 0u);
     for (size_t k = 0; k < ent.size(); ++k) {
       if (k == 0 || ent[k].row != ent[k - 1].row) {
         brow.push_back(ent[k].row);
         bptr.push_back((int)k);
-        bmask[(size_t)ent[k].row >> 5] |= 1u << (ent[k].row & 31);
+        bmask[2 * ((size_t)ent[k].row >> 5)] |= 1u << (ent[k].row & 31);
       }
       bpeer[k] = ent[k].peer;
       bdst[k] = ent[k].dst;
     }
     bptr.push_back((int)ent.size());
+    for (size_t w = 0, before = 0; 2 * w < bmask.size(); ++w) {
+      bmask[2 * w + 1] = (unsigned int)before;
+      before += (size_t)__builtin_popcount(bmask[2 * w]);
+    }
     H->n_brow = (int)brow.size();
     IIFE_CUDA(cudaMalloc((void **)&H->brow, (brow.size() + 1) * sizeof(int)));
     IIFE_CUDA(cudaMalloc((void **)&H->bptr, bptr.size() * sizeof(int)));

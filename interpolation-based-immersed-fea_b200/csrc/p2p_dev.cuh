@@ -22,7 +22,20 @@ struct P2PRed {
   int *err;
   int k_off;                     // iteration index inside a graph-captured chunk (the counter moves once per chunk)
   int ll;                        // 1: low-latency packed words (Mailbox::it_ll) instead of values + fence + flag
+  unsigned long long *trace;     // IIFE_CG_TRACE: [CG_TRACE_ITERS][CG_TRACE_SLOTS] globaltimer stamps (nullptr: off)
 };
+
+// development aid (IIFE_CG_TRACE=1): where the time of a row-partitioned CG iteration goes, in globaltimer nanoseconds
+constexpr int CG_TRACE_ITERS = 1024, CG_TRACE_SLOTS = 12;
+enum { TR_P_IN = 0, TR_P_WAITED, TR_P_OUT, TR_S_IN, TR_S_WAITED, TR_S_OUT, TR_U_IN, TR_U_WAITED, TR_U_OUT };
+__device__ __forceinline__ void cg_trace(const P2PRed &r, int slot) {
+  if (r.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long it_rel = *r.iter + (unsigned long long)r.k_off - r.iter[1];
+    r.trace[(it_rel % CG_TRACE_ITERS) * CG_TRACE_SLOTS + slot] = t;
+  }
+}
 
 // SpMV prologue of the three-kernel CG iteration: wait until the ghost entries of exchange *seq_base + k_off + 1 arrived
 struct HaloWait {

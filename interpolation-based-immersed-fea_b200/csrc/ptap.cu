@@ -55,8 +55,9 @@ static const Level SYM_LEVELS[4] = {{1, 256, 10, 8}, {1, 128, 12, 10}, {0, 256, 
 static const Level NUM_LEVELS[5] = {{1, 256, 8, 6}, {1, 128, 10, 8}, {0, 128, 11, 10}, {0, 256, 13, 12}, {0, 256, 0, 0}};
 constexpr int N_SYM_LEVELS = 4;
 constexpr int N_NUM_LEVELS = 5;
-constexpr int N_BINS = 7;  // numeric bins: 0..4 hashing levels, 5..6 slot-plan rows (ptap_slots.cuh)
-constexpr int SLOT_CAP1[2] = {128, 256}, SLOT_CAP2[2] = {32, 256};
+constexpr int N_BINS = 8;  // numeric bins: 0..4 hashing levels, 5..7 slot-plan rows (ptap_slots.cuh); 7 = wide rows, 2-byte slots
+constexpr int N_SLOT_BINS = 3;
+constexpr int SLOT_CAP1[N_SLOT_BINS] = {128, 256, 2040}, SLOT_CAP2[N_SLOT_BINS] = {32, 256, 512};
 
 struct Plan {
   uint64_t fpM = 0, fpA = 0, fpR = 0;
@@ -82,6 +83,7 @@ struct Plan {
   int logG1 = 4, logG2 = 2;
   // global-memory tables of the last numeric level
   int g_log_cap1 = 0, g_log_cap2 = 0, g_ctas = 0;
+  int wide_cap1 = 0, wide_cap2 = 0;  // accumulator sizes of bin 7 (longest intermediate / output row in it)
   int *g_keys = nullptr;
   double *g_vals = nullptr;
   size_t g_keys_n = 0, g_vals_n = 0;
@@ -360,10 +362,10 @@ __device__ __forceinline__ int rank_sorted(const int *a, int n, int key) {
 }
 
 // For the items (row ids in `ik`, n_items of them) of operand X, write for every entry the rank of its
-// column in the sorted key list `keys[0..nk)` as one byte at out[running offset].  One warp.
+// column in the sorted key list `keys[0..nk)` as one byte (two for wide rows) at out[running offset].  One warp.
 __device__ __forceinline__ void warp_emit_slots(int n_items, const int *ik, const int *__restrict__ x_rowptr,
                                                 const int *__restrict__ x_col, int logG, const int *keys, int nk,
-                                                unsigned char *out, int lane) {
+                                                unsigned char *out, int lane, bool wide) {
   const int G = 1 << logG, NG = 32 >> logG;
   const int g = lane >> logG, lg = lane & (G - 1);
   long long base_off = 0;
@@ -385,7 +387,11 @@ __device__ __forceinline__ void warp_emit_slots(int n_items, const int *ik, cons
       int l = __shfl_sync(0xffffffffu, len, src);
       int o = __shfl_sync(0xffffffffu, off, src);
       if (it < cnt)
-        for (int e = lg; e < l; e += G) out[base_off + o + e] = (unsigned char)rank_sorted(keys, nk, __ldg(x_col + b + e));
+        for (int e = lg; e < l; e += G) {
+          const int rk = rank_sorted(keys, nk, __ldg(x_col + b + e));
+          if (wide) ((unsigned short *)out)[base_off + o + e] = (unsigned short)rk;  // rows of bin 7: two bytes per term
+          else out[base_off + o + e] = (unsigned char)rk;
+        }
     }
     base_off += total;
   }
@@ -465,7 +471,7 @@ __global__ void k_ptap_symbolic(PtapArgs a) {
       team_bitonic<true>(rt.h1k, P1, 32, t);
       const int ib = a.inter_rowptr[i];
       for (int s = t; s < n1; s += 32) a.inter_col[ib + s] = rt.h1k[s];
-      warp_emit_slots(mt_n, a.mt_col + mt_b, a.a_rowptr, a.a_col, a.logG1, rt.h1k, n1, a.slot1 + a.s1_off[i], t);
+      warp_emit_slots(mt_n, a.mt_col + mt_b, a.a_rowptr, a.a_col, a.logG1, rt.h1k, n1, a.slot1 + a.s1_off[i], t, a.slot_row[i] == 2);
       __syncwarp();
     }
     if (!ovf) {
@@ -509,7 +515,7 @@ __global__ void k_ptap_symbolic(PtapArgs a) {
           for (int s = t; s < n2; s += T) a.c_col[cb + s] = rt.h2k[s];
           if (slot_fill) {
             team_sync<WARP>();
-            warp_emit_slots(n1, rt.h1k, a.m_rowptr, a.m_col, a.logG2, rt.h2k, n2, a.slot2 + a.s2_off[i], t);
+            warp_emit_slots(n1, rt.h1k, a.m_rowptr, a.m_col, a.logG2, rt.h2k, n2, a.slot2 + a.s2_off[i], t, a.slot_row[i] == 2);
           }
         }
       }
@@ -586,25 +592,27 @@ __global__ void k_fill_schar(signed char *p, int64_t n, signed char v) {
   for (; i < n; i += stride) p[i] = v;
 }
 
-// numeric level of each row from the exact counts; -1 for empty output rows
-// rows that get a slot plan: resolved by a warp-team symbolic level, both rows <= 256 entries.
-// Non-slot rows get zero sizes so that the plan arrays only hold slot rows.
+// rows that get a slot plan: resolved by a warp-team symbolic level; 1 = both rows <= 256 entries (one byte per
+// product term), 2 = wide rows (intermediate row <= 2040, output row <= 512 entries: two bytes per term).  The byte
+// counts e1 / e2 of a row are rounded up to even so that every row's plan starts 2-byte aligned.  Non-slot rows get zero
+// sizes so that the plan arrays only hold slot rows.
 __global__ void k_slot_rows(const int *__restrict__ n1, const int *__restrict__ n2, const signed char *__restrict__ level,
-                            int64_t n, int enable, unsigned char *__restrict__ slot_row, int *__restrict__ e1,
-                            int *__restrict__ e2, int *__restrict__ n1m) {
+                            int64_t n, int enable, unsigned char *__restrict__ slot_row, const int *__restrict__ t1,
+                            const int *__restrict__ t2, int *__restrict__ e1, int *__restrict__ e2, int *__restrict__ n1m) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    bool s = enable && level[i] >= 0 && level[i] <= 1 && n2[i] > 0 && n1[i] <= 256 && n2[i] <= 256;
-    slot_row[i] = s ? 1 : 0;
-    if (!s) {
-      e1[i] = 0;
-      e2[i] = 0;
-    }
-    n1m[i] = s ? n1[i] : 0;
+  for (; i < n; i += stride) {  // t1 / t2: product terms of the two stages (count pass), e1 / e2: bytes of the plan
+    const bool warp_row = level[i] >= 0 && level[i] <= 1 && n2[i] > 0;
+    const bool s = (enable & 1) && warp_row && n1[i] <= 256 && n2[i] <= 256;
+    const bool wide = (enable & 2) && warp_row && !s && n1[i] <= 2040 && n2[i] <= 512 && t1[i] < (1 << 29) && t2[i] < (1 << 29);
+    slot_row[i] = s ? 1 : (wide ? 2 : 0);
+    e1[i] = s ? ((t1[i] + 1) & ~1) : (wide ? 2 * t1[i] : 0);
+    e2[i] = s ? ((t2[i] + 1) & ~1) : (wide ? 2 * t2[i] : 0);
+    n1m[i] = (s || wide) ? n1[i] : 0;
   }
 }
 
+// numeric level of each row from the exact counts; -1 for empty output rows
 __global__ void k_numeric_level(const int *__restrict__ n1, const int *__restrict__ n2, int64_t n,
                                 signed char *__restrict__ lvl, int c10, int c20, int c11, int c21, int c12, int c22,
                                 int c13, int c23, const unsigned char *__restrict__ slot_row) {
@@ -614,6 +622,7 @@ __global__ void k_numeric_level(const int *__restrict__ n1, const int *__restric
     int a = n1[i], b = n2[i];
     signed char l;
     if (b == 0) l = -1;
+    else if (slot_row && slot_row[i] == 2) l = 7;
     else if (slot_row && slot_row[i]) l = (a <= 128 && b <= 32) ? 5 : 6;
     else if (2 * a <= c10 && 2 * b <= c20) l = 0;
     else if (2 * a <= c11 && 2 * b <= c21) l = 1;
@@ -1013,24 +1022,30 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
 
     // ---- slot plan sizes (ptap_slots.cuh): which rows, offsets of their product terms
     {
-      static const bool slots_on = !(getenv("IIFE_PTAP_SLOTS") && atoi(getenv("IIFE_PTAP_SLOTS")) == 0);
-      if (n_b) IIFE_LAUNCH(k_slot_rows, grid_for(n_b), 256, 0, P->n1, n2.p, level.p, n_b, slots_on ? 1 : 0, slot_row.p, e1.p, e2.p, n1m.p);
+      const bool slots_on = !(getenv("IIFE_PTAP_SLOTS") && atoi(getenv("IIFE_PTAP_SLOTS")) == 0);
+      const bool wide_on = !(getenv("IIFE_PTAP_SLOTS_WIDE") && atoi(getenv("IIFE_PTAP_SLOTS_WIDE")) == 0);
       if ((rc = dev_alloc_t(&P->s1_off, (size_t)n_b + 1)) != IIFE_OK) break;
       if ((rc = dev_alloc_t(&P->s2_off, (size_t)n_b + 1)) != IIFE_OK) break;
       if ((rc = dev_alloc_t(&P->inter_rowptr, (size_t)n_b + 1)) != IIFE_OK) break;
-      if ((rc = exclusive_scan_i32_i64(e1.p, P->s1_off, n_b, &P->s1_total)) != IIFE_OK) break;
-      if ((rc = exclusive_scan_i32_i64(e2.p, P->s2_off, n_b, &P->s2_total)) != IIFE_OK) break;
+      Tmp<int> b1, b2;  // bytes of the plan per row (e1 / e2 keep the term counts of the count pass)
+      if ((rc = b1.alloc((size_t)n_b + 1)) != IIFE_OK) break;
+      if ((rc = b2.alloc((size_t)n_b + 1)) != IIFE_OK) break;
       int64_t it_total = 0;
-      rc = exclusive_scan_i32(n1m.p, P->inter_rowptr, n_b, &it_total);
-      size_t free_b = 0, total_b = 0;
-      cudaMemGetInfo(&free_b, &total_b);
-      int64_t need = P->s1_total + P->s2_total + 4 * it_total;
-      if (rc == IIFE_ERR_UNSUPPORTED || (rc == IIFE_OK && need > (int64_t)(free_b / 2))) {
-        // plan would not fit (int32 pattern offsets or memory): fall back to the hashing kernels
-        if (n_b) IIFE_LAUNCH(k_slot_rows, grid_for(n_b), 256, 0, P->n1, n2.p, level.p, n_b, 0, slot_row.p, e1.p, e2.p, n1m.p);
-        if ((rc = exclusive_scan_i32_i64(e1.p, P->s1_off, n_b, &P->s1_total)) != IIFE_OK) break;
-        if ((rc = exclusive_scan_i32_i64(e2.p, P->s2_off, n_b, &P->s2_total)) != IIFE_OK) break;
-        if ((rc = exclusive_scan_i32(n1m.p, P->inter_rowptr, n_b, &it_total)) != IIFE_OK) break;
+      // narrow + wide rows, then narrow rows only, then none (hashing kernels): whatever fits (int32 pattern offsets, memory)
+      const int modes[3] = {slots_on ? (wide_on ? 3 : 1) : 0, slots_on ? 1 : 0, 0};
+      for (int attempt = 0; attempt < 3; ++attempt) {
+        if (attempt > 0 && modes[attempt] == modes[attempt - 1]) continue;
+        if (n_b) IIFE_LAUNCH(k_slot_rows, grid_for(n_b), 256, 0, P->n1, n2.p, level.p, n_b, modes[attempt], slot_row.p, e1.p, e2.p, b1.p, b2.p, n1m.p);
+        if ((rc = exclusive_scan_i32_i64(b1.p, P->s1_off, n_b, &P->s1_total)) != IIFE_OK) break;
+        if ((rc = exclusive_scan_i32_i64(b2.p, P->s2_off, n_b, &P->s2_total)) != IIFE_OK) break;
+        rc = exclusive_scan_i32(n1m.p, P->inter_rowptr, n_b, &it_total);
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const int64_t need = P->s1_total + P->s2_total + 4 * it_total;
+        const bool fits = rc == IIFE_OK && need <= (int64_t)(free_b / 2);
+        if (rc != IIFE_OK && rc != IIFE_ERR_UNSUPPORTED) break;
+        if (fits || modes[attempt] == 0) break;
+        rc = IIFE_OK;
       }
       if (rc != IIFE_OK) break;
       P->inter_total = it_total;
@@ -1110,6 +1125,23 @@ static int ptap_symbolic_impl(Mat *R, Mat *M, Mat *A, Plan **out) {
       P->bin_off[l + 1] = P->bin_off[l] + cnt;
     }
     if (rc != IIFE_OK) break;
+    // accumulator sizes of the wide slot-plan rows: the longest rows of the bin, not the bin's limits
+    {
+      const int64_t n_wide = P->bin_off[N_NUM_LEVELS + 3] - P->bin_off[N_NUM_LEVELS + 2];
+      P->wide_cap1 = SLOT_CAP1[2];
+      P->wide_cap2 = SLOT_CAP2[2];
+      if (n_wide > 0) {
+        const int *rows = P->bin_rows + P->bin_off[N_NUM_LEVELS + 2];
+        int m1 = 0, m2 = 0;
+        cudaMemsetAsync(n_ovf.p, 0, 2 * sizeof(int), c.stream);
+        IIFE_LAUNCH(k_list_max, grid_for(n_wide), 256, 0, P->n1, rows, n_wide, n_ovf.p);
+        IIFE_LAUNCH(k_list_max, grid_for(n_wide), 256, 0, n2.p, rows, n_wide, n_ovf.p + 1);
+        if ((rc = read_int(n_ovf.p, &m1)) != IIFE_OK) break;
+        if ((rc = read_int(n_ovf.p + 1, &m2)) != IIFE_OK) break;
+        P->wide_cap1 = std::min(SLOT_CAP1[2], (m1 + 7) & ~7);
+        P->wide_cap2 = std::min(SLOT_CAP2[2], (m2 + 7) & ~7);
+      }
+    }
     // global tables of the last numeric level
     int64_t n_last = P->bin_off[N_NUM_LEVELS] - P->bin_off[N_NUM_LEVELS - 1];  // bin 4 = global-memory tables
     if (n_last > 0) {
@@ -1550,11 +1582,12 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
         pg_free(P);
       }
     }
-    for (int sb = 0; sb < 2; ++sb) {  // slot-plan rows (ptap_slots.cuh)
+    for (int sb = 0; sb < N_SLOT_BINS; ++sb) {  // slot-plan rows (ptap_slots.cuh)
       int l = N_NUM_LEVELS + sb;
+      const bool wide = sb == 2;
       int64_t cnt = P->bin_off[l + 1] - P->bin_off[l];
       a.rows = P->bin_rows + P->bin_off[l];
-      if (use_tpl) {  // what the templates did not take
+      if (use_tpl && !wide) {  // what the templates did not take
         cnt = sb == 0 ? P->tp_rest5 : P->tp_rest6;
         a.rows = P->tp_rest_rows + (sb == 0 ? 0 : P->tp_rest5);
       }
@@ -1564,6 +1597,10 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
       int lg2 = a.logG2 < 2 ? 2 : (a.logG2 > 5 ? 5 : a.logG2);
       if (const char *e1v = getenv("IIFE_PTAP_LG1")) lg1 = atoi(e1v);
       if (const char *e2v = getenv("IIFE_PTAP_LG2")) lg2 = atoi(e2v);
+      if (wide) {
+        lg1 = lg1 < 4 ? 4 : lg1;
+        lg2 = lg2 < 3 ? 3 : lg2;
+      }
       if (sb == 0) {  // stage 2 as a per-row gather program (ptap_prog.cuh): small-row bin only, while it fits in memory
         const char *e3 = getenv("IIFE_PTAP_PROG");
         if ((!e3 || atoi(e3) != 0) && SLOT_CAP2[0] <= 32 && SLOT_CAP1[0] < PROG_IDLE) {
@@ -1598,9 +1635,9 @@ static int ptap_numeric_impl(Plan *P, Mat *R, Mat *M, Mat *A, Mat **C_io) {
           }
         }
       }
-      slot_kernel_t kern = pick_slot_kernel(lg1, lg2);
+      slot_kernel_t kern = pick_slot_kernel(lg1, lg2, wide);
       if (!kern) { rc = set_err(IIFE_ERR_ARG, "no slot kernel for group sizes 2^%d / 2^%d", lg1, lg2); break; }
-      int cap1 = SLOT_CAP1[sb], cap2 = SLOT_CAP2[sb];
+      int cap1 = wide ? P->wide_cap1 : SLOT_CAP1[sb], cap2 = wide ? P->wide_cap2 : SLOT_CAP2[sb];
       size_t per_warp = slot_per_warp_bytes(lg1, lg2, cap1, cap2);
       size_t smem_max = (size_t)(c.max_smem_optin ? c.max_smem_optin : 227 * 1024);
       int wpc = 8;
@@ -1779,10 +1816,12 @@ int iife_rap_numeric(iife_plan plan_, iife_mat R_, iife_mat A_, iife_mat P_, iif
   return IIFE_OK;
 }
 
-int iife_plan_bin_counts(iife_plan P_, int64_t *counts7) {
+int iife_plan_bin_counts(iife_plan P_, int64_t *counts7) { return iife_plan_bin_counts_n(P_, counts7, 7); }
+
+int iife_plan_bin_counts_n(iife_plan P_, int64_t *counts, int n) {
   Plan *P = (Plan *)P_;
-  if (!P || !counts7) return set_err(IIFE_ERR_ARG, "NULL argument");
-  for (int l = 0; l < N_BINS; ++l) counts7[l] = P->bin_off[l + 1] - P->bin_off[l];
+  if (!P || !counts || n < 0) return set_err(IIFE_ERR_ARG, "NULL argument");
+  for (int l = 0; l < n; ++l) counts[l] = l < N_BINS ? P->bin_off[l + 1] - P->bin_off[l] : 0;
   return IIFE_OK;
 }
 

@@ -14,8 +14,9 @@
 // convergence barriers and shuffles; this kernel executes a fraction of that.
 //
 // Layout per warp in shared memory: h1v[NG1][cap1] then h2v[NG2][cap2] (fp64), NG = 32 / lanes-per-row.
-// Rows qualify when both the intermediate and the output row have <= 256 entries (slot bytes);
-// everything else stays on the hashing kernels of ptap.cu / ptap_warp.cuh.
+// Rows qualify when both the intermediate and the output row have <= 256 entries (slot bytes), or, with two bytes per
+// term, <= 2040 / <= 512 entries (the wide rows of quadratic and 3-D unfitted backgrounds); everything else stays on the
+// hashing kernels of ptap.cu / ptap_warp.cuh.
 //
 // Kernel notes (second version, measured in round 2: 24.0 -> 18.9 ms at N_b=184 against the first one, which is gone):
 //   * the 32 item descriptors of a chunk {w, beg, off, len} are staged once in shared memory (16 B each) and
@@ -53,9 +54,9 @@ struct __align__(16) SlotDesc {
   unsigned offlen;  // off (low 16 bits: <= 32 * 256) | len << 16 (<= 256)
 };
 
-template <int LG>
+template <int LG, class ST>
 __device__ __forceinline__ void slot_stage2(int my_beg, int my_len, double my_w, int my_off,
-                                            const double *__restrict__ x_val, const unsigned char *__restrict__ slots,
+                                            const double *__restrict__ x_val, const ST *__restrict__ slots,
                                             double *hv, int stride, int lane, SlotDesc *desc, unsigned char *tail_src) {
   constexpr int G = 1 << LG, NG = 32 >> LG;
   const int g = lane >> LG, lg = lane & (G - 1);
@@ -127,7 +128,8 @@ __device__ __forceinline__ void slot_stage2(int my_beg, int my_len, double my_w,
   __syncwarp();  // descriptors and tail_src are rewritten by the next chunk
 }
 
-template <int LG1, int LG2>
+// ST = unsigned char: rows of bins 5 / 6 (both rows <= 256 entries); unsigned short: the wide rows of bin 7
+template <int LG1, int LG2, class ST>
 __global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots(PtapArgs a, int cap1, int cap2) {
   constexpr int NG1 = 32 >> LG1, NG2 = 32 >> LG2;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -152,8 +154,8 @@ __global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots(PtapArgs a, int cap1, int 
     const int mt_b = __ldg(a.mt_rowptr + i), mt_n = __ldg(a.mt_rowptr + i + 1) - mt_b;
     const int cb = __ldg(a.c_rowptr + i), n2 = __ldg(a.c_rowptr + i + 1) - cb;
     const int ib = __ldg(a.inter_rowptr + i), n1 = __ldg(a.inter_rowptr + i + 1) - ib;
-    const unsigned char *s1 = a.slot1 + a.s1_off[i];
-    const unsigned char *s2 = a.slot2 + a.s2_off[i];
+    const ST *s1 = (const ST *)(a.slot1 + a.s1_off[i]);
+    const ST *s2 = (const ST *)(a.slot2 + a.s2_off[i]);
     // ---- clear the accumulators: one contiguous range (h1v and h2v are adjacent), 16-byte stores
     {
       double2 *z = (double2 *)h1v;
@@ -182,7 +184,7 @@ __global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots(PtapArgs a, int cap1, int 
         }
         int total;
         const int my_off = warp_excl_scan(my_len, lane, &total);
-        slot_stage2<LG1>(my_beg, my_len, my_w, my_off, a_val, s1 + base_off, h1v, st1, lane, desc, tail_src);
+        slot_stage2<LG1, ST>(my_beg, my_len, my_w, my_off, a_val, s1 + base_off, h1v, st1, lane, desc, tail_src);
         base_off += total;
       }
     }
@@ -214,7 +216,7 @@ __global__ void IIFE_SLOT_BOUNDS k_ptap_numeric_slots(PtapArgs a, int cap1, int 
         }
         int total;
         const int my_off = warp_excl_scan(my_len, lane, &total);
-        slot_stage2<LG2>(my_beg, my_len, my_w, my_off, m_val, s2 + base_off, h2v, st2, lane, desc, tail_src);
+        slot_stage2<LG2, ST>(my_beg, my_len, my_w, my_off, m_val, s2 + base_off, h2v, st2, lane, desc, tail_src);
         base_off += total;
       }
     }
@@ -234,9 +236,16 @@ static size_t slot_per_warp_bytes(int lg1, int lg2, int cap1, int cap2) {
   return PS2_DESC_BYTES + acc * 8 + SLOT_TAIL_BYTES;
 }
 
-static slot_kernel_t pick_slot_kernel(int lg1, int lg2) {
+static slot_kernel_t pick_slot_kernel(int lg1, int lg2, bool wide = false) {
+  if (wide) {  // at most two copies of the 2040-entry intermediate row and four of the 512-entry output row
+#define PSKW(a_, b_) \
+  if (lg1 == a_ && lg2 == b_) return k_ptap_numeric_slots<a_, b_, unsigned short>;
+    PSKW(4, 3) PSKW(4, 4) PSKW(4, 5) PSKW(5, 3) PSKW(5, 4) PSKW(5, 5)
+#undef PSKW
+    return nullptr;
+  }
 #define PSK2(a_, b_) \
-  if (lg1 == a_ && lg2 == b_) return k_ptap_numeric_slots<a_, b_>;
+  if (lg1 == a_ && lg2 == b_) return k_ptap_numeric_slots<a_, b_, unsigned char>;
   PSK2(3, 2) PSK2(3, 3) PSK2(3, 4) PSK2(3, 5)
   PSK2(4, 2) PSK2(4, 3) PSK2(4, 4) PSK2(4, 5)
   PSK2(5, 2) PSK2(5, 3) PSK2(5, 4) PSK2(5, 5)

@@ -503,10 +503,12 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr,
   if (flag && *flag != 0) return;  // converged: the rest of the enqueued chunk is a row of no-ops
   __shared__ double red[32];
   __shared__ bool is_last;
+  if (hw.flags && blockIdx.x == 0 && threadIdx.x == 0) cg_trace(pr, TR_S_IN);
   if (!IFIRST && hw.flags) {  // three-kernel CG iteration: the neighbours' k_cg_p_push stores the ghost entries of x
     const int q = threadIdx.x;
     if (q < hw.nranks && ((hw.recv_mask >> q) & 1u)) spin_until(hw.flags + q, *hw.seq_base + (unsigned long long)hw.k_off + 1ull, hw.err);
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) cg_trace(pr, TR_S_WAITED);
   }
   const int lane = threadIdx.x & 31;
   const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -541,6 +543,7 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr,
       if (lane < hw.nranks && ((hw.recv_mask >> lane) & 1u))
         spin_until(hw.flags + lane, *hw.seq_base + (unsigned long long)hw.k_off + 1ull, hw.err);
       __syncwarp();
+      if (b0 == 0 && lane == 0) cg_trace(pr, TR_S_WAITED);
       for (int64_t b = b0; b < n_bnd; b += nw) {
         const int64_t s = b < hw.int_lo ? b : b + hw.n_int;
         const double acc = sell_slice<U, true>(sell_ptr, sell_cptr, sell_col, sell_val, x, s, lane, n_rows);
@@ -576,6 +579,7 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr,
       if (pr.enabled) {  // row-partitioned solver: hand the partial to every rank (no wait here)
         __syncthreads();
         p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 1ull, &s_sum, 1, threadIdx.x);
+        if (hw.flags && threadIdx.x == 0) cg_trace(pr, TR_S_OUT);
       }
     }
   }

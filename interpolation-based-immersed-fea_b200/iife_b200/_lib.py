@@ -53,6 +53,7 @@ PROTOTYPES = {
     "iife_rap_symbolic": (c_int, [c_vp, c_vp, c_vp, P(c_vp)]),
     "iife_rap_numeric": (c_int, [c_vp, c_vp, c_vp, c_vp, P(c_vp)]),
     "iife_plan_bin_counts": (c_int, [c_vp, P(c_i64)]),
+    "iife_plan_bin_counts_n": (c_int, [c_vp, P(c_i64), c_int]),
     "iife_plan_check": (c_int, [c_vp]),
     "iife_plan_tpl_info": (c_int, [c_vp, P(c_i64), P(c_i64), P(c_i64), c_vp]),
     "iife_tpl_emulate_row": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),

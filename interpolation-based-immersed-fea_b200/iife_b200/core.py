@@ -279,8 +279,8 @@ class PtapPlan:
 
     def bin_counts(self):
         """rows handled by each numeric kernel (see include/iife.h: iife_plan_bin_counts)"""
-        c = (ctypes.c_int64 * 7)()
-        check(lib.iife_plan_bin_counts(self._h, c))
+        c = (ctypes.c_int64 * 8)()
+        check(lib.iife_plan_bin_counts_n(self._h, c, 8))
         return list(c)
 
     def tpl_info(self):

@@ -302,6 +302,18 @@ class DistExtraction:
         self.C_op = None       # same values, local [owned | ghost] column ids (KSP operator)
         self.halo = None
         self.n_owned = T.R[0]
+        # the pattern of this rank's rows of A_f as handed over (numeric_csr checks a fresh matrix against it)
+        self._A_pattern = (A_loc[0].to(torch.int32, copy=True), A_loc[1].to(torch.int32, copy=True))
+
+    def numeric_csr(self, rowptr, colind, values):
+        """A freshly assembled local block of A_f (device CSR arrays: the reference builds a new matrix per
+        ``assemble``, common.py:432-435): the pattern must be the one this object was set up with (compared on the
+        device, one pass over the index arrays); then :meth:`numeric`.  Raises ValueError on a different pattern."""
+        rp0, ci0 = self._A_pattern
+        if (rowptr.numel() != rp0.numel() or colind.numel() != ci0.numel()
+                or not bool(torch.equal(rowptr.to(torch.int32), rp0)) or not bool(torch.equal(colind.to(torch.int32), ci0))):
+            raise ValueError("the pattern of A_f changed: set up a new DistExtraction")
+        return self.numeric(values)
 
     def numeric(self, A_val_local):
         """New foreground values (same pattern): exchange ghost-row values, run the numeric phase."""

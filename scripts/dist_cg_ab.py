@@ -90,7 +90,7 @@ for item in [e for e in extra.split(";") if e]:
     k, v = item.split("=")
     variants.append((f"default + {item}", {"IIFE_CG_INTERIOR_FIRST": "1", "IIFE_P2P_LL": "1", k: v}))
 ref = None
-for rep in range(2):
+for rep in range(int(os.environ.get("AB_REPS", "2"))):
     for name, env in variants:
         saved = {k: os.environ.get(k) for k in env}
         os.environ.update(env)

@@ -39,7 +39,16 @@ def block(t, r0, r1):
 
 ex = idist.DistExtraction(n_f, n_b, block(g["M"], f0, f1), block(g["A"], f0, f1))
 A_loc_vals = torch.from_numpy(g["A"][2][int(g["A"][0][f0]):int(g["A"][0][f1])].copy()).to(dev)
-C = ex.numeric(A_loc_vals)
+A_blk = block(g["A"], f0, f1)
+C = ex.numeric_csr(A_blk[0], A_blk[1], A_loc_vals)  # a freshly assembled block: pattern checked, then numeric
+try:
+    bad = A_blk[1].clone()
+    if bad.numel():
+        bad[0] = (bad[0] + 1) % n_f
+    ex.numeric_csr(A_blk[0], bad, A_loc_vals)
+    raise AssertionError("numeric_csr accepted a different pattern")
+except ValueError:
+    pass
 rp, ci, v = C.to_csr(np.int64)
 # single-GPU reference on every rank (small problem)
 dM = I.DeviceMat.from_csr(n_f, n_b, *g["M"])

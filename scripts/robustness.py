@@ -132,28 +132,29 @@ def run_case(name, A, M, n_f, n_b, b_f):
 
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 184
-sz = synthetic.cube_sizes(N)
-n_f, n_b = sz["n_f"], sz["n_b"]
-b_f = torch.empty(n_f, dtype=torch.float64, device=dev)
-A, M = I.synth_cube(N, 1.0, b_f=b_f)
-I.sync()
-run_case(f"S1 N_b={N}", A, M, n_f, n_b, b_f)
-g = torch.Generator(device=dev)
-g.manual_seed(1)
-pb = torch.randperm(n_b, device=dev, generator=g)
-M2 = permute(M, n_b, col_perm=pb)
-run_case(f"S1 N_b={N}, background shuffled", A, M2, n_f, n_b, b_f)
-del M2
-pf = torch.randperm(n_f, device=dev, generator=g)
-M3 = permute(M, n_b, row_perm=pf, col_perm=pb)
-del M
-A3 = permute(A, n_f, row_perm=pf, col_perm=pf)
-del A
-bf3 = torch.empty_like(b_f)
-bf3[pf] = b_f
-run_case(f"S1 N_b={N}, background and foreground shuffled", A3, M3, n_f, n_b, bf3)
-del A3, M3, bf3, pf, pb, b_f
-torch.cuda.empty_cache()
+if not os.environ.get("ROBUST_ONLY_S2"):  # development: only the unfitted cases
+    sz = synthetic.cube_sizes(N)
+    n_f, n_b = sz["n_f"], sz["n_b"]
+    b_f = torch.empty(n_f, dtype=torch.float64, device=dev)
+    A, M = I.synth_cube(N, 1.0, b_f=b_f)
+    I.sync()
+    run_case(f"S1 N_b={N}", A, M, n_f, n_b, b_f)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    pb = torch.randperm(n_b, device=dev, generator=g)
+    M2 = permute(M, n_b, col_perm=pb)
+    run_case(f"S1 N_b={N}, background shuffled", A, M2, n_f, n_b, b_f)
+    del M2
+    pf = torch.randperm(n_f, device=dev, generator=g)
+    M3 = permute(M, n_b, row_perm=pf, col_perm=pb)
+    del M
+    A3 = permute(A, n_f, row_perm=pf, col_perm=pf)
+    del A
+    bf3 = torch.empty_like(b_f)
+    bf3[pf] = b_f
+    run_case(f"S1 N_b={N}, background and foreground shuffled", A3, M3, n_f, n_b, bf3)
+    del A3, M3, bf3, pf, pb, b_f
+    torch.cuda.empty_cache()
 for spec, deg in ((int(sys.argv[2]) if len(sys.argv) > 2 else 171, 1), (int(sys.argv[3]) if len(sys.argv) > 3 else 128, 2)):
     gg = synthetic.unfitted_operators(spec, deg)
     A = I.DeviceMat.from_csr(gg["n_f"], gg["n_f"], *gg["A"])
@@ -165,7 +166,7 @@ for spec, deg in ((int(sys.argv[2]) if len(sys.argv) > 2 else 171, 1), (int(sys.
 print("# Robustness of the headline: the same phases on operators without the cube's regularity\n")
 print(f"`python scripts/robustness.py` on 1 x B200.  Fractions are algorithmic bytes (SURVEY.md §8d) over time over the measured "
       f"copy peak ({PEAK:.0f} GB/s).  CG: 200 iterations timed, tolerances disabled.\n")
-print("| case | n_f | n_b | nnz(A_f) | nnz(A_b) | nnz(M^T A_f) | symbolic ms | numeric PtAP ms | frac | template rows | bins [5 hashing, 2 slot] | "
+print("| case | n_f | n_b | nnz(A_f) | nnz(A_b) | nnz(M^T A_f) | symbolic ms | numeric PtAP ms | frac | template rows | bins [5 hashing, 3 slot-plan: 128/32, 256/256, wide] | "
       "SpMV(A_b) us | frac | CG us/it | frac | CG its to 1e-8 |")
 print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---|---|---:|---:|---:|---:|---|")
 for r in rows:

@@ -217,11 +217,15 @@ def test_ptap_random(iife, oracle, case):
     check_ptap(iife, oracle, M, A)
 
 
-def test_ptap_every_numeric_kernel_is_exercised(iife, oracle):
-    """Cases built to land rows in each bin of the numeric ladder (slot plans 128/32 and 256/256, warp and
-    CTA hashing levels, global-memory tables) — all against the oracle, and the plan reports the bins."""
+@pytest.mark.parametrize("wide_slots", [True, False])
+def test_ptap_every_numeric_kernel_is_exercised(iife, oracle, monkeypatch, wide_slots):
+    """Cases built to land rows in each bin of the numeric ladder (slot plans 128/32, 256/256 and the two-byte plan of
+    wide rows, warp and CTA hashing levels, global-memory tables) — all against the oracle, and the plan reports the
+    bins.  With IIFE_PTAP_SLOTS_WIDE=0 the wide rows go through the hashing kernels they used before."""
+    if not wide_slots:
+        monkeypatch.setenv("IIFE_PTAP_SLOTS_WIDE", "0")
     rng = np.random.default_rng(11)
-    seen = np.zeros(7, dtype=np.int64)
+    seen = np.zeros(8, dtype=np.int64)
 
     def one_entry_M(n_f, n_b):
         # every foreground row maps to exactly one background function: Mt rows have ~n_f/n_b entries
@@ -231,16 +235,21 @@ def test_ptap_every_numeric_kernel_is_exercised(iife, oracle):
     cases = [
         (ocsr(oracle, 1200, 400, rand_csr(rng, 1200, 400, 3, empty_frac=0.3)), ocsr(oracle, 1200, 1200, rand_csr(rng, 1200, 1200, 6))),   # slots 128/32-ish
         (ocsr(oracle, 800, 200, rand_csr(rng, 800, 200, 4)), ocsr(oracle, 800, 800, rand_csr(rng, 800, 800, 12))),                          # slots 256/256
-        (one_entry_M(3000, 100), ocsr(oracle, 3000, 3000, rand_csr(rng, 3000, 3000, 15))),                                                  # n1 ~ 450: warp hashing
+        (one_entry_M(3000, 100), ocsr(oracle, 3000, 3000, rand_csr(rng, 3000, 3000, 15))),                                                  # n1 ~ 450: wide slots / warp hashing
         (ocsr(oracle, 4000, 600, rand_csr(rng, 4000, 600, 2)), ocsr(oracle, 4000, 4000, rand_csr(rng, 4000, 4000, 50))),                     # CTA hashing
         (ocsr(oracle, 3000, 40, rand_csr(rng, 3000, 40, 8)), ocsr(oracle, 3000, 3000, rand_csr(rng, 3000, 3000, 20))),                       # fat rows
         (ocsr(oracle, 6000, 6, rand_csr(rng, 6000, 6, 2)), ocsr(oracle, 6000, 6000, rand_csr(rng, 6000, 6000, 30))),                         # global tables
+        (one_entry_M(6000, 300), ocsr(oracle, 6000, 6000, rand_csr(rng, 6000, 6000, 60))),                                                   # n1 ~ 1100, n2 <= 300: wide slots
     ]
     for M, A in cases:
         _, _, _, _, plan = check_ptap(iife, oracle, M, A)
         seen += np.array(plan.bin_counts())
-    assert seen[5] > 0 and seen[6] > 0, seen           # both slot-plan kernels
-    assert seen[1] + seen[2] + seen[3] > 0, seen        # shared-memory hashing levels
+    assert seen[5] > 0 and seen[6] > 0, seen           # both one-byte slot-plan kernels
+    if wide_slots:
+        assert seen[7] > 0, seen                        # two-byte slot plan of wide rows
+    else:
+        assert seen[7] == 0, seen
+        assert seen[1] + seen[2] + seen[3] > 0, seen    # shared-memory hashing levels
     assert seen[4] > 0, seen                            # global-memory tables
     print("rows per numeric kernel:", seen.tolist())
 
