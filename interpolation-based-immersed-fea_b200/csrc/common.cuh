@@ -59,30 +59,6 @@ const char *get_err();
 
 #define IIFE_CHECK_LAUNCH() IIFE_CUDA(cudaGetLastError())
 
-// Launch with programmatic stream serialisation (PDL) when `pdl` is set: the kernel may be scheduled while the previous
-// kernel of the stream is still draining; it MUST call pdl_wait() before it reads anything an earlier kernel wrote (all
-// CTAs, before any early exit), and the previous kernel releases it with pdl_launch() (or by finishing).  Only for
-// kernels written for it (the CG iteration: ksp.cu, k_spmv_sell).
-#define IIFE_LAUNCH_PDL(pdl, kernel, grid, block, smem, ...)                                             \
-  do {                                                                                                   \
-    if (pdl) {                                                                                           \
-      cudaLaunchConfig_t _cfg = {};                                                                      \
-      _cfg.gridDim = dim3((unsigned)(grid));                                                             \
-      _cfg.blockDim = dim3((unsigned)(block));                                                           \
-      _cfg.dynamicSmemBytes = (smem);                                                                    \
-      _cfg.stream = ::iife::ctx().stream;                                                                \
-      cudaLaunchAttribute _attr[1];                                                                      \
-      _attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                  \
-      _attr[0].val.programmaticStreamSerializationAllowed = 1;                                           \
-      _cfg.attrs = _attr;                                                                                \
-      _cfg.numAttrs = 1;                                                                                 \
-      cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                                                    \
-    } else {                                                                                             \
-      kernel<<<(grid), (block), (smem), ::iife::ctx().stream>>>(__VA_ARGS__);                            \
-    }                                                                                                    \
-    ::iife::ctx().launches++;                                                                            \
-  } while (0)
-
 // device allocation with accounting
 int dev_alloc(void **p, size_t bytes);
 int dev_free(void *p, size_t bytes);
@@ -170,7 +146,6 @@ int spmv_pick_lpr(const Mat *A);
 // padding would exceed 1.25x nnz, in which case callers stay on CSR) and refreshes values.
 int mat_ensure_sell(Mat *A);
 int mat_ensure_sell_order(Mat *A, int64_t n_owned);
-void spmv_set_pdl(bool on);  // the SpMV + dot launches that follow are part of a PDL chain (CG iteration)
 void mat_free_sell(Mat *A);
 
 // ghost-entry exchange plan of a row-partitioned operator (comm.cu)
@@ -230,8 +205,6 @@ static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); 
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

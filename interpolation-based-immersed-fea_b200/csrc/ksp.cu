@@ -172,7 +172,6 @@ __global__ void k_cg_init_scalars(double *sc, int *fl, double *hist, long long h
 __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_p(const double *__restrict__ r, const double *__restrict__ dinv, double *__restrict__ p, int64_t n,
        const double *__restrict__ sc, const int *__restrict__ fl) {
-  pdl_wait();
   if (fl[F_REASON] != 0) return;
   bool first = (fl[F_ITS] == 0);
   double bb = first ? 0.0 : sc[S_BETA] / sc[S_BETA_OLD];
@@ -196,7 +195,6 @@ k_cg_p(const double *__restrict__ r, const double *__restrict__ dinv, double *__
       if (i < n) p[i] = first ? z : fma(bb, pv[u], z);
     }
   }
-  pdl_launch();
 }
 
 // alpha = beta/delta; x += alpha p; r -= alpha w; z = D^-1 r; (z,r), (z,z) -> beta, dp, test(i+1)
@@ -210,7 +208,6 @@ __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
             const double *__restrict__ w, const double *__restrict__ dinv, int64_t n, double *sc, int *fl,
             double *partials, unsigned int *counter, double *hist, long long hist_len, P2PRed pr) {
-  pdl_wait();
   if (fl[F_REASON] != 0) return;
   __shared__ double red[32];
   __shared__ double out[2];
@@ -276,7 +273,6 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, const double *__rest
       }
     }
   }
-  pdl_launch();
   if (grid_reduce<2>(acc, partials, counter, out, red, &last)) {
     if (MODE == 2 || MODE == 3) {
       p2p_push(pr, 2ull * (*pr.iter + (unsigned long long)pr.k_off) + 2ull, out, 2, threadIdx.x);
@@ -317,56 +313,48 @@ __global__ void k_cg_scalars_p2p(double *sc, int *fl, double *hist, long long hi
 // of the solve) plus the iteration's index k inside the captured chunk; k_cg_chunk_end moves the counters once per chunk,
 // so no kernel reads a counter that another CTA of the same kernel writes.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VEC_THREADS)
-k_cg_p_push(const double *__restrict__ r, const double *__restrict__ dinv, double *__restrict__ p, int64_t n, double *sc,
-            int *fl, double *hist, long long hist_len, P2PRed pr, RowPush rp) {
-  pdl_wait();
-  if (fl[F_REASON] != 0) return;  // set by an earlier kernel (CTA 0 of THIS kernel can only reach the same verdict)
-  __shared__ double s_bb;
-  __shared__ int s_stop;
-  __shared__ bool last;
-  const unsigned long long git = *pr.iter + (unsigned long long)pr.k_off;
-  const unsigned long long it_rel = git - pr.iter[1];
-  const bool first = (it_rel == 0ull);
-  if (blockIdx.x == 0 && threadIdx.x == 0) cg_trace(pr, TR_P_IN);
-  if (!first) {
-    if (threadIdx.x < 32) {
-      double v[2];
-      p2p_wait_sum(pr, 2ull * (git - 1ull) + 2ull, v, 2);
-      if (threadIdx.x == 0) {
-        if (blockIdx.x == 0) cg_trace(pr, TR_P_WAITED);
-        // KSPSolve_CG after the update of iteration it_rel-1: beta_old <- beta, beta = (z, r), dp = ||z||, its, test
-        const double beta_old = sc[S_BETA2 + (int)((it_rel - 1ull) & 1ull)];
-        const double beta = v[0], dp = sqrt(v[1]);
-        const int its = (int)it_rel;
-        int reason = 0, its_out = its;
-        if (isnan(dp) || isinf(dp)) reason = IIFE_KSP_DIVERGED_NANORINF;
-        else if (dp <= sc[S_TTOL]) reason = (dp < sc[S_ATOL]) ? IIFE_KSP_CONVERGED_ATOL : IIFE_KSP_CONVERGED_RTOL;
-        else if (dp >= sc[S_DTOL] * sc[S_RHO0]) reason = IIFE_KSP_DIVERGED_DTOL;
-        else if (its >= fl[F_MAXIT]) reason = IIFE_KSP_DIVERGED_ITS;
-        else if (beta == 0.0) { reason = IIFE_KSP_CONVERGED_ATOL; its_out = its + 1; }
-        else if (beta < 0.0) { reason = IIFE_KSP_DIVERGED_INDEFINITE_PC; its_out = its + 1; }
-        else if (isnan(beta) || isinf(beta)) { reason = IIFE_KSP_DIVERGED_NANORINF; its_out = its + 1; }
-        s_bb = beta / beta_old;
-        s_stop = reason;
-        if (blockIdx.x == 0) {
-          sc[S_BETA2 + (int)(it_rel & 1ull)] = beta;
-          sc[S_BETA_OLD] = beta_old;
-          sc[S_BETA] = beta;
-          sc[S_DP] = dp;
-          log_hist(hist, hist_len, its, dp);
-          fl[F_ITS] = its_out;
-          if (reason) {
-            __threadfence();
-            fl[F_REASON] = reason;
-          }
+// scalar step of the three-kernel iteration, by warp 0 of EVERY CTA (all reach the same verdict; CTA 0 records it):
+// KSPSolve_CG after the update of iteration it_rel-1: beta_old <- beta, beta = (z, r), dp = ||z||, its, test.
+// git / it_rel: global / solve-relative index of the iteration that is about to start.  Results in shared memory.
+__device__ __forceinline__ void cg3_scalar_step(const P2PRed &pr, unsigned long long git, unsigned long long it_rel, double *sc, int *fl,
+                                                double *hist, long long hist_len, double *s_bb, int *s_stop) {
+  if (threadIdx.x < 32) {
+    double v[2];
+    p2p_wait_sum(pr, 2ull * (git - 1ull) + 2ull, v, 2);
+    if (threadIdx.x == 0) {
+      const double beta_old = sc[S_BETA2 + (int)((it_rel - 1ull) & 1ull)];
+      const double beta = v[0], dp = sqrt(v[1]);
+      const int its = (int)it_rel;
+      int reason = 0, its_out = its;
+      if (isnan(dp) || isinf(dp)) reason = IIFE_KSP_DIVERGED_NANORINF;
+      else if (dp <= sc[S_TTOL]) reason = (dp < sc[S_ATOL]) ? IIFE_KSP_CONVERGED_ATOL : IIFE_KSP_CONVERGED_RTOL;
+      else if (dp >= sc[S_DTOL] * sc[S_RHO0]) reason = IIFE_KSP_DIVERGED_DTOL;
+      else if (its >= fl[F_MAXIT]) reason = IIFE_KSP_DIVERGED_ITS;
+      else if (beta == 0.0) { reason = IIFE_KSP_CONVERGED_ATOL; its_out = its + 1; }
+      else if (beta < 0.0) { reason = IIFE_KSP_DIVERGED_INDEFINITE_PC; its_out = its + 1; }
+      else if (isnan(beta) || isinf(beta)) { reason = IIFE_KSP_DIVERGED_NANORINF; its_out = its + 1; }
+      *s_bb = beta / beta_old;
+      *s_stop = reason;
+      if (blockIdx.x == 0) {
+        sc[S_BETA2 + (int)(it_rel & 1ull)] = beta;
+        sc[S_BETA_OLD] = beta_old;
+        sc[S_BETA] = beta;
+        sc[S_DP] = dp;
+        log_hist(hist, hist_len, its, dp);
+        fl[F_ITS] = its_out;
+        if (reason) {
+          __threadfence();
+          fl[F_REASON] = reason;
         }
       }
     }
-    __syncthreads();
-    if (s_stop) return;
   }
-  const double bb = first ? 0.0 : s_bb;
+}
+
+// p = z + bb p (p = z when `first`), z = D^-1 r recomputed; the thread that updates a boundary row stores it into the
+// neighbours' ghost slots; the last CTA to finish raises the halo flags with sequence number halo_seq.
+__device__ __forceinline__ void cg3_p_and_push(const double *r, const double *__restrict__ dinv, double *p, int64_t n, double bb,
+                                               bool first, const RowPush &rp, unsigned long long halo_seq, bool *last) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   bool stored = false;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += VEC_ILP * stride) {
@@ -396,27 +384,125 @@ k_cg_p_push(const double *__restrict__ r, const double *__restrict__ dinv, doubl
       }
     }
   }
-  pdl_launch();
   if (stored) __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(rp.counter, 1u);
-    last = (t == gridDim.x - 1);
+    *last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (!last) return;
+  if (!*last) return;
   __threadfence_system();
   const int q = threadIdx.x;
-  if (q < rp.nranks && ((rp.send_mask >> q) & 1u)) st_flag(&rp.pt.mbox[q]->halo_flag[rp.me], *rp.seq_base + (unsigned long long)pr.k_off + 1ull);
-  if (threadIdx.x == 0) {
-    *rp.counter = 0u;
-    cg_trace(pr, TR_P_OUT);
+  if (q < rp.nranks && ((rp.send_mask >> q) & 1u)) st_flag(&rp.pt.mbox[q]->halo_flag[rp.me], halo_seq);
+  if (threadIdx.x == 0) *rp.counter = 0u;
+}
+
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_p_push(const double *__restrict__ r, const double *__restrict__ dinv, double *__restrict__ p, int64_t n, double *sc,
+            int *fl, double *hist, long long hist_len, P2PRed pr, RowPush rp) {
+  if (fl[F_REASON] != 0) return;  // set by an earlier kernel (CTA 0 of THIS kernel can only reach the same verdict)
+  __shared__ double s_bb;
+  __shared__ int s_stop;
+  __shared__ bool last;
+  const unsigned long long git = *pr.iter + (unsigned long long)pr.k_off;
+  const unsigned long long it_rel = git - pr.iter[1];
+  const bool first = (it_rel == 0ull);
+  if (blockIdx.x == 0 && threadIdx.x == 0) cg_trace(pr, TR_P_IN);
+  if (!first) {
+    cg3_scalar_step(pr, git, it_rel, sc, fl, hist, hist_len, &s_bb, &s_stop);
+    if (blockIdx.x == 0 && threadIdx.x == 0) cg_trace(pr, TR_P_WAITED);
+    __syncthreads();
+    if (s_stop) return;
   }
+  cg3_p_and_push(r, dinv, p, n, first ? 0.0 : s_bb, first, rp, *rp.seq_base + (unsigned long long)pr.k_off + 1ull, &last);
+  if (last && threadIdx.x == 0) cg_trace(pr, TR_P_OUT);
+}
+
+// Two-kernel iteration (IIFE_CG_MERGED, default on): k_cg_update<3> of iteration k and k_cg_p_push of iteration k+1 in
+// ONE kernel.  After its part of the x / r update every CTA waits for all ranks' (z.r, z.z) — the last CTA of every
+// rank pushes them — takes the scalar step and updates its part of p.  Every CTA spins inside the kernel, so the grid
+// must be co-resident (sized by the occupancy query in cg_solve); the spins are bounded like all the others.
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_update_p(double *x, double *r, double *p, const double *__restrict__ w, const double *__restrict__ dinv, int64_t n,
+              double *sc, int *fl, double *partials, unsigned int *counter, double *hist, long long hist_len, P2PRed pr,
+              RowPush rp) {
+  if (fl[F_REASON] != 0) return;
+  __shared__ double red[32];
+  __shared__ double out[2];
+  __shared__ bool last;
+  __shared__ double s_delta, s_bb;
+  __shared__ int s_stop;
+  const unsigned long long git = *pr.iter + (unsigned long long)pr.k_off;
+  const unsigned long long it_rel = git - pr.iter[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) cg_trace(pr, TR_U_IN);
+  if (threadIdx.x < 32) {
+    double d;
+    p2p_wait_sum(pr, 2ull * git + 1ull, &d, 1);
+    if (threadIdx.x == 0) {
+      s_delta = d;
+      if (blockIdx.x == 0) {
+        sc[S_DELTA] = d;
+        cg_trace(pr, TR_U_WAITED);
+      }
+    }
+  }
+  __syncthreads();
+  const double delta = s_delta;
+  if (!(delta > 0.0)) {  // (p, A p) <= 0 or NaN: DIVERGED_INDEFINITE_MAT, no update (PETSc: its = i+1 at that point)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      fl[F_ITS] = fl[F_ITS] + 1;
+      __threadfence();
+      fl[F_REASON] = isnan(delta) ? IIFE_KSP_DIVERGED_NANORINF : IIFE_KSP_DIVERGED_INDEFINITE_MAT;
+    }
+    return;
+  }
+  const double alpha = sc[S_BETA2 + (int)(it_rel & 1ull)] / delta;
+  double acc[2] = {0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += VEC_ILP * stride) {
+    double pv[VEC_ILP], wv[VEC_ILP], xv[VEC_ILP], rv[VEC_ILP], dv[VEC_ILP];
+#pragma unroll
+    for (int u = 0; u < VEC_ILP; ++u) {
+      const int64_t i = i0 + u * stride;
+      const bool in = i < n;
+      pv[u] = in ? p[i] : 0.0;
+      wv[u] = in ? __ldcs(w + i) : 0.0;
+      xv[u] = in ? x[i] : 0.0;
+      rv[u] = in ? r[i] : 0.0;
+      dv[u] = (in && dinv) ? dinv[i] : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < VEC_ILP; ++u) {  // same order of the sums as k_cg_update
+      const int64_t i = i0 + u * stride;
+      if (i < n) {
+        x[i] = fma(alpha, pv[u], xv[u]);
+        const double ri = fma(-alpha, wv[u], rv[u]);
+        r[i] = ri;
+        const double z = dv[u] * ri;
+        acc[0] = fma(z, ri, acc[0]);
+        acc[1] = fma(z, z, acc[1]);
+      }
+    }
+  }
+  if (grid_reduce<2>(acc, partials, counter, out, red, &last)) {
+    p2p_push(pr, 2ull * git + 2ull, out, 2, threadIdx.x);
+    if (threadIdx.x == 0) cg_trace(pr, TR_U_OUT);
+  }
+  // ---- iteration git + 1: scalar step, p update, ghost push (the thread that wrote r[i] above reads it again here)
+  P2PRed prn = pr;
+  prn.k_off = pr.k_off + 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) cg_trace(prn, TR_P_IN);
+  cg3_scalar_step(pr, git + 1ull, it_rel + 1ull, sc, fl, hist, hist_len, &s_bb, &s_stop);
+  if (blockIdx.x == 0 && threadIdx.x == 0) cg_trace(prn, TR_P_WAITED);
+  __syncthreads();
+  if (s_stop) return;
+  cg3_p_and_push(r, dinv, p, n, s_bb, false, rp, *rp.seq_base + (unsigned long long)pr.k_off + 2ull, &last);
+  if (last && threadIdx.x == 0) cg_trace(prn, TR_P_OUT);
 }
 
 // end of a captured chunk of `chunk` iterations: the counters the kernels above offset with k
 __global__ void k_cg_chunk_end(unsigned long long *dev_seq, int chunk) {
-  pdl_wait();
   dev_seq[0] += (unsigned long long)chunk;
   dev_seq[2] += (unsigned long long)chunk;
 }
@@ -896,22 +982,41 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   }
   // NCCL calls inside the loop: keep to plain stream launches (no graph capture) in that case
   const bool use_graph = env_int("IIFE_KSP_GRAPH", 1) != 0 && (!dist || p2p);
-  // programmatic dependent launch between the kernels of the iteration (single GPU and three-kernel peer path)
-  const bool pdl = env_int("IIFE_CG_PDL", 0) != 0 && (!dist || fused3);
-  spmv_set_pdl(pdl);
+  // two-kernel iteration: update of iteration k and p update of iteration k + 1 in one co-resident kernel
+  bool merged = fused3 && env_int("IIFE_CG_MERGED", 1) != 0;
+  int g_merged = g;
+  if (merged) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_update_p, VEC_THREADS, 0) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      merged = false;
+    } else {
+      g_merged = std::min(g, per_sm * c.sm_count);
+    }
+  }
   auto enqueue_iteration = [&](int k) -> int {
+    if (fused3 && merged) {
+      P2PRed prk = pr;
+      prk.k_off = k;
+      HaloWait hwk = hwait;
+      hwk.k_off = k;
+      IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl, &prk, &hwk));
+      IIFE_LAUNCH(k_cg_update_p, g_merged, VEC_THREADS, 0, x, r.p, p.p, (const double *)wv.p, dinv, n, w.sc, w.fl, w.partials, w.counters,
+                  w.hist, (long long)w.hist_len, prk, rpush);
+      return IIFE_OK;
+    }
     if (fused3) {
       P2PRed prk = pr;
       prk.k_off = k;
       HaloWait hwk = hwait;
       hwk.k_off = k;
-      IIFE_LAUNCH_PDL(pdl, k_cg_p_push, g, VEC_THREADS, 0, (const double *)r.p, dinv, p.p, n, w.sc, w.fl, w.hist, (long long)w.hist_len, prk, rpush);
+      IIFE_LAUNCH(k_cg_p_push, g, VEC_THREADS, 0, (const double *)r.p, dinv, p.p, n, w.sc, w.fl, w.hist, (long long)w.hist_len, prk, rpush);
       IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl, &prk, &hwk));
-      IIFE_LAUNCH_PDL(pdl, k_cg_update<3>, g, VEC_THREADS, 0, x, r.p, (const double *)p.p, (const double *)wv.p, dinv, n, w.sc, w.fl,
+      IIFE_LAUNCH(k_cg_update<3>, g, VEC_THREADS, 0, x, r.p, (const double *)p.p, (const double *)wv.p, dinv, n, w.sc, w.fl,
                       w.partials, w.counters, w.hist, (long long)w.hist_len, prk);
       return IIFE_OK;
     }
-    IIFE_LAUNCH_PDL(pdl && !dist, k_cg_p, g, VEC_THREADS, 0, (const double *)r.p, dinv, p.p, n, (const double *)w.sc, (const int *)w.fl);
+    IIFE_LAUNCH(k_cg_p, g, VEC_THREADS, 0, (const double *)r.p, dinv, p.p, n, (const double *)w.sc, (const int *)w.fl);
     if (dist && !dbg_nohalo) IIFE_TRY(xchg(w.fl));
     IIFE_TRY(spmv_dot_launch(A, p.p, wv.p, w.sc + S_DELTA, w.partials + 2 * MAX_PARTIALS, w.counters + 1, w.fl,
                              (p2p && !dbg_nored) ? &pr : nullptr));
@@ -931,7 +1036,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
       IIFE_TRY(ar(w.sc + S_RAW, 2, w.fl));
       IIFE_LAUNCH(k_cg_update_scalars, 1, 1, 0, w.sc, w.fl, w.hist, (long long)w.hist_len);
     } else {
-      IIFE_LAUNCH_PDL(pdl, k_cg_update<0>, g, VEC_THREADS, 0, x, r.p, (const double *)p.p, (const double *)wv.p, dinv, n, w.sc, w.fl,
+      IIFE_LAUNCH(k_cg_update<0>, g, VEC_THREADS, 0, x, r.p, (const double *)p.p, (const double *)wv.p, dinv, n, w.sc, w.fl,
                       w.partials, w.counters, w.hist, (long long)w.hist_len, pr);
     }
     return IIFE_OK;
@@ -972,7 +1077,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     if (e == cudaSuccess) {
       int rc = IIFE_OK;
       for (int k = 0; k < chunk && rc == IIFE_OK; ++k) rc = enqueue_iteration(k);
-      if (fused3 && rc == IIFE_OK) IIFE_LAUNCH_PDL(pdl, k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
+      if (fused3 && rc == IIFE_OK) IIFE_LAUNCH(k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
       e = cudaStreamEndCapture(c.stream, &graph);
       if (rc == IIFE_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
       if (rc != IIFE_OK || e != cudaSuccess || !exec) {
@@ -1003,7 +1108,7 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
       c.launches += launches_per_chunk;
     } else {
       for (int k = 0; k < chunk; ++k) IIFE_TRY(enqueue_iteration(k));
-      if (fused3) IIFE_LAUNCH_PDL(pdl, k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
+      if (fused3) IIFE_LAUNCH(k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
       IIFE_CUDA(cudaGetLastError());
     }
     IIFE_CUDA(cudaMemcpyAsync(hf[slot].fl, w.fl, sizeof(int) * F_COUNT, cudaMemcpyDeviceToHost, c.stream));
@@ -1011,6 +1116,11 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     enq += chunk;
     return IIFE_OK;
   };
+  if (merged) {  // p of the first iteration (the merged kernel produces the later ones)
+    P2PRed pr0 = pr;
+    pr0.k_off = 0;
+    IIFE_LAUNCH(k_cg_p_push, g, VEC_THREADS, 0, (const double *)r.p, dinv, p.p, n, w.sc, w.fl, w.hist, (long long)w.hist_len, pr0, rpush);
+  }
   rc = enqueue_chunk(0);
   if (rc == IIFE_OK) rc = enqueue_chunk(1);
   for (int k = 0; rc == IIFE_OK; ++k) {
@@ -1023,7 +1133,6 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
     rc = enqueue_chunk(slot);
   }
   cudaStreamSynchronize(c.stream);
-  spmv_set_pdl(false);
   if (trace.p && rc == IIFE_OK) {
     // averages over iterations 20 .. its-5 of this solve (nanoseconds between the stamps; see p2p_dev.cuh)
     std::vector<unsigned long long> t((size_t)CG_TRACE_ITERS * CG_TRACE_SLOTS);
@@ -1048,9 +1157,12 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
       }
       double tot = 0;
       for (double v : sum) tot += v;
-      fprintf(stderr, "[cg trace rank %d] %.1f us/iteration over iterations %d..%d:", H ? H->me : 0, tot / (hi - lo) * 1e-3, lo, hi);
-      for (int k = 0; k < 9; ++k) fprintf(stderr, " %s %.1f;", names[k], sum[k] / (hi - lo) * 1e-3);
-      fprintf(stderr, "\n");
+      char line[1024];  // one write per rank: the ranks share stderr
+      int len = snprintf(line, sizeof line, "[cg trace rank %d] %.1f us/iteration over iterations %d..%d:", H ? H->me : 0,
+                         tot / (hi - lo) * 1e-3, lo, hi);
+      for (int k = 0; k < 9 && len < (int)sizeof line; ++k)
+        len += snprintf(line + len, sizeof line - len, " %s %.1f;", names[k], sum[k] / (hi - lo) * 1e-3);
+      fprintf(stderr, "%s\n", line);
     }
   }
   cudaEventDestroy(ev[0]);

@@ -499,7 +499,6 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr,
             const double *__restrict__ sell_val, int64_t n_rows, int64_t n_slices, const double *__restrict__ x, double *__restrict__ y,
             double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *__restrict__ counter,
             const int *__restrict__ flag, P2PRed pr, HaloWait hw) {
-  pdl_wait();
   if (flag && *flag != 0) return;  // converged: the rest of the enqueued chunk is a row of no-ops
   __shared__ double red[32];
   __shared__ bool is_last;
@@ -555,7 +554,6 @@ k_spmv_sell(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr,
       }
     }
   }
-  pdl_launch();
   if (DOT) {
     double bs = block_sum(dsum, red);
     if (threadIdx.x == 0) {
@@ -693,9 +691,6 @@ static int sell_unroll() {
   return u;
 }
 
-static bool g_sell_pdl = false;  // set by the CG driver around its iteration launches (spmv_set_pdl)
-void spmv_set_pdl(bool on) { g_sell_pdl = on; }
-
 static int launch_sell(const Mat *A, bool dot, const double *x, double *y, double *dot_out, double *partials,
                        unsigned int *counter, const int *flag, const P2PRed *red_in = nullptr, const HaloWait *hw_in = nullptr) {
   P2PRed pr{};
@@ -706,9 +701,8 @@ static int launch_sell(const Mat *A, bool dot, const double *x, double *y, doubl
 #define SELL_GO(D, UU, IF)                                                                                          \
   {                                                                                                                 \
     int g = resident_grid(k_spmv_sell<D, UU, IF>, need);                                                            \
-    IIFE_LAUNCH_PDL(g_sell_pdl && dot, (k_spmv_sell<D, UU, IF>), g, SPMV_THREADS, 0, (const int *)A->sell_ptr, (const int *)A->sell_cptr, \
-                    (const int *)A->sell_col, (const double *)A->sell_val, A->n_rows, A->sell_slices, x, y, dot_out, partials, counter, flag, pr, \
-                    hw);                                                                                            \
+    IIFE_LAUNCH((k_spmv_sell<D, UU, IF>), g, SPMV_THREADS, 0, A->sell_ptr, A->sell_cptr, A->sell_col, A->sell_val, A->n_rows, \
+                A->sell_slices, x, y, dot_out, partials, counter, flag, pr, hw);                                    \
   }
   int u = sell_unroll();
   if (dot && hw.flags && hw.interior_first) {

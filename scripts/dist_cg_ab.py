@@ -80,15 +80,15 @@ def solve_timed(reps=3):
 
 
 variants = [
-    ("round-2 baseline: prologue wait, fence+flag reductions", {"IIFE_CG_INTERIOR_FIRST": "0", "IIFE_P2P_LL": "0"}),
-    ("interior first", {"IIFE_CG_INTERIOR_FIRST": "1", "IIFE_P2P_LL": "0"}),
-    ("packed reductions", {"IIFE_CG_INTERIOR_FIRST": "0", "IIFE_P2P_LL": "1"}),
-    ("interior first + packed reductions (default)", {"IIFE_CG_INTERIOR_FIRST": "1", "IIFE_P2P_LL": "1"}),
+    ("round-2 baseline: three kernels, prologue wait, fence+flag reductions", {"IIFE_CG_INTERIOR_FIRST": "0", "IIFE_P2P_LL": "0", "IIFE_CG_MERGED": "0"}),
+    ("three kernels, interior first + packed reductions", {"IIFE_CG_INTERIOR_FIRST": "1", "IIFE_P2P_LL": "1", "IIFE_CG_MERGED": "0"}),
+    ("two kernels (update + p merged), prologue wait", {"IIFE_CG_INTERIOR_FIRST": "0", "IIFE_P2P_LL": "1", "IIFE_CG_MERGED": "1"}),
+    ("two kernels, interior first + packed reductions (default)", {"IIFE_CG_INTERIOR_FIRST": "1", "IIFE_P2P_LL": "1", "IIFE_CG_MERGED": "1"}),
 ]
 extra = os.environ.get("AB_EXTRA", "")  # e.g. "IIFE_CG_PDL=1;IIFE_KSP_CHUNK=64"
 for item in [e for e in extra.split(";") if e]:
     k, v = item.split("=")
-    variants.append((f"default + {item}", {"IIFE_CG_INTERIOR_FIRST": "1", "IIFE_P2P_LL": "1", k: v}))
+    variants.append((f"default + {item}", {"IIFE_CG_INTERIOR_FIRST": "1", "IIFE_P2P_LL": "1", "IIFE_CG_MERGED": "1", k: v}))
 ref = None
 for rep in range(int(os.environ.get("AB_REPS", "2"))):
     for name, env in variants:
