@@ -364,25 +364,93 @@ __global__ void k_sell_widths(const int *__restrict__ rowptr, int64_t n_rows, in
   }
 }
 
-__global__ void k_sell_fill(const int *__restrict__ rowptr, const int *__restrict__ colind, const double *__restrict__ val,
-                            int64_t n_rows, int64_t n_cols, int64_t n_slices, const int *__restrict__ sell_ptr,
-                            int *__restrict__ sell_col, double *__restrict__ sell_val, int fill_cols) {
+// A slice is stored with SHARED column offsets (one word per slot instead of 32) when its rows can be ALIGNED to the
+// offsets of its longest row: every entry of every row sits in the slot whose offset (column - row) it has, the slots a
+// shorter row lacks are padded with zeros that read an owned entry of x.  Rows at the ends of a grid line then share the
+// slice's 27 offsets with their interior neighbours instead of making the whole slice carry 32 x width column words.
+// The walk below is the same in the decision (k_sell_align) and the fill (k_sell_fill): in slot order, a row takes its
+// next entry if the offsets agree, a zero otherwise; the slice aligns if every row ends with all entries placed.
+struct SellWalk {
+  int ref_lane, ref_b, ref_i;
+};
+__device__ __forceinline__ SellWalk sell_walk_begin(int len, int width, int b, int64_t i) {
+  SellWalk wk;
+  const unsigned longest = __ballot_sync(0xffffffffu, len == width);
+  wk.ref_lane = longest ? __ffs(longest) - 1 : 0;
+  wk.ref_b = __shfl_sync(0xffffffffu, b, wk.ref_lane);
+  wk.ref_i = __shfl_sync(0xffffffffu, (int)i, wk.ref_lane);
+  return wk;
+}
+
+// per slice: number of column words of the compact layout (width if the slice aligns, 32 x width otherwise)
+__global__ void k_sell_align(const int *__restrict__ rowptr, const int *__restrict__ colind, int64_t n_rows, int64_t n_pad_lim,
+                             int64_t n_slices, const int *__restrict__ sell_ptr, int *__restrict__ words, int force_full) {
   int lane = threadIdx.x & 31;
   int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t s = w; s < n_slices; s += nw) {
-    int64_t i = s * 32 + lane;
+    const int64_t i = s * 32 + lane;
+    const bool live = i < n_rows;
+    int b = 0, len = 0;
+    if (live) {
+      b = rowptr[i];
+      len = rowptr[i + 1] - b;
+    }
+    const int width = (sell_ptr[s + 1] - sell_ptr[s]) >> 5;
+    const SellWalk wk = sell_walk_begin(len, width, b, i);
+    bool ok = true;
+    int q = 0;
+    for (int k = 0; k < width; ++k) {
+      const int off = __ldg(colind + wk.ref_b + k) - wk.ref_i;  // same address in all lanes: one broadcast load
+      if (live) {
+        if (q < len && __ldg(colind + b + q) - (int)i == off) ++q;
+        else ok = ok && (i + off >= 0) && (i + off < n_pad_lim);  // a padded slot reads x[i + off]: must be an owned entry
+      }
+    }
+    ok = ok && (q == len);
+    ok = __all_sync(0xffffffffu, ok) && !force_full && width > 0;
+    if (lane == 0) words[s] = ok ? width : width * 32;
+  }
+}
+
+// values (and, with sell_col != nullptr, the compact columns) of every slice
+__global__ void k_sell_fill(const int *__restrict__ rowptr, const int *__restrict__ colind, const double *__restrict__ val,
+                            int64_t n_rows, int64_t n_cols, int64_t n_slices, const int *__restrict__ sell_ptr,
+                            const int *__restrict__ sell_cptr, int *__restrict__ sell_col, double *__restrict__ sell_val) {
+  int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = w; s < n_slices; s += nw) {
+    const int64_t i = s * 32 + lane;
     int b = 0, len = 0;
     if (i < n_rows) {
       b = rowptr[i];
       len = rowptr[i + 1] - b;
     }
-    int sb = sell_ptr[s], width = (sell_ptr[s + 1] - sb) >> 5;
-    int pad_col = (i < n_cols) ? (int)i : 0;
-    for (int k = 0; k < width; ++k) {
-      bool in = k < len;
-      if (fill_cols) sell_col[sb + k * 32 + lane] = in ? colind[b + k] : pad_col;
-      sell_val[sb + k * 32 + lane] = in ? val[b + k] : 0.0;
+    const int sb = sell_ptr[s], width = (sell_ptr[s + 1] - sb) >> 5;
+    const int cb = sell_cptr[s];
+    const bool shared = (sell_cptr[s + 1] - cb) == width;
+    const bool all_full = __all_sync(0xffffffffu, len == width);
+    if (!shared || all_full) {  // entries in CSR order, short rows padded at the end with (own column, 0)
+      const int pad_col = (i < n_cols) ? (int)i : 0;
+      for (int k = 0; k < width; ++k) {
+        const bool in = k < len;
+        if (sell_col) {
+          if (!shared) sell_col[cb + k * 32 + lane] = in ? colind[b + k] : pad_col;
+          else if (lane == 0) sell_col[cb + k] = colind[b + k] - (int)i;
+        }
+        sell_val[sb + k * 32 + lane] = in ? val[b + k] : 0.0;
+      }
+    } else {  // aligned slice with short rows: the walk of k_sell_align
+      const SellWalk wk = sell_walk_begin(len, width, b, i);
+      int q = 0;
+      for (int k = 0; k < width; ++k) {
+        const int off = __ldg(colind + wk.ref_b + k) - wk.ref_i;
+        const bool take = q < len && __ldg(colind + b + q) - (int)i == off;
+        sell_val[sb + k * 32 + lane] = take ? val[b + q] : 0.0;
+        if (take) ++q;
+        if (sell_col && lane == 0) sell_col[cb + k] = off;
+      }
     }
   }
 }
@@ -446,51 +514,6 @@ __device__ __forceinline__ double sell_slice(const int *__restrict__ sell_ptr, c
 #pragma unroll
   for (int u = 1; u < U; ++u) acc += a[u];
   return acc;
-}
-
-// per slice: number of column words of the compact layout (width if all live rows share the offsets)
-__global__ void k_sell_uniform(const int *__restrict__ sell_ptr, const int *__restrict__ full_col, int64_t n_rows,
-                               int64_t n_slices, int *__restrict__ words, int force_full) {
-  int lane = threadIdx.x & 31;
-  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t s = w; s < n_slices; s += nw) {
-    int sb = sell_ptr[s], width = (sell_ptr[s + 1] - sb) >> 5;
-    int64_t i = s * 32 + lane;
-    bool live = i < n_rows;
-    int first_live = __ffs(__ballot_sync(0xffffffffu, live)) - 1;
-    bool uni = true;
-    for (int k = 0; k < width; ++k) {
-      int off = live ? full_col[sb + k * 32 + lane] - (int)i : 0;
-      int ref = __shfl_sync(0xffffffffu, off, first_live < 0 ? 0 : first_live);
-      uni = uni && (!live || off == ref);
-    }
-    uni = __all_sync(0xffffffffu, uni) && !force_full;
-    if (lane == 0) words[s] = uni ? width : width * 32;
-  }
-}
-
-__global__ void k_sell_compact(const int *__restrict__ sell_ptr, const int *__restrict__ sell_cptr,
-                               const int *__restrict__ full_col, int64_t n_rows, int64_t n_slices, int *__restrict__ ccol) {
-  int lane = threadIdx.x & 31;
-  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t s = w; s < n_slices; s += nw) {
-    int sb = sell_ptr[s], width = (sell_ptr[s + 1] - sb) >> 5;
-    int cb = sell_cptr[s], words = sell_cptr[s + 1] - cb;
-    if (words == width) {
-      int64_t i = s * 32 + lane;
-      bool live = i < n_rows;
-      int first_live = __ffs(__ballot_sync(0xffffffffu, live)) - 1;
-      for (int k = 0; k < width; ++k) {
-        int off = live ? full_col[sb + k * 32 + lane] - (int)i : 0;
-        off = __shfl_sync(0xffffffffu, off, first_live < 0 ? 0 : first_live);
-        if (lane == 0) ccol[cb + k] = off;
-      }
-    } else {
-      for (int k = 0; k < width; ++k) ccol[cb + k * 32 + lane] = full_col[sb + k * 32 + lane];
-    }
-  }
 }
 
 template <bool DOT, int U, bool IFIRST>
@@ -808,20 +831,17 @@ int mat_ensure_sell(Mat *A) {
       mat_free_sell(A);
       return rc;
     }
-    // columns: fill the full layout into a temporary, then keep only the compact form
+    // which slices share their column offsets (k_sell_align), then values and compact columns in one pass
     {
-      Tmp<int> full, words;
+      Tmp<int> words;
       int *cptr = nullptr;
-      rc = full.alloc((size_t)padded);
-      if (rc == IIFE_OK) rc = words.alloc((size_t)n_slices + 1);
+      rc = words.alloc((size_t)n_slices + 1);
       if (rc == IIFE_OK) rc = dev_alloc_t(&cptr, (size_t)n_slices + 1);
       if (rc == IIFE_OK) {
         A->sell_cptr = cptr;
-        IIFE_LAUNCH(k_sell_fill, sell_grid(n_slices), SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, A->n_cols,
-                    n_slices, A->sell_ptr, full.p, A->sell_val, 1);
         static const bool no_compress = getenv("IIFE_SELL_NOCOMPRESS") != nullptr;
-        IIFE_LAUNCH(k_sell_uniform, sell_grid(n_slices), SPMV_THREADS, 0, A->sell_ptr, full.p, A->n_rows, n_slices, words.p,
-                    no_compress ? 1 : 0);
+        IIFE_LAUNCH(k_sell_align, sell_grid(n_slices), SPMV_THREADS, 0, A->rowptr, A->colind, A->n_rows,
+                    std::min<int64_t>(A->n_rows, A->n_cols), n_slices, A->sell_ptr, words.p, no_compress ? 1 : 0);
         int64_t cw = 0;
         rc = exclusive_scan_i32(words.p, cptr, n_slices, &cw);
         if (rc == IIFE_OK) {
@@ -829,8 +849,8 @@ int mat_ensure_sell(Mat *A) {
           rc = dev_alloc_t(&A->sell_col, (size_t)cw);
         }
         if (rc == IIFE_OK) {
-          IIFE_LAUNCH(k_sell_compact, sell_grid(n_slices), SPMV_THREADS, 0, A->sell_ptr, cptr, full.p, A->n_rows, n_slices,
-                      A->sell_col);
+          IIFE_LAUNCH(k_sell_fill, sell_grid(n_slices), SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, A->n_cols, n_slices,
+                      A->sell_ptr, A->sell_cptr, A->sell_col, A->sell_val);
           cudaError_t e = cudaStreamSynchronize(c.stream);
           if (e != cudaSuccess) rc = set_err(IIFE_ERR_CUDA, "SELL build: %s", cudaGetErrorString(e));
         }
@@ -845,7 +865,7 @@ int mat_ensure_sell(Mat *A) {
   }
   if (!A->sell_vals_valid) {
     IIFE_LAUNCH(k_sell_fill, sell_grid(A->sell_slices), SPMV_THREADS, 0, A->rowptr, A->colind, A->val, A->n_rows, A->n_cols,
-                A->sell_slices, A->sell_ptr, (int *)nullptr, A->sell_val, 0);
+                A->sell_slices, A->sell_ptr, A->sell_cptr, (int *)nullptr, A->sell_val);
     IIFE_CHECK_LAUNCH();
     A->sell_vals_valid = true;
   }
