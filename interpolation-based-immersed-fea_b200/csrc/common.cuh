@@ -146,6 +146,8 @@ int spmv_pick_lpr(const Mat *A);
 // padding would exceed 1.25x nnz, in which case callers stay on CSR) and refreshes values.
 int mat_ensure_sell(Mat *A);
 int mat_ensure_sell_order(Mat *A, int64_t n_owned);
+int spmv_launch_signature();       // everything env-selected that shapes the SpMV launches (key of cached graphs)
+void ksp_release_cached_graphs();  // ksp.cu: captured CG chunks kept between solves
 void mat_free_sell(Mat *A);
 
 // ghost-entry exchange plan of a row-partitioned operator (comm.cu)

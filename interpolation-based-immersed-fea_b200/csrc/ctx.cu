@@ -289,6 +289,7 @@ int iife_finalize(void) {
   if (!c.init) return IIFE_OK;
   iife_plan_cache_clear();
   cudaStreamSynchronize(c.stream);
+  ksp_release_cached_graphs();
   dev_release_cached();
   if (c.own_stream) cudaStreamDestroy(c.own_stream);
   c.own_stream = nullptr;

@@ -874,6 +874,78 @@ static int env_int(const char *name, int dflt) {
 // ------------------------------------------------------------------------------------------------
 // CG driver (device pointers)
 // ------------------------------------------------------------------------------------------------
+// Work arrays of a solve come from an arena that hands the k-th request of a solve the block the k-th request of the
+// previous solve got (same size): the addresses in the kernels' arguments stay the same from solve to solve, which is
+// what lets the captured CG chunk below be reused.  The blocks (a few vectors of the last system size) stay with the
+// library until iife_finalize.
+struct KspArena {
+  std::vector<std::pair<void *, size_t>> blocks;
+  size_t cursor = 0;
+};
+static KspArena g_arena;
+static int arena_alloc(void **p, size_t bytes) {
+  if (bytes < 8) bytes = 8;
+  KspArena &a = g_arena;
+  if (a.cursor < a.blocks.size() && a.blocks[a.cursor].second == bytes) {
+    *p = a.blocks[a.cursor++].first;
+    return IIFE_OK;
+  }
+  for (size_t k = a.cursor; k < a.blocks.size(); ++k) dev_free(a.blocks[k].first, a.blocks[k].second);
+  a.blocks.resize(a.cursor);
+  IIFE_TRY(dev_alloc(p, bytes));
+  a.blocks.emplace_back(*p, bytes);
+  a.cursor++;
+  return IIFE_OK;
+}
+static void arena_release() {
+  for (auto &b : g_arena.blocks) dev_free(b.first, b.second);
+  g_arena.blocks.clear();
+  g_arena.cursor = 0;
+}
+template <class T>
+struct Ws {  // like Tmp<T>, owned by the arena
+  T *p = nullptr;
+  int alloc(size_t count) { return arena_alloc((void **)&p, (count ? count : 1) * sizeof(T)); }
+};
+
+// The captured chunk of CG iterations is kept between solves: a graph depends on nothing but its kernels' arguments
+// and launch shapes, so it is reused while every value that enters them is unchanged (the caching allocator hands
+// the work vectors of the next solve the same blocks; a new A_b of the same plan gets the SELL arrays of the old
+// one).  Any difference in the key -> capture and instantiate again (0.2-0.4 ms).  IIFE_KSP_GRAPH_CACHE=0 disables.
+struct CgGraphKey {
+  const void *ptr[20];
+  long long n, slices, hist_len;
+  int ints[12];
+  P2PRed pr;
+  RowPush rp;
+  HaloWait hw;
+};
+struct CgGraphEntry {
+  bool valid = false;
+  CgGraphKey key;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+};
+// a few entries: consecutive steps alternate between two sets of addresses (the previous A_b is still alive while the
+// next one is built)
+constexpr int CG_GRAPH_CACHE = 4;
+static CgGraphEntry g_cg_graph[CG_GRAPH_CACHE];
+static int g_cg_graph_next = 0;
+
+static void cg_graph_entry_free(CgGraphEntry &e) {
+  if (e.exec) cudaGraphExecDestroy(e.exec);
+  if (e.graph) cudaGraphDestroy(e.graph);
+  e.exec = nullptr;
+  e.graph = nullptr;
+  e.valid = false;
+}
+
+void ksp_release_cached_graphs() {
+  for (auto &e : g_cg_graph) cg_graph_entry_free(e);
+  arena_release();
+}
+
 static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double *x, int64_t max_it, KspWork &w,
                     HostFlags *hf) {
   Ctx &c = ctx();
@@ -887,8 +959,8 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   // timing experiments only (results are wrong with these set): drop the halo / the reductions
   static const bool dbg_nohalo = getenv("IIFE_DBG_NOHALO") != nullptr, dbg_nored = getenv("IIFE_DBG_NORED") != nullptr;
   struct PBuf { double *p = nullptr; } p;
-  Tmp<double> r, p_own, wv;
-  Tmp<unsigned long long> trace;
+  Ws<double> r, p_own, wv;
+  Ws<unsigned long long> trace;
   IIFE_TRY(r.alloc((size_t)n));
   if (p2p) p.p = H->xbuf;
   else {
@@ -1071,28 +1143,81 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   int64_t launches_per_chunk = 0;
+  bool exec_cached = false, graph_hit = false;
   if (use_graph) {
-    int64_t before = c.launches;
-    cudaError_t e = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal);
-    if (e == cudaSuccess) {
-      int rc = IIFE_OK;
-      for (int k = 0; k < chunk && rc == IIFE_OK; ++k) rc = enqueue_iteration(k);
-      if (fused3 && rc == IIFE_OK) IIFE_LAUNCH(k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
-      e = cudaStreamEndCapture(c.stream, &graph);
-      if (rc == IIFE_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
-      if (rc != IIFE_OK || e != cudaSuccess || !exec) {
-        cudaGetLastError();
-        if (graph) cudaGraphDestroy(graph);
-        graph = nullptr;
-        exec = nullptr;
+    CgGraphKey key;
+    memset(&key, 0, sizeof key);
+    const void *ptrs[20] = {A->rowptr, A->colind, A->val, A->sell_ptr, A->sell_cptr, A->sell_col, A->sell_val, dinv, b, x,
+                            r.p, p.p, wv.p, w.sc, w.fl, w.partials, w.counters, w.hist, H ? (const void *)H->dev_seq : nullptr, nullptr};
+    for (int k = 0; k < 20; ++k) key.ptr[k] = ptrs[k];
+    key.n = n;
+    key.slices = A->sell_slices;
+    key.hist_len = (long long)w.hist_len;
+    const int ints[12] = {chunk, g, g_merged, fused3 ? 1 : 0, merged ? 1 : 0, dist ? 1 : 0, p2p ? 1 : 0, A->sell_state,
+                          mat_sell_ready(A) ? 1 : 0, spmv_pick_lpr(A), (dbg_nohalo ? 1 : 0) | (dbg_nored ? 2 : 0), spmv_launch_signature()};
+    for (int k = 0; k < 12; ++k) key.ints[k] = ints[k];
+    memcpy(&key.pr, &pr, sizeof pr);
+    memcpy(&key.rp, &rpush, sizeof rpush);
+    memcpy(&key.hw, &hwait, sizeof hwait);
+    const bool cache_on = env_int("IIFE_KSP_GRAPH_CACHE", 1) != 0;
+    const CgGraphEntry *hit = nullptr;
+    if (cache_on)
+      for (const auto &e : g_cg_graph)
+        if (e.valid && memcmp(&e.key, &key, sizeof key) == 0) hit = &e;
+    if (!hit && ksp_debug()) {  // which part of the key moved since the newest entry
+      const CgGraphEntry &le = g_cg_graph[(g_cg_graph_next + CG_GRAPH_CACHE - 1) % CG_GRAPH_CACHE];
+      if (le.valid) {
+        char line[256];
+        int len = snprintf(line, sizeof line, "[ksp] graph key differs from the newest entry in:");
+        for (int k = 0; k < 20; ++k)
+          if (le.key.ptr[k] != key.ptr[k]) len += snprintf(line + len, sizeof line - len, " ptr%d", k);
+        for (int k = 0; k < 12; ++k)
+          if (le.key.ints[k] != key.ints[k]) len += snprintf(line + len, sizeof line - len, " int%d", k);
+        if (memcmp(&le.key.pr, &key.pr, sizeof key.pr)) len += snprintf(line + len, sizeof line - len, " pr");
+        if (memcmp(&le.key.rp, &key.rp, sizeof key.rp)) len += snprintf(line + len, sizeof line - len, " rp");
+        if (memcmp(&le.key.hw, &key.hw, sizeof key.hw)) len += snprintf(line + len, sizeof line - len, " hw");
+        fprintf(stderr, "%s\n", line);
       }
-    } else {
-      cudaGetLastError();
     }
-    launches_per_chunk = c.launches - before;
-    c.launches = before;  // captured, not launched yet
+    if (hit) {
+      graph_hit = true;
+      exec = hit->exec;
+      launches_per_chunk = hit->launches;
+      exec_cached = true;
+    } else {
+      int64_t before = c.launches;
+      cudaError_t e = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        int rc = IIFE_OK;
+        for (int k = 0; k < chunk && rc == IIFE_OK; ++k) rc = enqueue_iteration(k);
+        if (fused3 && rc == IIFE_OK) IIFE_LAUNCH(k_cg_chunk_end, 1, 1, 0, H->dev_seq, chunk);
+        e = cudaStreamEndCapture(c.stream, &graph);
+        if (rc == IIFE_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+        if (rc != IIFE_OK || e != cudaSuccess || !exec) {
+          cudaGetLastError();
+          if (graph) cudaGraphDestroy(graph);
+          graph = nullptr;
+          exec = nullptr;
+        }
+      } else {
+        cudaGetLastError();
+      }
+      launches_per_chunk = c.launches - before;
+      c.launches = before;  // captured, not launched yet
+      if (exec && cache_on) {  // the cache owns it from here (round-robin replacement)
+        CgGraphEntry &e2 = g_cg_graph[g_cg_graph_next];
+        g_cg_graph_next = (g_cg_graph_next + 1) % CG_GRAPH_CACHE;
+        cg_graph_entry_free(e2);
+        e2.key = key;
+        e2.graph = graph;
+        e2.exec = exec;
+        e2.launches = launches_per_chunk;
+        e2.valid = true;
+        exec_cached = true;
+      }
+    }
   }
-  KSP_DBG("graph capture+inst");
+  KSP_DBG(graph_hit ? "graph: cached chunk" : "graph: capture+inst");
   // Chunks are enqueued two deep: the flag readback of chunk k is awaited while chunk k+1 already
   // runs, so host scheduling jitter between chunks never idles the GPU (after convergence the chunk
   // in flight is a row of no-op kernels).
@@ -1167,8 +1292,10 @@ static int cg_solve(Mat *A, Halo *H, const double *dinv, const double *b, double
   }
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
-  if (exec) cudaGraphExecDestroy(exec);
-  if (graph) cudaGraphDestroy(graph);
+  if (!exec_cached) {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
   return rc;
 }
 
@@ -1511,9 +1638,10 @@ static int ksp_solve_common(Mat *A, Halo *H, int ksp_type, int pc_type, double r
   }
   IIFE_TRY(mat_ensure_sell(A));  // SELL-32 copy of the operator for the iteration (CSR if rejected)
   KspWork w;
-  Tmp<double> sc, partials, dhist, dx, db;
-  Tmp<int> fl;
-  Tmp<unsigned int> counters;
+  g_arena.cursor = 0;  // the arena serves this solve's requests in order
+  Ws<double> sc, partials, dhist, dx, db;
+  Ws<int> fl;
+  Ws<unsigned int> counters;
   IIFE_TRY(sc.alloc(S_COUNT));
   IIFE_TRY(fl.alloc(F_COUNT));
   IIFE_TRY(partials.alloc(4 * MAX_PARTIALS));

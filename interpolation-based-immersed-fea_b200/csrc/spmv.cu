@@ -714,6 +714,11 @@ static int sell_unroll() {
   return u;
 }
 
+int spmv_launch_signature() {
+  const char *fd = getenv("IIFE_SELL_FUSED_DOT");
+  return sell_unroll() | ((fd && atoi(fd) == 0) ? 16 : 0);
+}
+
 static int launch_sell(const Mat *A, bool dot, const double *x, double *y, double *dot_out, double *partials,
                        unsigned int *counter, const int *flag, const P2PRed *red_in = nullptr, const HaloWait *hw_in = nullptr) {
   P2PRed pr{};

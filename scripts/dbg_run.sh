@@ -1,11 +1,11 @@
+N=${1:-2}
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu -x --tb=short 2>&1 | tail -8 > gpurun_out/verify_tests.log; tail -3 gpurun_out/verify_tests.log
-timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/dbg_bench.json 2> gpurun_out/dbg_bench.err
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/dbg_bench.json").read().strip().splitlines()[-1])
-r = d["roofline"]
-print("step", d["ms_per_step"], "spmv ms", r.get("launch_ms"), "frac", r.get("frac"), "cg", r.get("cg_iteration"), "ptap", r.get("ptap_numeric"))
-print("e2e", d["e2e"]["ms_per_step"], d["e2e"].get("fixed_pattern"))
-PY
-timeout 200 python scripts/cg_slope.py 184 2>&1 | tail -1
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 29511"
+timeout 1200 python -m pytest tests -q -m gpu -x --tb=short 2>&1 | tail -3
+for nb in 12 40; do
+  timeout 300 $TR scripts/dist_check.py $nb > gpurun_out/dist_check_w${N}_n${nb}.log 2>&1; echo "rc=$?" >> gpurun_out/dist_check_w${N}_n${nb}.log
+  grep -E "dist_check ok|rc=|Error|error|assert" gpurun_out/dist_check_w${N}_n${nb}.log | tail -4
+done
+IIFE_KSP_DEBUG=1 AB_REPS=1 timeout 600 $TR scripts/dist_cg_ab.py 184 > gpurun_out/dist_cg_ab_w${N}.log 2>&1; echo "ab rc=$?"
+grep -E "^\[w" gpurun_out/dist_cg_ab_w${N}.log | tail -8
+grep -c "graph: cached" gpurun_out/dist_cg_ab_w${N}.log; grep -c "graph: capture" gpurun_out/dist_cg_ab_w${N}.log

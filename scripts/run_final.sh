@@ -1,10 +1,8 @@
 #!/bin/bash
-# final single-GPU numbers: default bench line (e2e + CPU sample), configs 1-4 table, phase table incl. FGMRES, and the
-# CPU reference arm at the headline size (host cores of the GPU box)
+# final single-GPU numbers: default bench line (e2e + CPU sample) and the CPU reference arm at the headline size (host cores
+# of the GPU box); the configs 1-4 table, the phase table and the robustness table come from scripts/capture_profiles.sh
 mkdir -p gpurun_out
 timeout 900 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"
-timeout 300 python scripts/configs_1_4.py > gpurun_out/configs_1_4.md 2> gpurun_out/configs_1_4.err; echo "configs rc=$?"
-timeout 400 python scripts/phase_bench.py 184 > gpurun_out/phase184.log 2>&1; echo "phase rc=$?"
 timeout 900 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/final_reference.json 2> gpurun_out/final_reference.err; echo "reference rc=$?"
 python - <<'PY'
 import json
@@ -18,4 +16,3 @@ try:
 except Exception as e:
     print("reference failed", e, open("gpurun_out/final_reference.err").read()[-500:])
 PY
-tail -8 gpurun_out/configs_1_4.md; cat gpurun_out/phase184.log
