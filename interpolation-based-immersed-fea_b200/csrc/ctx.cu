@@ -1,6 +1,7 @@
 // ctx.cu — process context (one GPU per process), error strings, device allocation accounting and
 // the device-wide exclusive scan used by the symbolic phases.
 #include "common.cuh"
+#include <algorithm>
 #include <map>
 #include <unordered_map>
 
@@ -46,7 +47,11 @@ int dev_alloc(void **p, size_t bytes) {
   *p = nullptr;
   size_t want = round_size(bytes);
   auto it = g_free_blocks.lower_bound(want);
-  if (it != g_free_blocks.end() && it->first <= want + want / 4) {
+  // a cached block may be up to 25 % larger than the request; small requests take up to 4x (at most 8 MB more): the
+  // arrays of a small plan then find their blocks again after a plan of slightly different sizes was freed, instead of
+  // going to cudaMalloc (0.1-1 ms each: the spread of the cold times of configs 1-4)
+  const size_t slack = std::max(want / 4, std::min(want * 3, (size_t)8 << 20));
+  if (it != g_free_blocks.end() && it->first <= want + slack) {
     *p = it->second;
     g_cached_bytes -= (int64_t)it->first;
     g_ctx.dev_bytes += (int64_t)it->first;

@@ -38,9 +38,14 @@ for _m in ("gmres", "cg"):
     api.solveKSP(_wa, _wb, api.Vec(np.zeros(3)), method=_m, monitor=False)
 g0 = dict(np.load(os.path.join(ROOT, "tests", "golden", "full", "cfg3_inputs.npz")))
 _A0, _M0, _b0 = fx.fullsize_case(g0)
-api.assembleLinearSystemBackground(api.CSRMat((_A0.n_rows, _A0.n_cols), _A0.rowptr.astype(np.int32), _A0.colind, _A0.val), api.Vec(_b0),
-                                   api.CSRMat((_M0.n_rows, _M0.n_cols), _M0.rowptr.astype(np.int32), _M0.colind, _M0.val))
-I.plan_cache_clear()
+for _tpl in ("0", None):  # once with templates forced (their kernels are otherwise first used by config 2), once as shipped
+    if _tpl is not None:
+        os.environ["IIFE_TPL_MIN_PROBLEM"] = _tpl
+    else:
+        os.environ.pop("IIFE_TPL_MIN_PROBLEM", None)
+    api.assembleLinearSystemBackground(api.CSRMat((_A0.n_rows, _A0.n_cols), _A0.rowptr.astype(np.int32), _A0.colind, _A0.val), api.Vec(_b0),
+                                       api.CSRMat((_M0.n_rows, _M0.n_cols), _M0.rowptr.astype(np.int32), _M0.colind, _M0.val))
+    I.plan_cache_clear()
 
 rows = []
 for name, method in (("cfg1", "gmres"), ("cfg2", "gmres"), ("cfg3", "gmres"), ("cfg4", "gmres")):

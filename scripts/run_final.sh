@@ -2,6 +2,7 @@
 # final single-GPU numbers: default bench line (e2e + CPU sample) and the CPU reference arm at the headline size (host cores
 # of the GPU box); the configs 1-4 table, the phase table and the robustness table come from scripts/capture_profiles.sh
 mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -q -m gpu --tb=short 2>&1 | tail -6 > gpurun_out/final_tests.log; tail -2 gpurun_out/final_tests.log
 timeout 900 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"
 timeout 900 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/final_reference.json 2> gpurun_out/final_reference.err; echo "reference rc=$?"
 python - <<'PY'

@@ -385,6 +385,48 @@ def test_ksp_zero_rhs_nonzero_guess(iife, oracle, method):
     assert np.linalg.norm(x) <= 1e-6 * np.linalg.norm(x0)
 
 
+def test_cg_repeated_solves_on_device_vectors(iife, oracle):
+    """The captured chunk of CG iterations is kept between solves while the kernels' arguments are unchanged (device
+    vectors in place, same operator, work arrays from the arena): repeated solves, solves with other tolerances and
+    iteration limits (device scalars, not arguments), a value update of the operator in place, another preconditioner
+    and another system of the same size must all give what a fresh solve gives (the oracle)."""
+    import torch
+    from oracle.synthetic_cube import assemble_cube
+
+    A, M, b = assemble_cube(6)
+    C = oracle.AT_R_A(M, A)
+    bb = oracle.AT_x(M, b)
+    dC = dmat(iife, C)
+    b_d = torch.from_numpy(bb).cuda()
+    x_d = torch.zeros_like(b_d)
+
+    def solve(pc, **kw):
+        x_d.zero_()
+        info = iife.ksp_solve(dC, b_d, x_d, iife.KSP_CG, pc, **kw)
+        torch.cuda.synchronize()
+        return info, x_d.cpu().numpy()
+
+    ref = oracle.solve_ksp(C, bb, method="cg", rtol=1e-10, atol=1e-50)
+    for _ in range(3):  # same arguments every time
+        info, x = solve(iife.PC_JACOBI, rtol=1e-10, atol=1e-50)
+        assert info.reason == ref.reason and info.iterations == ref.iterations
+        assert np.linalg.norm(x - ref.x) <= 1e-9 * np.linalg.norm(ref.x)
+    ref5 = oracle.solve_ksp(C, bb, method="cg", rtol=1e-10, atol=1e-50, max_it=5)
+    info, x = solve(iife.PC_JACOBI, rtol=1e-10, atol=1e-50, max_it=5)  # limits live in device scalars
+    assert info.reason == ref5.reason and info.iterations == 5
+    assert np.linalg.norm(x - ref5.x) <= 1e-10 * np.linalg.norm(ref5.x)
+    refn = oracle.solve_ksp(C, bb, method="cg", PC="none", rtol=1e-10, atol=1e-50)
+    info, x = solve(iife.PC_NONE, rtol=1e-10, atol=1e-50)  # another preconditioner: another argument list
+    assert info.reason == refn.reason and abs(info.iterations - refn.iterations) <= 1
+    assert np.linalg.norm(x - refn.x) <= 1e-8 * np.linalg.norm(refn.x)
+    C2 = oracle.CSR(C.n_rows, C.n_cols, C.rowptr, C.colind, C.val * 3.0)  # new values in place, same addresses
+    dC.update_values(C2.val)
+    ref2 = oracle.solve_ksp(C2, bb, method="cg", rtol=1e-10, atol=1e-50)
+    info, x = solve(iife.PC_JACOBI, rtol=1e-10, atol=1e-50)
+    assert info.reason == ref2.reason and abs(info.iterations - ref2.iterations) <= 1
+    assert np.linalg.norm(x - ref2.x) <= 1e-9 * np.linalg.norm(ref2.x)
+
+
 @pytest.mark.parametrize("restart", [30, 7])
 def test_gcr_matches_oracle(iife, oracle, restart):
     """Device GCR (IIFE_KSP_GCR, reference common.py:559-560: method='gcr' -> KSPGCR) against the oracle's restatement:
