@@ -67,11 +67,23 @@ def run(args, I, stream, peak, peak_src, metric, unit, ClockSampler):
     x = torch.zeros(ex.n_owned, dtype=torch.float64, device=dev)
     state = {}
 
-    def step():
+    marks = []  # per timed step: events before numeric / rhs / solve / after (the phases of THIS step, not separate loops)
+
+    def step(record=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        if record:
+            ev[0].record(stream)
         ex.numeric(A_t[2])
+        if record:
+            ev[1].record(stream)
         bb = ex.rhs(b_f)
         x.zero_()
+        if record:
+            ev[2].record(stream)
         state["info"] = ex.solve(bb, x)
+        if record:
+            ev[3].record(stream)
+            marks.append(ev)
         state["bb"] = bb
 
     def barrier():
@@ -88,14 +100,18 @@ def run(args, I, stream, peak, peak_src, metric, unit, ClockSampler):
         barrier()
         e0.record(stream)
         for _ in range(args.steps):
-            step()
+            step(record=True)
         e1.record(stream)
         barrier()
     launches = I.launch_count()
     ms_step = _max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     info = state["info"]
+    t_numeric = _max_over_ranks(sum(ev[0].elapsed_time(ev[1]) for ev in marks) / len(marks), dev)
+    t_rhs = _max_over_ranks(sum(ev[1].elapsed_time(ev[2]) for ev in marks) / len(marks), dev)
+    t_cg = _max_over_ranks(sum(ev[2].elapsed_time(ev[3]) for ev in marks) / len(marks), dev)
+    its_cg = max(info.iterations, 1)
 
-    # ---- per-phase device times (max over ranks): what the scaling curve is made of
+    # ---- per-phase device times (max over ranks) were taken inside the timed steps above; the local SpMV separately
     def timed(fn, reps, warm=1):
         for _ in range(warm):
             fn()
@@ -108,16 +124,7 @@ def run(args, I, stream, peak, peak_src, metric, unit, ClockSampler):
         barrier()
         return _max_over_ranks(a.elapsed_time(b) / reps, dev)
 
-    t_numeric = timed(lambda: ex.numeric(A_t[2]), 3)
-    t_rhs = timed(lambda: ex.rhs(b_f), 10, warm=3)  # torch.distributed point-to-point inside: first calls set up channels
     bb = state["bb"]
-
-    def cg_once():
-        x.zero_()
-        state["info_cg"] = ex.solve(bb, x)
-
-    t_cg = timed(cg_once, 3)
-    its_cg = max(state["info_cg"].iterations, 1)
     # SpMV of the local operator block (roofline of the dominant kernel, per GPU)
     n_loc = ex.n_owned
     n_ext = n_loc + int(ex.ghost_ids.numel())

@@ -159,7 +159,13 @@ def refresh_values(plan: RowFetchPlan, val):
 
 def fetch_entries(plan: RowFetchPlan, vec_local):
     """entries of a row-partitioned VECTOR at the rows of ``plan`` (b_f at J)."""
-    return torch.cat(alltoallv([vec_local[idx] for idx in plan.req_local], recv_counts=plan.recv_row_counts))
+    rank, _ = _world()
+    if getattr(plan, "self_rows_identity", None) is None:  # the rows a rank "requests from itself" are usually all of its rows in order
+        p = plan.req_local[rank]
+        plan.self_rows_identity = bool(p.numel() == vec_local.numel() and (p.numel() == 0 or (
+            int(p[0]) == 0 and int(p[-1]) == p.numel() - 1 and bool((p[1:] > p[:-1]).all()))))
+    send = [vec_local if (q == rank and plan.self_rows_identity) else vec_local[idx] for q, idx in enumerate(plan.req_local)]
+    return torch.cat(alltoallv(send, recv_counts=plan.recv_row_counts))
 
 
 # --------------------------------------------------------------------------------------------------
