@@ -144,7 +144,7 @@ bool mat_sell_ready(const Mat *A);
 int spmv_pick_lpr(const Mat *A);
 // SELL-32 operator copy: builds it on first use (returns IIFE_OK with A->sell_state == -1 if the
 // padding would exceed 1.25x nnz, in which case callers stay on CSR) and refreshes values.
-int mat_ensure_sell(Mat *A);
+int mat_ensure_sell(Mat *A, bool want_dinv = false);  // want_dinv: the fill pass also writes A->dinv (PCJACOBI)
 int mat_ensure_sell_order(Mat *A, int64_t n_owned);
 int spmv_launch_signature();       // everything env-selected that shapes the SpMV launches (key of cached graphs)
 void ksp_release_cached_graphs();  // ksp.cu: captured CG chunks kept between solves

@@ -1632,11 +1632,12 @@ static int ksp_solve_common(Mat *A, Halo *H, int ksp_type, int pc_type, double r
   if (dtol <= 0.0) dtol = 1e4;
   const int64_t n = A->n_rows;
   const double *dinv = nullptr;
+  // SELL-32 copy of the operator for the iteration (CSR if rejected); its fill pass also yields the Jacobi diagonal
+  IIFE_TRY(mat_ensure_sell(A, pc_type == IIFE_PC_JACOBI));
   if (pc_type == IIFE_PC_JACOBI) {
-    IIFE_TRY(mat_ensure_dinv(A));
+    IIFE_TRY(mat_ensure_dinv(A));  // no-op when the fill pass wrote it
     dinv = A->dinv;
   }
-  IIFE_TRY(mat_ensure_sell(A));  // SELL-32 copy of the operator for the iteration (CSR if rejected)
   KspWork w;
   g_arena.cursor = 0;  // the arena serves this solve's requests in order
   Ws<double> sc, partials, dhist, dx, db;
