@@ -50,12 +50,16 @@ def _world():
     return (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
 
 
-def alltoallv(send, group=None, recv_counts=None):
+def alltoallv(send, group=None, recv_counts=None, recv_out=None):
     """send[q] = 1-D tensor for rank q (all same dtype/device).  Returns the list received from each rank.
     Counts travel with all_gather (skipped when the caller knows ``recv_counts`` from a stored plan: no host
-    synchronisation then), payloads with batched isend/irecv (works with NCCL and gloo)."""
+    synchronisation then), payloads with batched isend/irecv (works with NCCL and gloo).  ``recv_out``: preallocated
+    tensors to receive into (the own block is copied into recv_out[rank])."""
     rank, world = _world()
     if world == 1:
+        if recv_out is not None:
+            recv_out[0].copy_(send[0])
+            return recv_out
         return [send[0]]
     dev, dtype = send[0].device, send[0].dtype
     if recv_counts is None:
@@ -63,8 +67,12 @@ def alltoallv(send, group=None, recv_counts=None):
         gathered = [torch.empty_like(counts) for _ in range(world)]
         dist.all_gather(gathered, counts, group=group)
         recv_counts = [int(gathered[q][rank].item()) for q in range(world)]
-    recv = [torch.empty(int(recv_counts[q]), dtype=dtype, device=dev) for q in range(world)]
-    recv[rank] = send[rank]
+    if recv_out is not None:
+        recv = recv_out
+        recv[rank].copy_(send[rank])
+    else:
+        recv = [torch.empty(int(recv_counts[q]), dtype=dtype, device=dev) for q in range(world)]
+        recv[rank] = send[rank]
     ops = []
     for q in range(world):
         if q == rank:
@@ -145,7 +153,7 @@ def fetch_rows(rowptr, colind, val, row_start, part_t, wanted):
     return plan, rowptr_w, col_w, val_w
 
 
-def refresh_values(plan: RowFetchPlan, val):
+def refresh_values(plan: RowFetchPlan, val, out=None):
     """values of the fetched rows for new local values ``val`` (same pattern).  The block a rank "sends
     to itself" is usually ALL of its rows in order: then it is passed through without a gather."""
     rank, _ = _world()
@@ -154,6 +162,12 @@ def refresh_values(plan: RowFetchPlan, val):
         plan.self_identity = bool(p.numel() == val.numel() and (p.numel() == 0 or (int(p[0]) == 0 and int(p[-1]) == p.numel() - 1
                                                                                    and bool((p[1:] > p[:-1]).all()))))
     send = [val if (q == rank and plan.self_identity) else val[p] for q, p in enumerate(plan.gather_pos)]
+    if out is not None:  # straight into the operand's value array: no concatenation, no second copy
+        offs = [0]
+        for cnt in plan.recv_entry_counts:
+            offs.append(offs[-1] + int(cnt))
+        alltoallv(send, recv_counts=plan.recv_entry_counts, recv_out=[out[offs[q]:offs[q + 1]] for q in range(len(offs) - 1)])
+        return out
     return torch.cat(alltoallv(send, recv_counts=plan.recv_entry_counts))
 
 
@@ -287,6 +301,22 @@ def _mat_from_tensors(core, shape, rp, ci, v, unsorted_ok=False):
     return core.DeviceMat(h.value)
 
 
+class _RawCudaArray:
+    """Minimal __cuda_array_interface__ carrier: lets torch wrap memory the library owns without copying."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def _device_view_f64(ptr, n):
+    if not ptr or n <= 0:
+        return None
+    try:
+        return torch.as_tensor(_RawCudaArray(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
+    except Exception:  # fall back to the copying path
+        return None
+
+
 class DistExtraction:
     """Row-partitioned A_b = M^T A_f M, b_b = M^T b_f and Jacobi-CG on the GPUs of one box."""
 
@@ -308,6 +338,8 @@ class DistExtraction:
         self.C_op = None       # same values, local [owned | ghost] column ids (KSP operator)
         self.halo = None
         self.n_owned = T.R[0]
+        # torch view of the value array of the local A operand (None if the view cannot be made: values are copied then)
+        self._A_val_view = _device_view_f64(self.A.device_ptrs()[2], self.A.nnz) if os.environ.get("IIFE_DIST_DIRECT", "1") != "0" else None
         # the pattern of this rank's rows of A_f as handed over (numeric_csr checks a fresh matrix against it)
         self._A_pattern = (A_loc[0].to(torch.int32, copy=True), A_loc[1].to(torch.int32, copy=True))
 
@@ -323,8 +355,11 @@ class DistExtraction:
 
     def numeric(self, A_val_local):
         """New foreground values (same pattern): exchange ghost-row values, run the numeric phase."""
-        vals = refresh_values(self.T.planA, A_val_local)
-        self.A.update_values(vals)
+        if self._A_val_view is not None:  # the fetched values land in the operand's own array (same entry order)
+            refresh_values(self.T.planA, A_val_local, out=self._A_val_view)
+            check(lib.iife_mat_touch(self.A.handle))
+        else:
+            self.A.update_values(refresh_values(self.T.planA, A_val_local))
         h = ctypes.c_void_p(self.C.handle.value if self.C is not None else 0)
         check(lib.iife_rap_numeric(self.plan, self.R.handle, self.A.handle, self.P.handle, ctypes.byref(h)))
         if self.C is None:
