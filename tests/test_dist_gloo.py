@@ -83,6 +83,10 @@ def _worker(rank, world, port, n_cells, out_dir):
         C2 = O.AT_R_A(M, A2)
         Cl2 = O.matmult(O.matmult(R, O.CSR(Al.n_rows, Al.n_cols, Al.rowptr, Al.colind, v2)), Pl)
         assert np.array_equal(Cl2.val, C2.val[g])
+        # the same refresh received straight into a preallocated array (what DistExtraction.numeric does on the device)
+        out = torch.full((v2.size,), np.nan, dtype=torch.float64)
+        idist.refresh_values(T.planA, torch.from_numpy(A2v[A.rowptr[f0]:A.rowptr[f1]].copy()), out=out)
+        assert np.array_equal(out.numpy(), v2)
         # b_b = M^T b_f through the gathered entries of b_f
         bJ = idist.fetch_entries(T.planA, torch.from_numpy(b[f0:f1].copy())).numpy()
         assert np.array_equal(bJ, b[Jn])
